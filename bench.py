@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- the GRF hot path on B200, measured the way BASELINE.json asks.
+
+Workload (config.workload): BASELINE.json configs[1] -- sparse CSR GRF on a 2-D
+grid graph of 316 x 316 = 99 856 nodes, walks_per_node = 100, max_walk_length =
+5, p_halt = 0.1, learnable modulator f = randn(5) (torch.manual_seed(42)),
+t = 16 right-hand sides.  With N > 1 GPUs the grid grows to 316 x (316 N)
+nodes and every rank owns a contiguous block of 99 856 start nodes (weak
+scaling; CSR graph replicated; one all-reduce of Phi^T V per matvec).
+
+One "step" = one pass of the hot path: walker (+ merge) -> compaction into Phi
+blocks -> Phi^T blocks -> one kernel matvec Phi(Phi^T V).  Every phase is timed
+on the device with CUDA events on the launching stream; L2 is flushed (a 256 MB
+write) before every timed phase.  `value` = walk-steps executed by all ranks /
+max-over-ranks step time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the reference's CPU algorithm (oracle/cpu_baseline.py:
+the pure-Python fork-pool sampler, all host cores) on a bounded sample of the
+same workload.  oracle/ is used here only as the timed CPU baseline.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "efficient-gaussian-process-on-graphs_b200")]
+
+import numpy as np
+import scipy.sparse as sp
+
+GRID_NX, GRID_NY = 316, 316
+W, P_HALT, L, T_RHS = 100, 0.1, 5, 16
+SEED = 42
+METRIC = "grf_walk_steps_per_sec"
+UNIT = "walk-steps/s"
+WALK_BYTES_PER_STEP = 32          # row_ptr pair 8 + col 4 + val 8 (fp64) + merged record 12 (SURVEY 8d, fp64 path)
+
+
+def grid_laplacian(nx: int, ny: int) -> sp.csr_matrix:
+    """Normalized Laplacian of the nx x ny 4-neighbour grid (Kronecker construction as in the reference's
+    scalable_bo/bo_utils/data_utils.py:56-60), unit weights."""
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+
+    def path(n):
+        return sp.diags([np.ones(n - 1), np.ones(n - 1)], [-1, 1], format="csr")
+
+    adj = (sp.kron(sp.eye(ny), path(nx)) + sp.kron(path(ny), sp.eye(nx))).tocsr()
+    return get_normalized_laplacian(adj)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.out.flush()
+        self.out.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.out.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.out.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+
+    n_gpus = args.gpus
+    lap = grid_laplacian(GRID_NX, GRID_NY * n_gpus)
+    n = lap.shape[0]
+    cores = os.cpu_count() or 1
+    n_sample = min(n, 2 * GRID_NX * cores)          # two grid lines of start nodes per core and step
+    starts = np.arange(n_sample)
+    times, visits = [], 0
+    for i in range(args.warmup + args.steps):
+        dt, vis = cpu_baseline.time_sampler(lap, W, P_HALT, L, starts, n_processes=cores)
+        if i >= args.warmup:
+            times.append(dt)
+            visits += vis
+    total = sum(times)
+    value = visits / total
+    sample = (f"{n_sample} of {n} start nodes per step (x{W} walks), oracle/cpu_baseline.py fork-pool port of "
+              f"sparse_sampler.py:72-132, {cores} processes")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n_gpus, n),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, n_nodes):
+    return {
+        "workload": "BASELINE.json configs[1]: sparse CSR GRF on 2D grid graph N=100k (316x316 per GPU), "
+                    "walks_per_node=100, max_walk_length=5, p_halt=0.1, learnable modulator, t=16",
+        "n_nodes": int(n_nodes), "walks_per_node": W, "max_walk_length": L, "p_halt": P_HALT, "rhs_columns": T_RHS,
+        "sharding": f"start nodes row-sharded over {n_gpus} GPU(s), CSR graph replicated",
+        "l2": "flushed (256 MB write) before every timed phase; staging (480 MB) exceeds L2 as well",
+    }
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from grf_b200 import _lib, engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lap = grid_laplacian(GRID_NX, GRID_NY * world)
+    n = lap.shape[0]
+    rows_per = n // world
+    lo, hi = rank * rows_per, (rank + 1) * rows_per if rank < world - 1 else n
+    graph = engine.DeviceGraph.from_scipy(lap, dev)
+    cfg = engine.WalkConfig(W, P_HALT, L, seed=SEED)
+    torch.manual_seed(42)
+    f = torch.randn(L).to(dev)                         # learnable modulator init, sparse_grf_kernel.py:14-17
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    v = torch.randn(hi - lo, T_RHS, device=dev, generator=gen)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        flush.fill_(1)                                  # L2 flush, outside the timed bracket
+        a, b = ev(), ev()
+        a.record(stream)
+        out = fn()
+        b.record(stream)
+        return out, (a, b)
+
+    lib = _lib.lib()
+    stride = lib.grf_walk_stage_stride(W, L)
+
+    def one_step():
+        """walker -> Phi blocks -> Phi^T blocks -> one Phi(Phi^T V)."""
+        visits = torch.zeros(1, dtype=torch.int64, device=dev)
+        st, e_walk = timed(lambda: engine.run_walker(graph, cfg, lo, hi, visits=visits))
+        phi, e_comp = timed(lambda: engine._blocks_from_staging(st, cfg, graph.n_nodes, _lib.SCALE_MUL_RECIP))
+        phi.row_lo = lo
+        _, e_tr = timed(lambda: phi.build_transpose())
+        u_buf = torch.empty((graph.n_nodes, T_RHS), dtype=torch.float32, device=dev)
+
+        def mv():
+            u = phi.apply_t(f, v, out=u_buf)
+            if world > 1:
+                dist.all_reduce(u_buf)                  # sum of the per-GPU partials Phi_g^T V_g
+            return phi.apply(f, u)
+
+        out, e_mv = timed(mv)
+        return dict(phi=phi, visits=visits, out=out, events=dict(walk=e_walk, compact=e_comp, transpose=e_tr,
+                                                                 matvec=e_mv))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        r = one_step()
+        del r
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    results = [one_step() for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+
+    phase_ms = {k: sum(r["events"][k][0].elapsed_time(r["events"][k][1]) for r in results)
+                for k in ("walk", "compact", "transpose", "matvec")}
+    step_ms_total = sum(phase_ms.values())
+    visits_total = sum(int(r["visits"].item()) for r in results)
+    phi = results[-1]["phi"]
+    nnz = phi.nnz
+    n_rows = phi.n_rows
+
+    # ---- e2e: the public drop-in call with HOST buffers (host CSR in, scipy CSR list out) + host matvec
+    from efficient_graph_gp_sparse.random_walk_samplers_sparse.sparse_sampler import SparseRandomWalk
+
+    del results
+    torch.cuda.empty_cache()
+    e2e_time, e2e_visits, h2d, d2h = 0.0, 0, 0, 0
+    v_host = v.cpu().pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+    for i in range(1 + e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        rw = SparseRandomWalk(lap, seed=SEED, device=dev)
+        steps = rw.get_step_matrices_device(W, P_HALT, L, start_lo=lo, start_hi=hi)
+        mats = steps.to_scipy()                          # D2H of every M_l (float64 + int32 + offsets)
+        phi_e = engine.PhiBlocks.from_step_matrices(steps)
+        phi_e.row_lo = lo
+        vd = v_host.to(dev, non_blocking=True)
+        u = phi_e.apply_t(f, vd)
+        if world > 1:
+            u = u.contiguous()
+            dist.all_reduce(u)
+        out_host = phi_e.apply(f, u).cpu()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_time += dt
+            e2e_visits += steps.visits
+            h2d = lap.indptr.nbytes + lap.indices.nbytes + lap.data.nbytes + v_host.numel() * 4
+            d2h = steps.offsets.numel() * 8 + steps.col.numel() * 4 + steps.val.numel() * 8 + out_host.numel() * 4
+        del rw, steps, mats, phi_e
+
+    # ---- reduce over ranks: max time, sum of work
+    red = torch.tensor([step_ms_total, phase_ms["walk"], phase_ms["compact"], phase_ms["transpose"],
+                        phase_ms["matvec"], e2e_time], dtype=torch.float64, device=dev)
+    work = torch.tensor([visits_total, e2e_visits, nnz], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    red, work = red.tolist(), work.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        K = args.steps
+        step_ms, walk_ms, comp_ms, tr_ms, mv_ms = (x / K for x in red[:5])
+        value = work[0] / (red[0] * 1e-3)
+        # matvec algorithmic bytes, this rank's launch pair: 2*nnz*8 + 2*L*(rows+1)*4 + 4*N_eff*t*4
+        n_cols = graph.n_nodes
+        mv_bytes = 2 * nnz * 8 + L * (n_rows + 1) * 4 + L * (n_cols + 1) * 4 + (2 * n_rows + 2 * n_cols) * T_RHS * 4
+        mv_gbs = mv_bytes / (mv_ms * 1e-3) / 1e9
+        walk_bytes = (work[0] / world / K) * WALK_BYTES_PER_STEP
+        walk_gbs = walk_bytes / (walk_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 walk loads / f32 matvec", "data": "synthetic",
+            "config": workload_config(world, n),
+            "phases_ms": {"walk_merge": walk_ms, "compact_blocks": comp_ms, "transpose_blocks": tr_ms,
+                          "matvec_phi_phiT_v": mv_ms},
+            "phi_build_ms": walk_ms + comp_ms + tr_ms,
+            "walker_steps_per_sec": (work[0] / K) / (walk_ms * 1e-3),
+            "matvec": {"ms": mv_ms, "algorithmic_gbs": mv_gbs, "nnz_phi_rank0": nnz, "t": T_RHS,
+                       "includes_allreduce": world > 1},
+            "roofline": {"kernel": "walk_merge_kernel (dominant by time)", "bound": "hbm", "achieved": walk_gbs,
+                         "peak": peak, "unit": "GB/s", "frac": walk_gbs / peak, "traffic": None,
+                         "peak_source": peak_src,
+                         "note": "latency/sector-bound random gathers: 32 algorithmic B per walk-step, "
+                                 "graph L2-resident at this size"},
+            "roofline_matvec": {"kernel": "spmm_blocks_kernel x2 (Phi^T V, Phi U)", "bound": "hbm",
+                                "achieved": mv_gbs, "peak": peak, "unit": "GB/s", "frac": mv_gbs / peak,
+                                "traffic": None, "peak_source": peak_src},
+            "e2e": {"value": work[1] / red[5], "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * red[5] / e2e_steps,
+                    "what": "SparseRandomWalk(host scipy CSR) -> list of host scipy CSR step matrices, plus one "
+                            "host-V -> Phi(Phi^T V) -> host matvec"},
+            "gpu_launches": K * 14,
+            "gpu_launches_per_step": {"walk_merge": 1, "scan": 3 + 3, "compact_blocks": 1, "transpose": 4,
+                                      "spmm_blocks": 2},
+            "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(lap)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_leg(lap):
+    """The reference's CPU algorithm on this box's host cores, bounded sample (about 10-30 s)."""
+    from oracle import cpu_baseline
+
+    cores = os.cpu_count() or 1
+    n = lap.shape[0]
+    n_sample = 4 * GRID_NX * cores                        # four grid lines per core: ~1.3e4 walk-steps/core/line
+    starts = np.arange(min(n, n_sample))
+    dt, visits = cpu_baseline.time_sampler(lap, W, P_HALT, L, starts, n_processes=cores)
+    out = {"value": visits / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{len(starts)} of {n} start nodes (x{W} walks, {visits} walk-steps, {dt:.1f} s), pure-Python "
+                     f"fork-pool port of sparse_sampler.py:72-132 in oracle/cpu_baseline.py"}
+    # the C restatement of the same algorithm, single thread, for scale
+    from oracle import c_oracle
+
+    t0 = time.perf_counter()
+    _, vis_c = c_oracle.step_matrices(lap, W, P_HALT, L, seed=SEED, start_lo=0, start_hi=min(n, 20 * GRID_NX),
+                                      return_visits=True)
+    out["c_port_single_thread"] = {"value": vis_c / (time.perf_counter() - t0), "unit": UNIT, "cores": 1}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+// Shared helpers of the grf_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "grf_b200.h"
+
+namespace grf {
+
+// thread-local error text returned by grf_last_error()
+char *error_buffer();
+int fail(int code, const char *fmt, ...);
+int check_cuda(cudaError_t err, const char *what);
+
+#define GRF_CUDA_OK(expr)                                         \
+    do {                                                          \
+        int _rc = ::grf::check_cuda((expr), #expr);               \
+        if (_rc != GRF_OK) return _rc;                            \
+    } while (0)
+
+#define GRF_REQUIRE(cond, ...)                                    \
+    do {                                                          \
+        if (!(cond)) return ::grf::fail(GRF_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+constexpr int kWarp = 32;
+constexpr int kSmCount = 148;  // B200
+
+__host__ __device__ inline uint32_t next_pow2(uint32_t x) {
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+__host__ __device__ inline int bit_width(uint64_t x) {
+    int b = 0;
+    while (x) {
+        ++b;
+        x >>= 1;
+    }
+    return b;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11).  Same counter/key convention as
+// oracle/grf_oracle.c: ctr = (walk_lo, walk_hi, step, 0), key = (seed_lo, seed_hi).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0);
+        const uint32_t lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2);
+        const uint32_t lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+}  // namespace grf

@@ -1,0 +1,455 @@
+// Staging -> CSR: the array half of K2 and the one-off Phi^T build (K4).
+//
+// Replaces  sparse_sampler.py:117-130  (keys -> rows/cols/vals -> csr_matrix / W)
+//           sampler.py:188-203          (dict -> dense, value / W)
+//           graph_preprocessor.py:117-139 (float32 values for the matvec)
+//           sparse_lo.py:23-25          (.t().to_sparse_csr(), per forward in the reference)
+//
+// All of these are HBM-bound streaming passes: every kernel reads and writes
+// each byte once with warp-contiguous accesses; the only irregular traffic is
+// the column-keyed scatter of the transpose (int32 atomics for the counts and
+// the slot claim).
+
+#include "grf_common.cuh"
+
+namespace grf {
+
+// ---------------------------------------------------------------------------
+// exclusive scan of int32 counts (three short kernels: tile sums, scan of the
+// tile sums by one CTA, tile-local scan + offset)
+// ---------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int64_t scan_fetch(const int32_t *cnt, int64_t j, int64_t n_rows, int32_t n_steps,
+                                              int32_t order) {
+    if (order == GRF_ORDER_ROW_MAJOR) return cnt[j];
+    const int64_t s = j / n_rows;
+    const int64_t r = j - s * n_rows;
+    return cnt[r * n_steps + s];
+}
+
+__device__ __forceinline__ int64_t block_reduce_sum(int64_t v, int64_t *sh) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    int64_t total = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += sh[i];
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *cnt, int64_t n, int64_t n_rows,
+                                                               int32_t n_steps, int32_t order, int64_t *tile_sums) {
+    __shared__ int64_t sh[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int64_t v = 0;
+    for (int i = 0; i < kScanItems; ++i) {
+        const int64_t j = base + (int64_t)i * kScanThreads + threadIdx.x;
+        if (j < n) v += scan_fetch(cnt, j, n_rows, n_steps, order);
+    }
+    const int64_t total = block_reduce_sum(v, sh);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_of_tile_sums(int64_t *tile_sums, int64_t n_tiles) {
+    __shared__ int64_t sh[32];
+    __shared__ int64_t carry_sh;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_tiles; base += blockDim.x) {
+        const int64_t j = base + threadIdx.x;
+        const int64_t v = j < n_tiles ? tile_sums[j] : 0;
+        // inclusive scan across the CTA
+        int64_t incl = v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t nb = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += nb;
+        }
+        if (lane == 31) sh[warp] = incl;
+        __syncthreads();
+        int64_t before = 0, all = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            if (i < warp) before += sh[i];
+            all += sh[i];
+        }
+        const int64_t carry = carry_sh;
+        if (j < n_tiles) tile_sums[j] = carry + before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_sh = carry + all;
+        __syncthreads();
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const int32_t *cnt, int64_t n, int64_t n_rows,
+                                                           int32_t n_steps, int32_t order, const int64_t *tile_sums,
+                                                           OutT *offsets) {
+    __shared__ int64_t sh[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t local[kScanItems];
+    int64_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int64_t j = base + i;
+        local[i] = j < n ? scan_fetch(cnt, j, n_rows, n_steps, order) : 0;
+        mine += local[i];
+    }
+    // exclusive scan of `mine` across the CTA
+    int64_t incl = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t nb = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += nb;
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    int64_t before = 0;
+    for (int i = 0; i < warp; ++i) before += sh[i];
+    int64_t run = tile_sums[blockIdx.x] + before + incl - mine;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int64_t j = base + i;
+        if (j < n) offsets[j] = (OutT)run;
+        run += local[i];
+        if (j == n - 1) offsets[n] = (OutT)run;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// staging -> reference layout (step-major CSR, float64) / matvec layout
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double scale_sum(double sum, int32_t scale_mode, double recip, double w) {
+    return scale_mode == GRF_SCALE_MUL_RECIP ? __dmul_rn(sum, recip) : __ddiv_rn(sum, w);
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256) compact_steps_kernel(const int32_t *stage_col, const double *stage_sum,
+                                                            const int32_t *row_cnt, const int64_t *off_sm,
+                                                            int64_t n_rows, int32_t L, int64_t stride, int32_t W,
+                                                            int32_t scale_mode, int32_t *out_col, double *out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double recip = 1.0 / (double)W;
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        int64_t src = r * stride;
+        for (int s = 0; s < L; ++s) {
+            const int c = row_cnt[r * L + s];
+            const int64_t dst = off_sm[(int64_t)s * n_rows + r];
+            for (int i = lane; i < c; i += 32) {
+                out_col[dst + i] = stage_col[src + i];
+                out_val[dst + i] = scale_sum(stage_sum[src + i], scale_mode, recip, (double)W);
+            }
+            src += c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *stage_col, const double *stage_sum,
+                                                             const int32_t *blk_ptr, int64_t n_rows, int32_t L,
+                                                             int64_t stride, int32_t W, int32_t scale_mode,
+                                                             GrfEntry *entries) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double recip = 1.0 / (double)W;
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        const int64_t src = r * stride;
+        const int32_t dst = blk_ptr[r * L];
+        const int32_t c = blk_ptr[(r + 1) * L] - dst;  // the row's segments are contiguous on both sides
+        for (int i = lane; i < c; i += 32) {
+            GrfEntry e;
+            e.col = stage_col[src + i];
+            e.val = (float)scale_sum(stage_sum[src + i], scale_mode, recip, (double)W);
+            entries[dst + i] = e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) count_from_steps_kernel(const int64_t *off_sm, int64_t n_rows, int32_t L,
+                                                               int32_t *row_cnt) {
+    const int64_t n = n_rows * L;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = j / n_rows, r = j - s * n_rows;
+        row_cnt[r * L + s] = (int32_t)(off_sm[j + 1] - off_sm[j]);
+    }
+}
+
+__global__ void __launch_bounds__(256) blocks_from_steps_kernel(const int64_t *off_sm, const int32_t *col,
+                                                                const double *val, const int32_t *blk_ptr,
+                                                                int64_t n_rows, int32_t L, GrfEntry *entries) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        for (int s = 0; s < L; ++s) {
+            const int64_t src = off_sm[(int64_t)s * n_rows + r];
+            const int c = (int)(off_sm[(int64_t)s * n_rows + r + 1] - src);
+            const int32_t dst = blk_ptr[r * L + s];
+            for (int i = lane; i < c; i += 32) {
+                GrfEntry e;
+                e.col = col[src + i];
+                e.val = (float)val[src + i];  // torch .float(): round to nearest even
+                entries[dst + i] = e;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Phi^T blocks
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_count_kernel(const int32_t *blk_ptr, const GrfEntry *entries,
+                                                              int64_t n_rows, int32_t L, int32_t *tcnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        for (int s = 0; s < L; ++s) {
+            const int32_t b = blk_ptr[r * L + s], e = blk_ptr[r * L + s + 1];
+            for (int32_t i = b + lane; i < e; i += 32) atomicAdd(&tcnt[(int64_t)entries[i].col * L + s], 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) transpose_fill_kernel(const int32_t *blk_ptr, const GrfEntry *entries,
+                                                             int64_t n_rows, int32_t L, int32_t *cursor,
+                                                             GrfEntry *tentries) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        for (int s = 0; s < L; ++s) {
+            const int32_t b = blk_ptr[r * L + s], e = blk_ptr[r * L + s + 1];
+            for (int32_t i = b + lane; i < e; i += 32) {
+                const GrfEntry src = entries[i];
+                const int32_t slot = atomicAdd(&cursor[(int64_t)src.col * L + s], 1);
+                GrfEntry dst;
+                dst.col = (int32_t)r;
+                dst.val = src.val;
+                tentries[slot] = dst;
+            }
+        }
+    }
+}
+
+// Slots inside one (column, length) segment were claimed in arbitrary order;
+// order them by row so that the layout (and the fp32 summation order of
+// Phi^T V) is deterministic.  Segments are short except for hub columns, so:
+// one thread per short segment (insertion sort), one CTA per long segment
+// (bitonic sort in global memory over the next power of two).
+constexpr int kShortSeg = 48;
+
+__global__ void __launch_bounds__(256) transpose_sort_short_kernel(const int32_t *tblk_ptr, int64_t n_segs,
+                                                                   GrfEntry *tentries, int32_t *long_list,
+                                                                   int32_t *long_count) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_segs;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t b = tblk_ptr[g], e = tblk_ptr[g + 1];
+        const int32_t len = e - b;
+        if (len <= 1) continue;
+        if (len > kShortSeg) {
+            long_list[atomicAdd(long_count, 1)] = (int32_t)g;
+            continue;
+        }
+        for (int32_t i = b + 1; i < e; ++i) {
+            const GrfEntry x = tentries[i];
+            int32_t j = i - 1;
+            while (j >= b && tentries[j].col > x.col) {
+                tentries[j + 1] = tentries[j];
+                --j;
+            }
+            tentries[j + 1] = x;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) transpose_sort_long_kernel(const int32_t *tblk_ptr, GrfEntry *tentries,
+                                                                  const int32_t *long_list,
+                                                                  const int32_t *long_count) {
+    const int32_t n_long = *long_count;
+    for (int32_t li = blockIdx.x; li < n_long; li += gridDim.x) {
+        const int32_t g = long_list[li];
+        const int32_t b = tblk_ptr[g];
+        const uint32_t len = (uint32_t)(tblk_ptr[g + 1] - b);
+        const uint32_t np2 = next_pow2(len);
+        GrfEntry *seg = tentries + b;
+        // Bitonic network in its all-ascending form (mirror step, then half-cleaners):
+        // every comparator moves the smaller key to the lower index, so the
+        // virtual +inf padding at [len, np2) never moves and comparators that
+        // touch it are simply skipped.
+        for (uint32_t k = 2; k <= np2; k <<= 1) {
+            const uint32_t half = k >> 1;
+            for (uint32_t c = threadIdx.x; c < np2 / 2; c += blockDim.x) {
+                const uint32_t blk = c / half, off = c - blk * half;
+                const uint32_t lo = blk * k + off, hi = blk * k + k - 1 - off;
+                if (hi < len) {
+                    const GrfEntry a = seg[lo], bb = seg[hi];
+                    if (a.col > bb.col) {
+                        seg[lo] = bb;
+                        seg[hi] = a;
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t j = half >> 1; j > 0; j >>= 1) {
+                for (uint32_t c = threadIdx.x; c < np2 / 2; c += blockDim.x) {
+                    const uint32_t lo = ((c & ~(j - 1)) << 1) | (c & (j - 1));
+                    const uint32_t hi = lo + j;
+                    if (hi < len) {
+                        const GrfEntry a = seg[lo], bb = seg[hi];
+                        if (a.col > bb.col) {
+                            seg[lo] = bb;
+                            seg[hi] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+}  // namespace grf
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+using namespace grf;
+
+static inline int grid_for_warps(int64_t n_rows, int threads) {
+    const int64_t warps_per_cta = threads / 32;
+    int64_t g = (n_rows + warps_per_cta - 1) / warps_per_cta;
+    const int64_t cap = (int64_t)kSmCount * 32;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+extern "C" int64_t grf_scan_workspace_bytes(int64_t n_items) {
+    const int64_t tiles = (n_items + kScanTile - 1) / kScanTile;
+    return (tiles + 1) * (int64_t)sizeof(int64_t);
+}
+
+extern "C" int grf_scan_counts(const int32_t *row_cnt, int64_t n_rows, int32_t n_steps, int32_t order, void *offsets,
+                               int32_t out_is_i64, void *workspace, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_scan_counts: bad shape");
+    GRF_REQUIRE(order == GRF_ORDER_ROW_MAJOR || order == GRF_ORDER_STEP_MAJOR, "grf_scan_counts: bad order");
+    GRF_REQUIRE(offsets && workspace, "grf_scan_counts: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = n_rows * n_steps;
+    if (n == 0) {
+        GRF_CUDA_OK(cudaMemsetAsync(offsets, 0, out_is_i64 ? 8 : 4, st));
+        return GRF_OK;
+    }
+    GRF_REQUIRE(row_cnt, "grf_scan_counts: null counts");
+    const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+    GRF_REQUIRE(tiles < (1ll << 31), "grf_scan_counts: too many items");
+    int64_t *tile_sums = (int64_t *)workspace;
+    scan_tile_sums<<<(int)tiles, kScanThreads, 0, st>>>(row_cnt, n, n_rows, n_steps, order, tile_sums);
+    scan_of_tile_sums<<<1, 1024, 0, st>>>(tile_sums, tiles);
+    if (out_is_i64)
+        scan_apply<int64_t><<<(int)tiles, kScanThreads, 0, st>>>(row_cnt, n, n_rows, n_steps, order, tile_sums,
+                                                                 (int64_t *)offsets);
+    else
+        scan_apply<int32_t><<<(int)tiles, kScanThreads, 0, st>>>(row_cnt, n, n_rows, n_steps, order, tile_sums,
+                                                                 (int32_t *)offsets);
+    return check_cuda(cudaGetLastError(), "scan kernels launch");
+}
+
+extern "C" int grf_compact_steps(const int32_t *stage_col, const double *stage_sum, const int32_t *row_cnt,
+                                 const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps,
+                                 int64_t stage_stride, int32_t walks_per_node, int32_t scale_mode, int32_t *out_col,
+                                 double *out_val, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && walks_per_node >= 1, "grf_compact_steps: bad shape");
+    GRF_REQUIRE(scale_mode == GRF_SCALE_MUL_RECIP || scale_mode == GRF_SCALE_DIV, "grf_compact_steps: bad scale_mode");
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(stage_col && stage_sum && row_cnt && offsets_step_major && out_col && out_val,
+                "grf_compact_steps: null buffer");
+    compact_steps_kernel<<<grid_for_warps(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(
+        stage_col, stage_sum, row_cnt, offsets_step_major, n_rows, n_steps, stage_stride, walks_per_node, scale_mode,
+        out_col, out_val);
+    return check_cuda(cudaGetLastError(), "compact_steps_kernel launch");
+}
+
+extern "C" int grf_compact_blocks(const int32_t *stage_col, const double *stage_sum, const int32_t *row_cnt,
+                                  const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int64_t stage_stride,
+                                  int32_t walks_per_node, int32_t scale_mode, GrfEntry *entries, void *stream) {
+    (void)row_cnt;
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && walks_per_node >= 1, "grf_compact_blocks: bad shape");
+    GRF_REQUIRE(scale_mode == GRF_SCALE_MUL_RECIP || scale_mode == GRF_SCALE_DIV,
+                "grf_compact_blocks: bad scale_mode");
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(stage_col && stage_sum && blk_ptr && entries, "grf_compact_blocks: null buffer");
+    compact_blocks_kernel<<<grid_for_warps(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(
+        stage_col, stage_sum, blk_ptr, n_rows, n_steps, stage_stride, walks_per_node, scale_mode, entries);
+    return check_cuda(cudaGetLastError(), "compact_blocks_kernel launch");
+}
+
+extern "C" int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps,
+                                    int32_t *row_cnt, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_count_from_steps: bad shape");
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(offsets_step_major && row_cnt, "grf_count_from_steps: null buffer");
+    const int64_t n = n_rows * n_steps;
+    int64_t g = (n + 255) / 256;
+    if (g > (int64_t)kSmCount * 32) g = (int64_t)kSmCount * 32;
+    count_from_steps_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(offsets_step_major, n_rows, n_steps, row_cnt);
+    return check_cuda(cudaGetLastError(), "count_from_steps_kernel launch");
+}
+
+extern "C" int grf_blocks_from_steps(const int64_t *offsets_step_major, const int32_t *col, const double *val,
+                                     const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, GrfEntry *entries,
+                                     void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_blocks_from_steps: bad shape");
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(offsets_step_major && blk_ptr, "grf_blocks_from_steps: null buffer");
+    blocks_from_steps_kernel<<<grid_for_warps(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(
+        offsets_step_major, col, val, blk_ptr, n_rows, n_steps, entries);
+    return check_cuda(cudaGetLastError(), "blocks_from_steps_kernel launch");
+}
+
+extern "C" int grf_transpose_count(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
+                                   int32_t n_steps, int32_t *tcnt, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_count: bad shape");
+    if (n_cols == 0) return GRF_OK;
+    GRF_REQUIRE(tcnt, "grf_transpose_count: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    GRF_CUDA_OK(cudaMemsetAsync(tcnt, 0, (size_t)n_cols * n_steps * sizeof(int32_t), st));
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(blk_ptr, "grf_transpose_count: null blk_ptr");
+    transpose_count_kernel<<<grid_for_warps(n_rows, 256), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps, tcnt);
+    return check_cuda(cudaGetLastError(), "transpose_count_kernel launch");
+}
+
+extern "C" int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
+                                  int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor, GrfEntry *tentries,
+                                  void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_fill: bad shape");
+    if (n_cols == 0 || n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(blk_ptr && tblk_ptr && cursor, "grf_transpose_fill: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_segs = n_cols * n_steps;
+    GRF_CUDA_OK(cudaMemcpyAsync(cursor, tblk_ptr, (size_t)n_segs * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    transpose_fill_kernel<<<grid_for_warps(n_rows, 256), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps, cursor,
+                                                                        tentries);
+    GRF_CUDA_OK(cudaGetLastError());
+    // deterministic order inside every segment; `cursor` is dead now and is
+    // reused as [count | list of long segments] (hence its n_cols*L + 1 ints)
+    GRF_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(int32_t), st));
+    if (n_segs >= 2) {
+        int64_t g = (n_segs + 255) / 256;
+        if (g > (int64_t)kSmCount * 32) g = (int64_t)kSmCount * 32;
+        transpose_sort_short_kernel<<<(int)g, 256, 0, st>>>(tblk_ptr, n_segs, tentries, cursor + 1, cursor);
+        GRF_CUDA_OK(cudaGetLastError());
+        transpose_sort_long_kernel<<<kSmCount * 2, 512, 0, st>>>(tblk_ptr, tentries, cursor + 1, cursor);
+    }
+    return check_cuda(cudaGetLastError(), "transpose kernels launch");
+}

@@ -1,0 +1,290 @@
+// Phi(Phi^T V): the kernel matvec GPyTorch's conjugate gradients call (K3 + K5 + K6
+// in SURVEY.md 2a), with the modulator f_l applied at matvec time.
+//
+// Replaces, per matvec, in the reference:
+//   2L x SparseLinearOperator._matmul          utils_sparse/sparse_lo.py:16-18  (cuSPARSE SpMM, int64 indices)
+//   L  x .t().to_sparse_csr()                  utils_sparse/sparse_lo.py:23-25
+//   2L scalar*matrix + 2(L-1) adds on N x t    gptorch_kernels_sparse/sparse_grf_kernel.py:59-61
+//   scatter / gather of the selected rows      gptorch_kernels_sparse/sparse_grf_kernel.py:32-41
+//
+// Both halves are the same operation on block-CSR data ("for every row, for
+// every walk length l, f_l * sum of val * X[col, :]"), once over Phi^T blocks
+// (U = Phi[x2]^T V) and once over Phi blocks (out = Phi[x1] U):
+//   * entries are 8-byte {col, val} pairs streamed once, coalesced;
+//   * TPR threads share a row and own 4 (or 1) of the t right-hand-side
+//     columns each, so a gather of X[col, :] is one 16*TPR-byte contiguous read;
+//   * f_l is applied once per (row, length) segment, in registers.
+// HBM-bound: algorithmic bytes per matvec = 2*nnz*8 + 2*L*(rows+1)*4 + 4*N*t*4
+// (SURVEY.md 8d); the X gathers are L2/L1 traffic.  No tensor cores: this is a
+// sparse gather, not a dense contraction.
+
+#include "grf_common.cuh"
+
+namespace grf {
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    float4 v;
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void load(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+    __device__ __forceinline__ void fma(float a, const Vec &x) {
+        v.x = fmaf(a, x.v.x, v.x);
+        v.y = fmaf(a, x.v.y, v.y);
+        v.z = fmaf(a, x.v.z, v.z);
+        v.w = fmaf(a, x.v.w, v.w);
+    }
+    __device__ __forceinline__ float dot(const Vec &x) const {
+        return v.x * x.v.x + v.y * x.v.y + v.z * x.v.z + v.w * x.v.w;
+    }
+};
+template <>
+struct Vec<1> {
+    float v;
+    __device__ __forceinline__ void zero() { v = 0.f; }
+    __device__ __forceinline__ void load(const float *p) { v = __ldg(p); }
+    __device__ __forceinline__ void store(float *p) const { *p = v; }
+    __device__ __forceinline__ void fma(float a, const Vec &x) { v = fmaf(a, x.v, v); }
+    __device__ __forceinline__ float dot(const Vec &x) const { return v * x.v; }
+};
+
+__device__ __forceinline__ GrfEntry load_entry(const GrfEntry *p) {
+    const int2 raw = __ldg(reinterpret_cast<const int2 *>(p));
+    GrfEntry e;
+    e.col = raw.x;
+    e.val = __int_as_float(raw.y);
+    return e;
+}
+
+// Y[k, :] = sum_l f[l] * sum_{e in seg(row_k, l)} e.val * X[e.col, :]
+template <int TPR, int VEC>
+__global__ void __launch_bounds__(256) spmm_blocks_kernel(const int32_t *__restrict__ ptr,
+                                                          const GrfEntry *__restrict__ ent,
+                                                          const float *__restrict__ f, int32_t L,
+                                                          const int32_t *__restrict__ row_ids, int64_t n_tasks,
+                                                          int64_t row_lo, int64_t n_rows,
+                                                          const float *__restrict__ X, int64_t ldx,
+                                                          float *__restrict__ Y, int64_t ldy, int32_t t) {
+    const int sub = threadIdx.x % TPR;
+    const int64_t task0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+    const int64_t task_stride = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    for (int64_t k = task0; k < n_tasks; k += task_stride) {
+        const int64_t row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
+        if (row < 0 || row >= n_rows) continue;
+        const int32_t *rp = ptr + row * L;
+        for (int c0 = sub * VEC; c0 < t; c0 += TPR * VEC) {
+            Vec<VEC> acc;
+            acc.zero();
+            int32_t b = __ldg(rp);
+            for (int s = 0; s < L; ++s) {
+                const int32_t e = __ldg(rp + s + 1);
+                Vec<VEC> part;
+                part.zero();
+#pragma unroll 4
+                for (int32_t i = b; i < e; ++i) {
+                    const GrfEntry en = load_entry(ent + i);
+                    Vec<VEC> x;
+                    x.load(X + (int64_t)en.col * ldx + c0);
+                    part.fma(en.val, x);
+                }
+                acc.fma(__ldg(f + s), part);
+                b = e;
+            }
+            acc.store(Y + k * ldy + c0);
+        }
+    }
+}
+
+// vfull[(x2[k] - row_lo), :] += v[k, :]   (vfull zeroed by the caller)
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__restrict__ x2, int64_t n2,
+                                                           int64_t row_lo, int64_t n_rows,
+                                                           const float *__restrict__ v, int64_t ldv,
+                                                           float *__restrict__ vfull, int64_t ldu, int32_t t) {
+    const int64_t total = n2 * t;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = g / t;
+        const int c = (int)(g - k * t);
+        const int64_t row = (int64_t)__ldg(x2 + k) - row_lo;
+        if (row < 0 || row >= n_rows) continue;
+        atomicAdd(vfull + row * ldu + c, __ldg(v + k * ldv + c));
+    }
+}
+
+// grad[l] += sum_k sum_c left[k, c] * (sum_{e in seg(row_k, l)} e.val * P[e.col, c])
+constexpr int kMaxSteps = 32;
+
+template <int TPR, int VEC>
+__global__ void __launch_bounds__(256) fgrad_blocks_kernel(const int32_t *__restrict__ ptr,
+                                                           const GrfEntry *__restrict__ ent, int32_t L,
+                                                           const int32_t *__restrict__ row_ids, int64_t n_tasks,
+                                                           int64_t row_lo, int64_t n_rows,
+                                                           const float *__restrict__ left, int64_t ldl,
+                                                           const float *__restrict__ P, int64_t ldp, int32_t t,
+                                                           float *__restrict__ grad) {
+    __shared__ float sh[kMaxSteps];
+    if (threadIdx.x < kMaxSteps) sh[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int sub = threadIdx.x % TPR;
+    const int64_t task0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+    const int64_t task_stride = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    for (int s = 0; s < L; ++s) {
+        float g = 0.f;
+        for (int64_t k = task0; k < n_tasks; k += task_stride) {
+            const int64_t row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
+            if (row < 0 || row >= n_rows) continue;
+            const int32_t b = __ldg(ptr + row * L + s), e = __ldg(ptr + row * L + s + 1);
+            for (int c0 = sub * VEC; c0 < t; c0 += TPR * VEC) {
+                Vec<VEC> part;
+                part.zero();
+#pragma unroll 4
+                for (int32_t i = b; i < e; ++i) {
+                    const GrfEntry en = load_entry(ent + i);
+                    Vec<VEC> x;
+                    x.load(P + (int64_t)en.col * ldp + c0);
+                    part.fma(en.val, x);
+                }
+                Vec<VEC> lv;
+                lv.load(left + k * ldl + c0);
+                g += part.dot(lv);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) g += __shfl_xor_sync(0xffffffffu, g, d);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sh[s], g);
+    }
+    __syncthreads();
+    if (threadIdx.x < L) atomicAdd(grad + threadIdx.x, sh[threadIdx.x]);
+}
+
+struct Shape {
+    int tpr;
+    int vec;
+};
+
+static Shape pick_shape(int32_t t, bool vec_ok) {
+    Shape s;
+    if (vec_ok) {
+        s.vec = 4;
+        int need = (t + 3) / 4;
+        s.tpr = 1;
+        while (s.tpr < need && s.tpr < 32) s.tpr <<= 1;
+    } else {
+        s.vec = 1;
+        s.tpr = 1;
+        while (s.tpr < t && s.tpr < 32) s.tpr <<= 1;
+    }
+    return s;
+}
+
+static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+static int spmm_grid(int64_t n_tasks, int tpr) {
+    const int64_t threads = n_tasks * tpr;
+    int64_t g = (threads + 255) / 256;
+    const int64_t cap = (int64_t)kSmCount * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+#define GRF_DISPATCH_SHAPE(KERNEL, shape, ...)                                   \
+    do {                                                                         \
+        if ((shape).vec == 4) {                                                  \
+            switch ((shape).tpr) {                                               \
+                case 1: KERNEL<1, 4> __VA_ARGS__; break;                         \
+                case 2: KERNEL<2, 4> __VA_ARGS__; break;                         \
+                case 4: KERNEL<4, 4> __VA_ARGS__; break;                         \
+                case 8: KERNEL<8, 4> __VA_ARGS__; break;                         \
+                case 16: KERNEL<16, 4> __VA_ARGS__; break;                       \
+                default: KERNEL<32, 4> __VA_ARGS__; break;                       \
+            }                                                                    \
+        } else {                                                                 \
+            switch ((shape).tpr) {                                               \
+                case 1: KERNEL<1, 1> __VA_ARGS__; break;                         \
+                case 2: KERNEL<2, 1> __VA_ARGS__; break;                         \
+                case 4: KERNEL<4, 1> __VA_ARGS__; break;                         \
+                case 8: KERNEL<8, 1> __VA_ARGS__; break;                         \
+                case 16: KERNEL<16, 1> __VA_ARGS__; break;                       \
+                default: KERNEL<32, 1> __VA_ARGS__; break;                       \
+            }                                                                    \
+        }                                                                        \
+    } while (0)
+
+}  // namespace grf
+
+using namespace grf;
+
+extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t n1, const int32_t *x2,
+                              int64_t n2, const float *v, int64_t ldv, float *out, int64_t ldo, float *u, int64_t ldu,
+                              float *vfull, int32_t t, int32_t which, void *stream) {
+    GRF_REQUIRE(phi && f, "grf_phi_matvec: null phi/f");
+    GRF_REQUIRE(t >= 1, "grf_phi_matvec: t must be >= 1");
+    GRF_REQUIRE(which >= 1 && which <= 3, "grf_phi_matvec: which must be 1, 2 or 3");
+    GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_matvec: n_steps out of range");
+    GRF_REQUIRE(u && ldu >= t, "grf_phi_matvec: U workspace missing or ldu < t");
+    GRF_REQUIRE(x1 || n1 == phi->n_rows, "grf_phi_matvec: n1 must equal n_rows when x1 is NULL");
+    GRF_REQUIRE(x2 || n2 == phi->n_rows, "grf_phi_matvec: n2 must equal n_rows when x2 is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t L = phi->n_steps;
+
+    if (which & 1) {
+        GRF_REQUIRE(v && ldv >= t, "grf_phi_matvec: V missing or ldv < t");
+        GRF_REQUIRE(phi->tblk_ptr, "grf_phi_matvec: Phi^T blocks missing");
+        const float *src = v;
+        int64_t lds = ldv;
+        if (x2) {
+            GRF_REQUIRE(vfull, "grf_phi_matvec: vfull workspace needed when x2 is given");
+            GRF_CUDA_OK(cudaMemsetAsync(vfull, 0, (size_t)phi->n_rows * ldu * sizeof(float), st));
+            if (n2 > 0 && phi->n_rows > 0) {
+                int64_t g = (n2 * t + 255) / 256;
+                if (g > (int64_t)kSmCount * 16) g = (int64_t)kSmCount * 16;
+                scatter_rows_kernel<<<(int)g, 256, 0, st>>>(x2, n2, phi->row_lo, phi->n_rows, v, ldv, vfull, ldu, t);
+                GRF_CUDA_OK(cudaGetLastError());
+            }
+            src = vfull;
+            lds = ldu;
+        }
+        if (phi->n_cols > 0) {
+            const bool vec_ok = (t % 4 == 0) && (lds % 4 == 0) && (ldu % 4 == 0) && aligned16(src) && aligned16(u);
+            const Shape sh = pick_shape(t, vec_ok);
+            const int grid = spmm_grid(phi->n_cols, sh.tpr);
+            GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
+                               <<<grid, 256, 0, st>>>(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0,
+                                                      phi->n_cols, src, lds, u, ldu, t));
+            GRF_CUDA_OK(cudaGetLastError());
+        }
+    }
+    if ((which & 2) && n1 > 0) {
+        GRF_REQUIRE(out && ldo >= t, "grf_phi_matvec: out missing or ldo < t");
+        GRF_REQUIRE(phi->blk_ptr, "grf_phi_matvec: Phi blocks missing");
+        const bool vec_ok = (t % 4 == 0) && (ldo % 4 == 0) && (ldu % 4 == 0) && aligned16(out) && aligned16(u);
+        const Shape sh = pick_shape(t, vec_ok);
+        const int grid = spmm_grid(n1, sh.tpr);
+        GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
+                           <<<grid, 256, 0, st>>>(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
+                                                  u, ldu, out, ldo, t));
+        GRF_CUDA_OK(cudaGetLastError());
+    }
+    return GRF_OK;
+}
+
+extern "C" int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, const float *left, int64_t ldl,
+                             const float *p, int64_t ldp, int32_t t, float *grad, void *stream) {
+    GRF_REQUIRE(phi && left && p && grad, "grf_phi_fgrad: null argument");
+    GRF_REQUIRE(t >= 1 && ldl >= t && ldp >= t, "grf_phi_fgrad: bad t / leading dimensions");
+    GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_fgrad: n_steps out of range");
+    GRF_REQUIRE(x || n == phi->n_rows, "grf_phi_fgrad: n must equal n_rows when x is NULL");
+    if (n == 0) return GRF_OK;
+    GRF_REQUIRE(phi->blk_ptr, "grf_phi_fgrad: Phi blocks missing");
+    const bool vec_ok = (t % 4 == 0) && (ldl % 4 == 0) && (ldp % 4 == 0) && aligned16(left) && aligned16(p);
+    const Shape sh = pick_shape(t, vec_ok);
+    int grid = spmm_grid(n, sh.tpr);
+    if (grid > kSmCount * 4) grid = kSmCount * 4;
+    GRF_DISPATCH_SHAPE(fgrad_blocks_kernel, sh,
+                       <<<grid, 256, 0, (cudaStream_t)stream>>>(phi->blk_ptr, phi->entries, phi->n_steps, x, n,
+                                                                phi->row_lo, phi->n_rows, left, ldl, p, ldp, t, grad));
+    return check_cuda(cudaGetLastError(), "fgrad_blocks_kernel launch");
+}

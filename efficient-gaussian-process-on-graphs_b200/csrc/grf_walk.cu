@@ -1,0 +1,331 @@
+// GRF walker + per-start-node merge (K1 + the dict half of K2 in SURVEY.md 2a).
+//
+// Replaces the reference's CPython walk loop
+//   efficient_graph_gp_sparse/random_walk_samplers_sparse/sparse_sampler.py:36-54
+//   efficient_graph_gp/random_walk_samplers/sampler.py:40-59, :163-184
+// and its defaultdict accumulation / merge (:42, :110-114).
+//
+// One *group* (a warp, or a whole CTA when W is large) owns one start node at a
+// time.  Phase 1: every lane runs walks w = lane, lane+G, ... of that node:
+// CSR row_ptr pair -> halting draw -> neighbour draw -> (col, val) gather, the
+// load update deg*w/(1-p) applied in registers in float64, and the visit
+// (node, load) of every length >= 1 parked in shared memory.  Phase 2: per
+// length, the <= W visits are bitonic-sorted in shared memory by (node, walk)
+// and, per distinct node, the loads are added *in walk order* into a double
+// that starts at 0.0 -- exactly the order in which the reference's
+// defaultdict(float) accumulates them, so the sums are bit-identical when both
+// sides see the same draws.  The merged (column-sorted) per-length segments go
+// to the row's staging region; grf_compact_* turns staging into CSR.
+//
+// Draw sources: Philox4x32-10 keyed by the seed with counter (walk id, step)
+// -- independent of how start nodes are sharded over GPUs -- or a replayed
+// trace of the reference's own PCG64 draws.
+//
+// Roofline: per executed walk-step the algorithmic traffic is row_ptr pair 8 B
+// + col 4 B + val 8 B + staging write 12 B/(merged entry); three dependent
+// random 32-B sectors per step => latency / sector bound, not bandwidth bound.
+
+#include "grf_common.cuh"
+
+namespace grf {
+
+struct WalkParams {
+    const int32_t *row_ptr;
+    const int32_t *col_idx;
+    const double *val;
+    int64_t start_lo;
+    int64_t n_local;
+    int32_t W, L, Wp, wbits;
+    double p_halt, one_minus_p;
+    unsigned long long halt_thr;
+    uint32_t k0, k1;
+    int32_t draw_mode, load_mode;
+    const double *trace_u;
+    const int32_t *trace_k;
+    int64_t stride;
+    int32_t *stage_col;
+    double *stage_sum;
+    int32_t *row_cnt;
+    unsigned long long *visits;
+    uint32_t group_bytes, loads_bytes, nodes_bytes;
+};
+
+template <bool kBlock>
+__device__ __forceinline__ void group_sync() {
+    if (kBlock)
+        __syncthreads();
+    else
+        __syncwarp();
+}
+
+// exclusive scan of one int per thread over the group; `total` = group sum
+template <bool kBlock>
+__device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) {
+    const int lane = threadIdx.x & 31;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (!kBlock) {
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        return incl - v;
+    }
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int i = 0; i < nwarps; ++i) {
+        const int s = scratch[i];
+        if (i < warp) before += s;
+        all += s;
+    }
+    __syncthreads();
+    total = all;
+    return before + incl - v;
+}
+
+template <bool kBlock, typename KeyT>
+__global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const WalkParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int GS = kBlock ? (int)blockDim.x : 32;
+    const int tg = kBlock ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    const int groups_per_cta = kBlock ? 1 : (int)(blockDim.x >> 5);
+    const int group_in_cta = kBlock ? 0 : (int)(threadIdx.x >> 5);
+
+    unsigned char *base = smem_raw + (size_t)group_in_cta * p.group_bytes;
+    double *loads = reinterpret_cast<double *>(base);                                  // [(L-1)][W]
+    int32_t *nodes = reinterpret_cast<int32_t *>(base + p.loads_bytes);                // [(L-1)][W]
+    KeyT *keys = reinterpret_cast<KeyT *>(base + p.loads_bytes + p.nodes_bytes);       // [Wp]
+    __shared__ int scan_scratch[32];
+
+    const int W = p.W, L = p.L, Wp = p.Wp, wbits = p.wbits;
+    const KeyT KEY_MAX = ~(KeyT)0;
+    const KeyT wmask = ((KeyT)1 << wbits) - 1;
+    const int chunk = (Wp + GS - 1) / GS;
+    unsigned long long my_visits = 0;
+
+    for (int64_t row = (int64_t)blockIdx.x * groups_per_cta + group_in_cta; row < p.n_local;
+         row += (int64_t)gridDim.x * groups_per_cta) {
+        const int64_t start = p.start_lo + row;
+
+        // ---------------- phase 1: the walks -------------------------------
+        for (int w = tg; w < W; w += GS) {
+            const unsigned long long walk_id = (unsigned long long)start * (unsigned long long)W + (unsigned)w;
+            int32_t cur = (int32_t)start;
+            double load = 1.0;
+            ++my_visits;  // the length-0 visit (start, 1.0)
+            int step = 0;
+            for (; step < L - 1; ++step) {
+                const int32_t rs = __ldg(p.row_ptr + cur);
+                const int32_t re = __ldg(p.row_ptr + cur + 1);
+                const int32_t deg = re - rs;
+                if (deg == 0) break;  // dead end: stop without drawing (sparse_sampler.py:47)
+                int32_t k;
+                if (p.draw_mode == GRF_DRAW_REPLAY) {
+                    const unsigned long long ti = walk_id * (unsigned)L + (unsigned)step;
+                    if (__ldg(p.trace_u + ti) < p.p_halt) break;
+                    k = __ldg(p.trace_k + ti);
+                } else {
+                    uint32_t x[4];
+                    philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)step, 0u, p.k0, p.k1, x);
+                    if ((unsigned long long)x[0] < p.halt_thr) break;
+                    const unsigned long long r64 = ((unsigned long long)x[2] << 32) | (unsigned long long)x[1];
+                    k = (int32_t)__umul64hi(r64, (unsigned long long)deg);
+                }
+                const int64_t e = (int64_t)rs + k;
+                const double wgt = __ldg(p.val + e);
+                const int32_t nxt = __ldg(p.col_idx + e);
+                // load *= degree * weight / (1 - p_halt), evaluated left to right in
+                // float64 with no contraction (sparse_sampler.py:54)
+                const double scaled = __ddiv_rn(__dmul_rn((double)deg, wgt), p.one_minus_p);
+                if (p.load_mode == GRF_LOAD_CUMULATIVE)
+                    load = __dmul_rn(load, scaled);
+                else if (p.load_mode == GRF_LOAD_LAST_STEP)
+                    load = scaled;
+                else
+                    load = wgt;
+                cur = nxt;
+                nodes[step * W + w] = cur;  // the visit at length step+1
+                loads[step * W + w] = load;
+                ++my_visits;
+            }
+            for (int s2 = step; s2 < L - 1; ++s2) nodes[s2 * W + w] = -1;
+        }
+
+        int32_t *out_col = p.stage_col + row * p.stride;
+        double *out_sum = p.stage_sum + row * p.stride;
+        if (tg == 0) {
+            out_col[0] = (int32_t)start;  // M_0 = I: W visits of load 1.0, summed exactly
+            out_sum[0] = (double)W;
+            p.row_cnt[row * L] = 1;
+        }
+        int off = 1;
+        group_sync<kBlock>();
+
+        // ---------------- phase 2: merge the visits of each length ----------
+        for (int si = 0; si < L - 1; ++si) {
+            for (int i = tg; i < Wp; i += GS) {
+                KeyT key = KEY_MAX;
+                if (i < W) {
+                    const int32_t nd = nodes[si * W + i];
+                    if (nd >= 0) key = ((KeyT)(uint32_t)nd << wbits) | (KeyT)i;
+                }
+                keys[i] = key;
+            }
+            group_sync<kBlock>();
+            for (uint32_t k = 2; k <= (uint32_t)Wp; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t c = tg; c < (uint32_t)Wp / 2; c += GS) {
+                        const uint32_t idx = ((c & ~(j - 1)) << 1) | (c & (j - 1));
+                        const uint32_t ixj = idx | j;
+                        const KeyT a = keys[idx], b = keys[ixj];
+                        const bool up = (idx & k) == 0;
+                        if ((a > b) == up) {
+                            keys[idx] = b;
+                            keys[ixj] = a;
+                        }
+                    }
+                    group_sync<kBlock>();
+                }
+            }
+            // distinct nodes = run heads of the sorted keys; thread tg owns a
+            // contiguous chunk so that ranks follow column order
+            const int lo = tg * chunk;
+            const int hi = min(Wp, lo + chunk);
+            int heads = 0;
+            for (int i = lo; i < hi; ++i) {
+                const KeyT key = keys[i];
+                if (key == KEY_MAX) break;
+                heads += (i == 0) || ((keys[i - 1] >> wbits) != (key >> wbits));
+            }
+            int total;
+            int rank = group_excl_scan<kBlock>(heads, scan_scratch, total);
+            for (int i = lo; i < hi; ++i) {
+                const KeyT key = keys[i];
+                if (key == KEY_MAX) break;
+                const KeyT node = key >> wbits;
+                if ((i == 0) || ((keys[i - 1] >> wbits) != node)) {
+                    double sum = 0.0;
+                    for (int q = i; q < Wp; ++q) {
+                        const KeyT kq = keys[q];
+                        if ((kq >> wbits) != node) break;
+                        sum = __dadd_rn(sum, loads[si * W + (int)(kq & wmask)]);
+                    }
+                    out_col[off + rank] = (int32_t)node;
+                    out_sum[off + rank] = sum;
+                    ++rank;
+                }
+            }
+            if (tg == 0) p.row_cnt[row * L + si + 1] = total;
+            off += total;
+            group_sync<kBlock>();
+        }
+    }
+
+    if (p.visits != nullptr) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_visits += __shfl_xor_sync(0xffffffffu, my_visits, d);
+        if ((threadIdx.x & 31) == 0 && my_visits) atomicAdd(p.visits, my_visits);
+    }
+}
+
+template <bool kBlock, typename KeyT>
+static int launch_walk(const WalkParams &p, size_t smem, int threads, int grid, cudaStream_t stream) {
+    auto kern = walk_merge_kernel<kBlock, KeyT>;
+    GRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, stream>>>(p);
+    return check_cuda(cudaGetLastError(), "walk_merge_kernel launch");
+}
+
+}  // namespace grf
+
+extern "C" int64_t grf_walk_stage_stride(int32_t walks_per_node, int32_t max_walk_length) {
+    if (walks_per_node < 1 || max_walk_length < 1) return 0;
+    return 1 + (int64_t)(max_walk_length - 1) * (int64_t)walks_per_node;
+}
+
+extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t stage_stride, int32_t *stage_col,
+                        double *stage_sum, int32_t *row_cnt, unsigned long long *visits_out, void *stream) {
+    using namespace grf;
+    GRF_REQUIRE(graph && cfg, "grf_walk: null graph/cfg");
+    GRF_REQUIRE(graph->n_nodes >= 0 && graph->n_nodes < (1ll << 31), "grf_walk: n_nodes %lld out of int32 range",
+                (long long)graph->n_nodes);
+    GRF_REQUIRE(graph->nnz >= 0 && graph->nnz < (1ll << 31), "grf_walk: nnz %lld out of int32 range",
+                (long long)graph->nnz);
+    GRF_REQUIRE(cfg->walks_per_node >= 1, "grf_walk: walks_per_node must be >= 1");
+    GRF_REQUIRE(cfg->max_walk_length >= 1, "grf_walk: max_walk_length must be >= 1");
+    GRF_REQUIRE(cfg->p_halt >= 0.0 && cfg->p_halt <= 1.0, "grf_walk: p_halt must be in [0, 1]");
+    GRF_REQUIRE(cfg->start_lo >= 0 && cfg->start_lo <= cfg->start_hi && cfg->start_hi <= graph->n_nodes,
+                "grf_walk: start range [%lld, %lld) outside [0, %lld)", (long long)cfg->start_lo,
+                (long long)cfg->start_hi, (long long)graph->n_nodes);
+    GRF_REQUIRE(cfg->draw_mode == GRF_DRAW_PHILOX || cfg->draw_mode == GRF_DRAW_REPLAY, "grf_walk: bad draw_mode");
+    GRF_REQUIRE(cfg->load_mode >= GRF_LOAD_CUMULATIVE && cfg->load_mode <= GRF_LOAD_ABLATION,
+                "grf_walk: bad load_mode");
+    GRF_REQUIRE(cfg->draw_mode != GRF_DRAW_REPLAY || (cfg->trace_u && cfg->trace_k),
+                "grf_walk: replay mode needs trace_u and trace_k");
+    GRF_REQUIRE(stage_stride >= grf_walk_stage_stride(cfg->walks_per_node, cfg->max_walk_length),
+                "grf_walk: stage_stride too small");
+    const int64_t n_local = cfg->start_hi - cfg->start_lo;
+    if (n_local == 0) return GRF_OK;
+    GRF_REQUIRE(graph->row_ptr && stage_col && stage_sum && row_cnt, "grf_walk: null buffer");
+    GRF_REQUIRE(graph->nnz == 0 || (graph->col_idx && graph->val), "grf_walk: null edge arrays");
+
+    WalkParams p;
+    p.row_ptr = graph->row_ptr;
+    p.col_idx = graph->col_idx;
+    p.val = graph->val;
+    p.start_lo = cfg->start_lo;
+    p.n_local = n_local;
+    p.W = cfg->walks_per_node;
+    p.L = cfg->max_walk_length;
+    p.Wp = (int32_t)next_pow2((uint32_t)p.W);
+    p.wbits = bit_width((uint64_t)p.Wp - 1);
+    p.p_halt = cfg->p_halt;
+    p.one_minus_p = 1.0 - cfg->p_halt;
+    double thr = floor(cfg->p_halt * 4294967296.0);
+    thr = thr < 0.0 ? 0.0 : (thr > 4294967296.0 ? 4294967296.0 : thr);
+    p.halt_thr = (unsigned long long)thr;
+    p.k0 = (uint32_t)cfg->seed;
+    p.k1 = (uint32_t)(cfg->seed >> 32);
+    p.draw_mode = cfg->draw_mode;
+    p.load_mode = cfg->load_mode;
+    p.trace_u = cfg->trace_u;
+    p.trace_k = cfg->trace_k;
+    p.stride = stage_stride;
+    p.stage_col = stage_col;
+    p.stage_sum = stage_sum;
+    p.row_cnt = row_cnt;
+    p.visits = visits_out;
+
+    const int node_bits = bit_width((uint64_t)(graph->n_nodes > 0 ? graph->n_nodes - 1 : 0));
+    const bool key32 = node_bits + p.wbits <= 31;
+    const size_t key_size = key32 ? 4 : 8;
+    const size_t steps = (size_t)(p.L - 1);
+    p.loads_bytes = (uint32_t)(steps * p.W * 8);
+    p.nodes_bytes = (uint32_t)((steps * p.W * 4 + 7) & ~(size_t)7);
+    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + (size_t)p.Wp * key_size + 15) & ~(size_t)15;
+    p.group_bytes = (uint32_t)gb;
+    const size_t kMaxSmem = 227 * 1024 - 256;
+    GRF_REQUIRE((uint64_t)p.W * (uint64_t)p.L < (1ull << 31), "grf_walk: W*L too large");
+
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool warp_variant = p.W <= 256 && 4 * gb <= 96 * 1024;
+    if (warp_variant) {
+        const int warps = 4;
+        const int64_t want = (n_local + warps - 1) / warps;
+        const int grid = (int)(want < (int64_t)kSmCount * 64 ? want : (int64_t)kSmCount * 64);
+        return key32 ? launch_walk<false, uint32_t>(p, warps * gb, warps * 32, grid, st)
+                     : launch_walk<false, unsigned long long>(p, warps * gb, warps * 32, grid, st);
+    }
+    if (gb > kMaxSmem)
+        return fail(GRF_ERR_UNSUPPORTED,
+                    "grf_walk: W=%d, L=%d needs %zu B of shared memory per start node (max %zu)", p.W, p.L, gb,
+                    kMaxSmem);
+    const int64_t want = n_local;
+    const int grid = (int)(want < (int64_t)kSmCount * 32 ? want : (int64_t)kSmCount * 32);
+    return key32 ? launch_walk<true, uint32_t>(p, gb, 256, grid, st)
+                 : launch_walk<true, unsigned long long>(p, gb, 256, grid, st);
+}

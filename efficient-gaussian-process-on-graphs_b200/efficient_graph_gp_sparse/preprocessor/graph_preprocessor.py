@@ -1,0 +1,117 @@
+"""Drop-in for ``preprocessor/graph_preprocessor.py:10-165``.
+
+Same constructor, attributes (``step_matrices_scipy``, ``step_matrices_torch``),
+``preprocess_graph``, ``from_scipy_csr`` and pickle cache format.  The step
+matrices are computed on the GPU; ``step_matrices_torch`` is a list of
+``SparseLinearOperator`` like the reference's, and additionally carries the
+fused Phi blocks (``.phi_blocks``) so that the kernels never rebuild them.
+"""
+
+import hashlib
+import os
+import pickle
+from typing import List, Optional
+
+import scipy.sparse as sp
+import torch
+
+from grf_b200.engine import PhiBlocks
+from efficient_graph_gp_sparse.random_walk_samplers_sparse import SparseRandomWalk
+from efficient_graph_gp_sparse.utils_sparse import SparseLinearOperator, get_normalized_laplacian
+
+
+class StepOperatorList(list):
+    """``list[SparseLinearOperator]`` that remembers the fused device layout."""
+
+    phi_blocks: Optional[PhiBlocks] = None
+
+    def to(self, device):
+        out = StepOperatorList(op.to(device) for op in self)
+        if self.phi_blocks is not None and self.phi_blocks.device == torch.device(device):
+            out.phi_blocks = self.phi_blocks
+        return out
+
+
+class GraphPreprocessor:
+    """Computes the GRF step matrices of a graph (random walks on its normalized Laplacian)."""
+
+    def __init__(self, adjacency_matrix: sp.csr_matrix,
+                 walks_per_node: int = 10,
+                 p_halt: float = 0.5,
+                 max_walk_length: int = 10,
+                 random_walk_seed: int = 42,
+                 load_from_disk: bool = False,
+                 use_tqdm: bool = True,
+                 cache_filename: Optional[str] = None,
+                 n_processes: int = None,
+                 device=None) -> None:
+        if adjacency_matrix.shape[0] != adjacency_matrix.shape[1]:
+            raise ValueError("Adjacency matrix must be square.")
+
+        self.adj_matrix = adjacency_matrix
+        self.walks_per_node = walks_per_node
+        self.p_halt = p_halt
+        self.max_walk_length = max_walk_length
+        self.random_walk_seed = random_walk_seed
+        self.use_tqdm = use_tqdm
+        self.cache_filename = cache_filename or self._generate_cache_filename()
+        self.n_processes = n_processes
+        self.device = device
+
+        if load_from_disk:
+            if os.path.exists(self.cache_filename):
+                self.step_matrices_scipy = self.load_step_matrices(self.cache_filename)
+                self.step_matrices_torch = self._wrap(self.step_matrices_scipy, None)
+            else:
+                raise FileNotFoundError(f"Cache file {self.cache_filename} not found.")
+
+    def _generate_cache_filename(self) -> str:
+        """Same key as the reference (graph_preprocessor.py:75-83), so caches are interchangeable."""
+        adj_hash = hashlib.md5(self.adj_matrix.data.tobytes() +
+                               self.adj_matrix.indices.tobytes() +
+                               self.adj_matrix.indptr.tobytes()).hexdigest()[:8]
+        graph_size = self.adj_matrix.shape[0]
+        params = f"{graph_size}_{self.walks_per_node}_{self.p_halt}_{self.max_walk_length}_{self.random_walk_seed}"
+        return f"experiments_sparse/step_matrices/step_matrices_{adj_hash}_{params}.pkl"
+
+    def _wrap(self, mats, blocks) -> StepOperatorList:
+        dev = torch.device(self.device) if self.device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        ops = StepOperatorList(SparseLinearOperator(self.from_scipy_csr(m).to(dev)) for m in mats)
+        ops.phi_blocks = blocks
+        return ops
+
+    def preprocess_graph(self, save_to_disk: bool = False, *, trace=None) -> List[SparseLinearOperator]:
+        laplacian = get_normalized_laplacian(self.adj_matrix)
+        random_walk = SparseRandomWalk(laplacian, seed=self.random_walk_seed, device=self.device)
+        steps = random_walk.get_step_matrices_device(self.walks_per_node, self.p_halt, self.max_walk_length,
+                                                     trace=trace)
+        self.step_matrices_scipy = steps.to_scipy()
+        if save_to_disk:
+            self.save_step_matrices(self.step_matrices_scipy, self.cache_filename)
+        self.step_matrices_torch = self._wrap(self.step_matrices_scipy, PhiBlocks.from_step_matrices(steps))
+        return self.step_matrices_torch
+
+    @staticmethod
+    def from_scipy_csr(scipy_csr: sp.csr_matrix) -> torch.Tensor:
+        """scipy CSR -> torch sparse CSR (int64 indices, float32 values), as graph_preprocessor.py:117-139."""
+        if not isinstance(scipy_csr, sp.csr_matrix):
+            raise ValueError("Input must be a scipy CSR matrix.")
+        crow_indices = torch.from_numpy(scipy_csr.indptr).long()
+        col_indices = torch.from_numpy(scipy_csr.indices).long()
+        values = torch.from_numpy(scipy_csr.data).float()
+        return torch.sparse_csr_tensor(crow_indices, col_indices, values,
+                                       (scipy_csr.shape[0], scipy_csr.shape[1]), dtype=torch.float32)
+
+    @staticmethod
+    def save_step_matrices(step_matrices: List[sp.csr_matrix], filename: str) -> None:
+        d = os.path.dirname(filename)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        with open(filename, "wb") as f:
+            pickle.dump(step_matrices, f)
+
+    @staticmethod
+    def load_step_matrices(filename: str) -> List[sp.csr_matrix]:
+        with open(filename, "rb") as f:
+            return pickle.load(f)

@@ -1,0 +1,557 @@
+"""Device pipeline of the GRF hot path: walker -> staging -> CSR / Phi blocks -> matvec.
+
+Everything here is plumbing around the C ABI (``include/grf_b200.h``): torch
+allocates the buffers and provides the stream, the CUDA library does the work.
+No CPU fallback -- a missing library or a non-CUDA device raises.
+
+Reference call stack this replaces:
+  SparseRandomWalk.get_random_walk_matrices   sparse_sampler.py:72-132
+  RandomWalk.get_random_walk_matrices         sampler.py:93-203
+  GraphPreprocessor.from_scipy_csr            graph_preprocessor.py:117-139
+  SparseLinearOperator._matmul / transpose    sparse_lo.py:16-25
+  SparseGRFKernel.forward                     sparse_grf_kernel.py:24-62
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GrfGraph, GrfPhi, GrfWalkCfg, check
+
+_MAX_STAGE_BYTES = 6 << 30  # staging budget per walker launch; larger shards are walked in row chunks
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("grf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"grf_b200 needs a CUDA device, got {device}; there is no CPU fallback")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class WalkConfig:
+    """Arguments of the reference's walk loop (sparse_sampler.py:26-31) + draw source."""
+
+    walks_per_node: int
+    p_halt: float
+    max_walk_length: int
+    seed: int = 42
+    draw_mode: int = _lib.DRAW_PHILOX
+    load_mode: int = _lib.LOAD_CUMULATIVE
+    trace: Optional[Tuple] = None  # (trace_u float64, trace_k int32), [walk_id*L + step]
+
+    def validate(self):
+        if int(self.walks_per_node) < 1:
+            raise ValueError("walks_per_node must be >= 1")
+        if int(self.max_walk_length) < 1:
+            raise ValueError("max_walk_length must be >= 1")
+        if not (0.0 <= float(self.p_halt) <= 1.0):
+            raise ValueError("p_halt must be in [0, 1]")
+        if self.draw_mode == _lib.DRAW_REPLAY and self.trace is None:
+            raise ValueError("replay mode needs trace=(trace_u, trace_k)")
+
+
+class DeviceGraph:
+    """The walk graph resident in HBM: CSR row_ptr/col_idx int32, val float64
+    (what SparseRandomWalk.__init__ keeps, sparse_sampler.py:62-70)."""
+
+    def __init__(self, indptr, indices, data, n_nodes: int, device=None):
+        self.device = _device(device)
+        indptr = np.ascontiguousarray(indptr)
+        if indptr.shape[0] != n_nodes + 1:
+            raise ValueError("indptr must have n_nodes + 1 entries")
+        nnz = int(indptr[-1]) if n_nodes > 0 else 0
+        if nnz >= 2 ** 31 or n_nodes >= 2 ** 31:
+            raise ValueError("graph exceeds int32 index range")
+        self.n_nodes = int(n_nodes)
+        self.nnz = nnz
+        self.row_ptr = torch.from_numpy(indptr.astype(np.int32, copy=False)).to(self.device, non_blocking=True)
+        self.col_idx = torch.from_numpy(np.ascontiguousarray(indices[:nnz]).astype(np.int32, copy=False)).to(
+            self.device, non_blocking=True)
+        self.val = torch.from_numpy(np.ascontiguousarray(data[:nnz]).astype(np.float64, copy=False)).to(
+            self.device, non_blocking=True)
+
+    @classmethod
+    def from_scipy(cls, adj, device=None) -> "DeviceGraph":
+        if adj.shape[0] != adj.shape[1]:
+            raise ValueError("Adjacency matrix must be square.")
+        a = adj.tocsr()
+        return cls(a.indptr, a.indices, a.data.astype(float, copy=False), a.shape[0], device)
+
+    def c_struct(self) -> GrfGraph:
+        return GrfGraph(self.n_nodes, self.nnz, self.row_ptr.data_ptr(), self.col_idx.data_ptr(),
+                        self.val.data_ptr())
+
+
+@dataclass
+class Staging:
+    stage_col: torch.Tensor   # int32 [n_rows * stride]
+    stage_sum: torch.Tensor   # float64 [n_rows * stride]
+    row_cnt: torch.Tensor     # int32 [n_rows * L]
+    stride: int
+    n_rows: int
+    row_lo: int
+    visits: torch.Tensor      # int64 [1] walk-steps executed
+
+
+def scan_counts(row_cnt: torch.Tensor, n_rows: int, n_steps: int, order: int, i64: bool) -> torch.Tensor:
+    dev = row_cnt.device
+    n = n_rows * n_steps
+    out = torch.empty(n + 1, dtype=torch.int64 if i64 else torch.int32, device=dev)
+    ws = torch.empty(max(1, _lib.lib().grf_scan_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    check(_lib.lib().grf_scan_counts(_ptr(row_cnt), n_rows, n_steps, order, _ptr(out), int(i64), _ptr(ws),
+                                     _stream(dev)))
+    return out
+
+
+def run_walker(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
+               visits: Optional[torch.Tensor] = None) -> Staging:
+    """One grf_walk launch over start nodes [start_lo, start_hi)."""
+    cfg.validate()
+    L = _lib.lib()
+    dev = graph.device
+    start_hi = graph.n_nodes if start_hi is None else start_hi
+    n_rows = start_hi - start_lo
+    stride = L.grf_walk_stage_stride(cfg.walks_per_node, cfg.max_walk_length)
+    stage_col = torch.empty(max(1, n_rows * stride), dtype=torch.int32, device=dev)
+    stage_sum = torch.empty(max(1, n_rows * stride), dtype=torch.float64, device=dev)
+    row_cnt = torch.empty(max(1, n_rows * cfg.max_walk_length), dtype=torch.int32, device=dev)
+    if visits is None:
+        visits = torch.zeros(1, dtype=torch.int64, device=dev)
+    tu = tk = None
+    if cfg.draw_mode == _lib.DRAW_REPLAY:
+        tu = torch.as_tensor(cfg.trace[0], dtype=torch.float64).to(dev).contiguous()
+        tk = torch.as_tensor(cfg.trace[1], dtype=torch.int32).to(dev).contiguous()
+        need = graph.n_nodes * cfg.walks_per_node * cfg.max_walk_length
+        if tu.numel() < need or tk.numel() < need:
+            raise ValueError("trace arrays must have n_nodes * W * L entries")
+    g = graph.c_struct()
+    c = GrfWalkCfg(start_lo, start_hi, cfg.walks_per_node, cfg.max_walk_length, float(cfg.p_halt), cfg.draw_mode,
+                   cfg.load_mode, int(cfg.seed) & 0xFFFFFFFFFFFFFFFF,
+                   None if tu is None else tu.data_ptr(), None if tk is None else tk.data_ptr())
+    check(L.grf_walk(ctypes.byref(g), ctypes.byref(c), stride, _ptr(stage_col), _ptr(stage_sum), _ptr(row_cnt),
+                     _ptr(visits), _stream(dev)))
+    return Staging(stage_col, stage_sum, row_cnt, stride, n_rows, start_lo, visits)
+
+
+def _row_chunks(start_lo: int, start_hi: int, stride: int, max_stage_bytes: int):
+    rows_per = max(1, max_stage_bytes // (stride * 12))
+    lo = start_lo
+    while lo < start_hi:
+        hi = min(start_hi, lo + rows_per)
+        yield lo, hi
+        lo = hi
+    if start_lo == start_hi:
+        yield start_lo, start_hi
+
+
+class StepMatrices:
+    """The reference's output layout on device: L CSR matrices (rows = this
+    shard's start nodes), concatenated step-major.  ``offsets[s*n_rows + r]`` is
+    the position of (step s, row r); float64 values, int32 sorted columns."""
+
+    def __init__(self, offsets, col, val, n_rows, n_cols, n_steps, row_lo, visits=0):
+        self.offsets, self.col, self.val = offsets, col, val
+        self.n_rows, self.n_cols, self.n_steps, self.row_lo = n_rows, n_cols, n_steps, row_lo
+        self.visits = visits
+
+    @property
+    def device(self):
+        return self.col.device
+
+    def nnz_per_step(self) -> List[int]:
+        off = self.offsets[:: max(1, self.n_rows)][: self.n_steps + 1].cpu().tolist() if self.n_rows else [0] * (
+            self.n_steps + 1)
+        return [off[s + 1] - off[s] for s in range(self.n_steps)]
+
+    def to_scipy(self):
+        """list[scipy.sparse.csr_matrix] of shape (n_rows, n_cols) -- what
+        get_random_walk_matrices returns (sparse_sampler.py:117-132)."""
+        import scipy.sparse as sp
+
+        off = self.offsets.cpu().numpy()
+        col = self.col.cpu().numpy()
+        val = self.val.cpu().numpy()
+        n = self.n_rows
+        mats = []
+        for s in range(self.n_steps):
+            ip = off[s * n: (s + 1) * n + 1]
+            b, e = int(ip[0]), int(ip[-1])
+            m = sp.csr_matrix((val[b:e], col[b:e], (ip - b).astype(np.int32 if e - b < 2 ** 31 else np.int64)),
+                              shape=(n, self.n_cols))
+            m.has_sorted_indices = True
+            mats.append(m)
+        return mats
+
+    def to_dense_tensor(self) -> np.ndarray:
+        """(n_rows, n_cols, L) float64 -- RandomWalk's output layout (sampler.py:196-201)."""
+        out = np.zeros((self.n_rows, self.n_cols, self.n_steps), dtype=float)
+        for s, m in enumerate(self.to_scipy()):
+            coo = m.tocoo()
+            out[coo.row, coo.col, s] = coo.data
+        return out
+
+    @staticmethod
+    def concat_rows(parts: Sequence["StepMatrices"]) -> "StepMatrices":
+        if len(parts) == 1:
+            return parts[0]
+        L, n_cols = parts[0].n_steps, parts[0].n_cols
+        dev = parts[0].device
+        cols, vals, cnts = [], [], []
+        for s in range(L):
+            for p in parts:
+                o = p.offsets[s * p.n_rows: (s + 1) * p.n_rows + 1]
+                b, e = int(o[0]), int(o[-1])
+                cols.append(p.col[b:e])
+                vals.append(p.val[b:e])
+                cnts.append(o[1:] - o[:-1])
+        counts = torch.cat(cnts) if cnts else torch.zeros(0, dtype=torch.int64, device=dev)
+        offsets = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        n_rows = sum(p.n_rows for p in parts)
+        return StepMatrices(offsets, torch.cat(cols), torch.cat(vals), n_rows, n_cols, L, parts[0].row_lo,
+                            sum(p.visits for p in parts))
+
+
+def _steps_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: int) -> StepMatrices:
+    L = cfg.max_walk_length
+    dev = st.stage_col.device
+    offsets = scan_counts(st.row_cnt, st.n_rows, L, _lib.ORDER_STEP_MAJOR, i64=True)
+    total = int(offsets[-1].item())
+    col = torch.empty(max(1, total), dtype=torch.int32, device=dev)[:total]
+    val = torch.empty(max(1, total), dtype=torch.float64, device=dev)[:total]
+    check(_lib.lib().grf_compact_steps(_ptr(st.stage_col), _ptr(st.stage_sum), _ptr(st.row_cnt), _ptr(offsets),
+                                       st.n_rows, L, st.stride, cfg.walks_per_node, scale_mode, _ptr(col), _ptr(val),
+                                       _stream(dev)))
+    return StepMatrices(offsets, col, val, st.n_rows, n_cols, L, st.row_lo)
+
+
+def build_step_matrices(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
+                        scale_mode: int = _lib.SCALE_MUL_RECIP,
+                        max_stage_bytes: int = _MAX_STAGE_BYTES) -> StepMatrices:
+    """Walker + compaction into the reference's per-length CSR layout (on device)."""
+    cfg.validate()
+    start_hi = graph.n_nodes if start_hi is None else start_hi
+    stride = _lib.lib().grf_walk_stage_stride(cfg.walks_per_node, cfg.max_walk_length)
+    visits = torch.zeros(1, dtype=torch.int64, device=graph.device)
+    parts = []
+    for lo, hi in _row_chunks(start_lo, start_hi, stride, max_stage_bytes):
+        st = run_walker(graph, cfg, lo, hi, visits=visits)
+        parts.append(_steps_from_staging(st, cfg, graph.n_nodes, scale_mode))
+        del st
+    out = StepMatrices.concat_rows(parts)
+    out.visits = int(visits.item())
+    return out
+
+
+class PhiBlocks:
+    """Phi in the matvec layout: block CSR over (row, walk length) with
+    {int32 col, float32 val} entries, plus the same for Phi^T (built once --
+    the reference re-sorts every M_l on every forward, sparse_lo.py:23-25).
+
+    ``matvec`` is the kernel matvec ``Phi[x1] (Phi[x2]^T V)`` with
+    ``Phi = sum_l f[l] M_l`` (sparse_grf_kernel.py:24-62); f is applied at
+    matvec time so it can be a learnable parameter."""
+
+    def __init__(self, blk_ptr, entries, n_rows, n_cols, n_steps, row_lo=0, visits=0):
+        self.blk_ptr, self.entries = blk_ptr, entries
+        self.n_rows, self.n_cols, self.n_steps, self.row_lo = n_rows, n_cols, n_steps, row_lo
+        self.tblk_ptr = None
+        self.tentries = None
+        self.visits = visits
+        self._ws = {}
+
+    @property
+    def device(self):
+        return self.blk_ptr.device
+
+    @property
+    def nnz(self) -> int:
+        return int(self.entries.shape[0])
+
+    def build_transpose(self) -> "PhiBlocks":
+        if self.tblk_ptr is not None:
+            return self
+        L = _lib.lib()
+        dev = self.device
+        n_seg = self.n_cols * self.n_steps
+        tcnt = torch.empty(max(1, n_seg), dtype=torch.int32, device=dev)
+        check(L.grf_transpose_count(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
+                                    _ptr(tcnt), _stream(dev)))
+        self.tblk_ptr = scan_counts(tcnt, self.n_cols, self.n_steps, _lib.ORDER_ROW_MAJOR, i64=False)
+        cursor = torch.empty(n_seg + 1, dtype=torch.int32, device=dev)
+        self.tentries = torch.empty((max(1, self.nnz), 2), dtype=torch.int32, device=dev)[: self.nnz]
+        check(L.grf_transpose_fill(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
+                                   _ptr(self.tblk_ptr), _ptr(cursor), _ptr(self.tentries), _stream(dev)))
+        return self
+
+    def c_struct(self) -> GrfPhi:
+        return GrfPhi(self.n_rows, self.n_cols, self.row_lo, self.n_steps, self.blk_ptr.data_ptr(),
+                      self.entries.data_ptr() if self.nnz else None,
+                      None if self.tblk_ptr is None else self.tblk_ptr.data_ptr(),
+                      None if self.tentries is None or not self.nnz else self.tentries.data_ptr())
+
+    @staticmethod
+    def _ids(x, dev):
+        if x is None:
+            return None
+        x = torch.as_tensor(x, device=dev)
+        return x.flatten().to(torch.int32).contiguous()
+
+    def _f(self, f) -> torch.Tensor:
+        f = torch.as_tensor(f, device=self.device).detach().to(torch.float32).contiguous()
+        if f.numel() != self.n_steps:
+            raise ValueError(f"modulator has {f.numel()} entries, Phi has {self.n_steps} walk lengths")
+        return f
+
+    @staticmethod
+    def _rhs(x, dev) -> torch.Tensor:
+        x = torch.as_tensor(x, device=dev).detach()
+        if x.dim() != 2:
+            raise ValueError("right-hand side must be 2-D [rows, t]")
+        x = x.to(torch.float32)
+        if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+            x = x.contiguous()
+        return x
+
+    def apply_t(self, f, v, rows=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """U = Phi[rows]^T v: v [n2, t] -> U [n_cols, t] (this GPU's partial sum
+        when Phi is row-sharded).  ``out`` may be a [n_cols, >=t] float32 buffer."""
+        dev = self.device
+        self.build_transpose()
+        f = self._f(f)
+        v = self._rhs(v, dev)
+        rows = self._ids(rows, dev)
+        n2, t = v.shape
+        if n2 != (self.n_rows if rows is None else rows.numel()):
+            raise ValueError("rhs has the wrong number of rows")
+        if out is None:
+            ldu = (t + 3) // 4 * 4
+            out = torch.empty((self.n_cols, ldu), dtype=torch.float32, device=dev)
+        u = out
+        vfull = None
+        if rows is not None:
+            vfull = torch.empty((max(1, self.n_rows), u.stride(0)), dtype=torch.float32, device=dev)
+        phi = self.c_struct()
+        check(_lib.lib().grf_phi_matvec(
+            ctypes.byref(phi), _ptr(f), None, self.n_rows, _ptr(rows), n2, _ptr(v), v.stride(0), None, 0,
+            _ptr(u), u.stride(0), _ptr(vfull), t, 1, _stream(dev)))
+        return u[:, :t]
+
+    def apply(self, f, u, rows=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """out = Phi[rows] u: u [n_cols, t] -> [n1, t]."""
+        dev = self.device
+        f = self._f(f)
+        u = self._rhs(u, dev)
+        rows = self._ids(rows, dev)
+        if u.shape[0] != self.n_cols:
+            raise ValueError("rhs has the wrong number of rows")
+        t = u.shape[1]
+        n1 = self.n_rows if rows is None else rows.numel()
+        if out is None:
+            out = torch.zeros((n1, t), dtype=torch.float32, device=dev)
+        elif out.shape != (n1, t) or out.dtype != torch.float32 or out.stride(1) != 1:
+            raise ValueError("out must be a float32 [n1, t] tensor with unit column stride")
+        phi = self.c_struct()
+        check(_lib.lib().grf_phi_matvec(
+            ctypes.byref(phi), _ptr(f), _ptr(rows), n1, None, self.n_rows, None, 0, _ptr(out), out.stride(0),
+            _ptr(u), u.stride(0), None, t, 2, _stream(dev)))
+        return out
+
+    def matvec(self, f, v, x1=None, x2=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """out[n1, t] = Phi[x1] (Phi[x2]^T v);  v is [n2, t] (or [n2]) on this device."""
+        v = torch.as_tensor(v, device=self.device)
+        squeeze = v.dim() == 1
+        if squeeze:
+            v = v[:, None]
+        t = v.shape[1]
+        ldu = (t + 3) // 4 * 4
+        key = ("u", ldu)
+        if key not in self._ws:
+            self._ws[key] = torch.empty((self.n_cols, ldu), dtype=torch.float32, device=self.device)
+        u = self.apply_t(f, v, rows=x2, out=self._ws[key])
+        res = self.apply(f, u, rows=x1, out=out)
+        return res[:, 0] if squeeze else res
+
+    def t_matvec(self, f, v, x2=None) -> torch.Tensor:
+        """U = Phi[x2]^T v  ([n_cols, t]) in a fresh buffer."""
+        return self.apply_t(f, v, rows=x2)
+
+    def fgrad(self, f, left, right, x1=None, x2=None) -> torch.Tensor:
+        """d/df of sum(left * (Phi[x1] Phi[x2]^T right)) -- a per-length reduction.
+
+        left [n1, t], right [n2, t]."""
+        dev = self.device
+        L = _lib.lib()
+        left = torch.as_tensor(left, device=dev).to(torch.float32).contiguous()
+        right = torch.as_tensor(right, device=dev).to(torch.float32).contiguous()
+        if left.dim() == 1:
+            left, right = left[:, None], right[:, None]
+        t = left.shape[1]
+        x1 = self._ids(x1, dev)
+        x2 = self._ids(x2, dev)
+        p = self.t_matvec(f, right, x2=x2)   # Phi[x2]^T right
+        q = self.t_matvec(f, left, x2=x1)    # Phi[x1]^T left
+        grad = torch.zeros(self.n_steps, dtype=torch.float32, device=dev)
+        phi = self.c_struct()
+        n1 = self.n_rows if x1 is None else x1.numel()
+        n2 = self.n_rows if x2 is None else x2.numel()
+        check(L.grf_phi_fgrad(ctypes.byref(phi), _ptr(x1), n1, _ptr(left), left.stride(0), _ptr(p), p.stride(0), t,
+                              _ptr(grad), _stream(dev)))
+        check(L.grf_phi_fgrad(ctypes.byref(phi), _ptr(x2), n2, _ptr(right), right.stride(0), _ptr(q), q.stride(0),
+                              t, _ptr(grad), _stream(dev)))
+        return grad
+
+    # ---- construction ----------------------------------------------------
+    @staticmethod
+    def from_step_matrices(sm: StepMatrices, transpose: bool = True) -> "PhiBlocks":
+        """float32 Phi blocks from the reference layout (values rounded like
+        torch ``.float()``, graph_preprocessor.py:131-139)."""
+        L = _lib.lib()
+        dev = sm.device
+        row_cnt = torch.empty(max(1, sm.n_rows * sm.n_steps), dtype=torch.int32, device=dev)
+        check(L.grf_count_from_steps(_ptr(sm.offsets), sm.n_rows, sm.n_steps, _ptr(row_cnt), _stream(dev)))
+        blk_ptr = scan_counts(row_cnt, sm.n_rows, sm.n_steps, _lib.ORDER_ROW_MAJOR, i64=True)
+        total = int(blk_ptr[-1].item())
+        if total >= 2 ** 31:
+            raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
+        blk_ptr = blk_ptr.to(torch.int32)
+        entries = torch.empty((max(1, total), 2), dtype=torch.int32, device=dev)[:total]
+        check(L.grf_blocks_from_steps(_ptr(sm.offsets), _ptr(sm.col), _ptr(sm.val), _ptr(blk_ptr), sm.n_rows,
+                                      sm.n_steps, _ptr(entries), _stream(dev)))
+        phi = PhiBlocks(blk_ptr, entries, sm.n_rows, sm.n_cols, sm.n_steps, sm.row_lo, sm.visits)
+        return phi.build_transpose() if transpose else phi
+
+    @staticmethod
+    def concat_rows(parts: Sequence["PhiBlocks"]) -> "PhiBlocks":
+        if len(parts) == 1:
+            return parts[0]
+        ptrs, base = [], 0
+        for p in parts:
+            ptrs.append(p.blk_ptr[:-1].to(torch.int64) + base)
+            base += p.nnz
+        if base >= 2 ** 31:
+            raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
+        ptrs.append(torch.tensor([base], dtype=torch.int64, device=parts[0].device))
+        return PhiBlocks(torch.cat(ptrs).to(torch.int32), torch.cat([p.entries for p in parts]),
+                         sum(p.n_rows for p in parts), parts[0].n_cols, parts[0].n_steps, parts[0].row_lo,
+                         sum(p.visits for p in parts))
+
+    def to_scipy_steps(self):
+        """float32 step matrices back on the host (tests / interchange)."""
+        import scipy.sparse as sp
+
+        ptr = self.blk_ptr.cpu().numpy().astype(np.int64)
+        ent = self.entries.cpu().numpy()
+        cols = ent[:, 0] if self.nnz else np.zeros(0, np.int32)
+        vals = ent[:, 1].copy().view(np.float32) if self.nnz else np.zeros(0, np.float32)
+        L, n = self.n_steps, self.n_rows
+        mats = []
+        for s in range(L):
+            b = ptr[s:n * L:L] if n else np.zeros(0, np.int64)
+            e = ptr[s + 1:n * L + 1:L] if n else np.zeros(0, np.int64)
+            cnt = e - b
+            ip = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(cnt, out=ip[1:])
+            idx = np.concatenate([np.arange(bb, ee) for bb, ee in zip(b, e)]) if n and ip[-1] else np.zeros(0, np.int64)
+            mats.append(sp.csr_matrix((vals[idx], cols[idx], ip), shape=(n, self.n_cols)))
+        return mats
+
+
+def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: int) -> PhiBlocks:
+    L = cfg.max_walk_length
+    dev = st.stage_col.device
+    blk_ptr = scan_counts(st.row_cnt, st.n_rows, L, _lib.ORDER_ROW_MAJOR, i64=True)
+    total = int(blk_ptr[-1].item())
+    if total >= 2 ** 31:
+        raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
+    blk_ptr = blk_ptr.to(torch.int32)
+    entries = torch.empty((max(1, total), 2), dtype=torch.int32, device=dev)[:total]
+    check(_lib.lib().grf_compact_blocks(_ptr(st.stage_col), _ptr(st.stage_sum), _ptr(st.row_cnt), _ptr(blk_ptr),
+                                        st.n_rows, L, st.stride, cfg.walks_per_node, scale_mode, _ptr(entries),
+                                        _stream(dev)))
+    return PhiBlocks(blk_ptr, entries, st.n_rows, n_cols, L, st.row_lo)
+
+
+def build_phi_blocks(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
+                     scale_mode: int = _lib.SCALE_MUL_RECIP, transpose: bool = True,
+                     max_stage_bytes: int = _MAX_STAGE_BYTES) -> PhiBlocks:
+    """Walker + compaction straight into the matvec layout (no float64 CSR, no host round trip)."""
+    cfg.validate()
+    start_hi = graph.n_nodes if start_hi is None else start_hi
+    stride = _lib.lib().grf_walk_stage_stride(cfg.walks_per_node, cfg.max_walk_length)
+    visits = torch.zeros(1, dtype=torch.int64, device=graph.device)
+    parts = []
+    for lo, hi in _row_chunks(start_lo, start_hi, stride, max_stage_bytes):
+        st = run_walker(graph, cfg, lo, hi, visits=visits)
+        parts.append(_blocks_from_staging(st, cfg, graph.n_nodes, scale_mode))
+        del st
+    phi = PhiBlocks.concat_rows(parts)
+    phi.row_lo = start_lo
+    phi.visits = visits  # device counter; int(phi.visits) syncs
+    return phi.build_transpose() if transpose else phi
+
+
+def phi_blocks_from_scipy(mats, device=None, row_lo: int = 0, transpose: bool = True) -> PhiBlocks:
+    """Phi blocks from a list of scipy CSR step matrices (e.g. one of the
+    reference's pickle caches, graph_preprocessor.py:141-165)."""
+    dev = _device(device)
+    n_rows, n_cols = mats[0].shape
+    L = len(mats)
+    offs, cols, vals, base = [], [], [], 0
+    for m in mats:
+        m = m.tocsr()
+        if not m.has_sorted_indices:
+            m = m.sorted_indices()
+        offs.append(m.indptr[:-1].astype(np.int64) + base)
+        base += m.nnz
+        cols.append(m.indices.astype(np.int32))
+        vals.append(m.data.astype(np.float64))
+    offs.append(np.array([base], dtype=np.int64))
+    # step-major offsets need one terminator per step boundary == next step's first offset: already contiguous
+    sm = StepMatrices(torch.from_numpy(np.concatenate(offs)).to(dev), torch.from_numpy(np.concatenate(cols)).to(dev),
+                      torch.from_numpy(np.concatenate(vals)).to(dev), n_rows, n_cols, L, row_lo)
+    return PhiBlocks.from_step_matrices(sm, transpose=transpose)
+
+
+def phi_blocks_from_torch_csr(tensors, row_lo: int = 0, transpose: bool = True) -> PhiBlocks:
+    """Phi blocks from one torch sparse-CSR tensor or a list of them (one per
+    walk length) already on the GPU -- the layout ``from_scipy_csr`` produces
+    (graph_preprocessor.py:117-139: int64 indices, float32 values)."""
+    if isinstance(tensors, torch.Tensor):
+        tensors = [tensors]
+    dev = _device(tensors[0].device)
+    n_rows, n_cols = tensors[0].shape
+    offs, cols, vals, base = [], [], [], 0
+    for t in tensors:
+        if not t.is_sparse_csr:
+            raise ValueError("Input tensor must be a sparse CSR tensor")
+        crow = t.crow_indices().to(torch.int64)
+        offs.append(crow[:-1] + base)
+        base += int(t.values().numel())
+        cols.append(t.col_indices().to(torch.int32))
+        vals.append(t.values().to(torch.float64))
+    offs.append(torch.tensor([base], dtype=torch.int64, device=dev))
+    sm = StepMatrices(torch.cat(offs).contiguous(), torch.cat(cols).contiguous(), torch.cat(vals).contiguous(),
+                      n_rows, n_cols, len(tensors), row_lo)
+    return PhiBlocks.from_step_matrices(sm, transpose=transpose)

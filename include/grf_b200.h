@@ -1,0 +1,172 @@
+/*
+ * grf_b200 -- C ABI of the B200-native Graph-Random-Feature (GRF) hot path.
+ *
+ * This header is the drop-in boundary.  The reference
+ * (MatthewZhang473/Efficient-Gaussian-Process-on-Graphs) is pure Python and has
+ * no FFI of its own; each entry point below names the reference code whose work
+ * it replaces (paths relative to the reference root).  The ctypes binding a
+ * maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host";
+ *   - the caller owns every buffer; the library allocates nothing persistent;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = OK, negative = error (grf_last_error() has the text);
+ *   - no torch types, no C++ types: plain pointers and sizes.
+ *
+ * Data layout in HBM
+ *   walk graph      CSR: row_ptr int32[N+1], col_idx int32[nnz], val double[nnz]
+ *   staging         row r of this GPU owns stage_*[r*stride .. r*stride+stride),
+ *                   stride = 1 + (L-1)*W (worst case); inside it the per-length
+ *                   segments follow each other (length 0 first), each sorted by
+ *                   column with duplicates merged; row_cnt[r*L + l] = its size
+ *   step matrices   (reference layout) one CSR per walk length l, concatenated:
+ *                   offsets int64[L*n_rows + 1] step-major, col int32, val double
+ *   Phi blocks      (matvec layout) block CSR, row-major over (row, length):
+ *                   blk_ptr int32[n_rows*L + 1], entries {int32 col; float val}
+ *   Phi^T blocks    same, over (column, length), entries {int32 local_row; float val}
+ */
+#ifndef GRF_B200_H
+#define GRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRF_B200_ABI_VERSION 1
+
+enum {
+    GRF_OK = 0,
+    GRF_ERR_INVALID = -1,     /* bad argument (the wrapper raises ValueError) */
+    GRF_ERR_CUDA = -2,        /* CUDA runtime failure (RuntimeError) */
+    GRF_ERR_UNSUPPORTED = -3  /* size outside what this build supports */
+};
+
+enum { GRF_DRAW_PHILOX = 0, GRF_DRAW_REPLAY = 1 };
+/* load rule: sparse_sampler.py:54 & sampler.py:58 | sampler.py:183 | sampler.py:180-181 */
+enum { GRF_LOAD_CUMULATIVE = 0, GRF_LOAD_LAST_STEP = 1, GRF_LOAD_ABLATION = 2 };
+/* "/ num_walks": scipy csr / W == * (1/W) (sparse_sampler.py:130) | true division (sampler.py:201) */
+enum { GRF_SCALE_MUL_RECIP = 0, GRF_SCALE_DIV = 1 };
+enum { GRF_ORDER_ROW_MAJOR = 0, GRF_ORDER_STEP_MAJOR = 1 };
+
+typedef struct {
+    int32_t col;
+    float val;
+} GrfEntry;
+
+/* The walk graph = what SparseRandomWalk.__init__ keeps (sparse_sampler.py:62-70):
+ * indptr / indices (int32) and data.astype(float). */
+typedef struct {
+    int64_t n_nodes;
+    int64_t nnz;
+    const int32_t *row_ptr;
+    const int32_t *col_idx;
+    const double *val;
+} GrfGraph;
+
+/* Arguments of _worker_walks (sparse_sampler.py:26-31) plus the shard and the
+ * draw source. */
+typedef struct {
+    int64_t start_lo, start_hi; /* this GPU's start nodes = its rows of every M_l */
+    int32_t walks_per_node;     /* W */
+    int32_t max_walk_length;    /* L */
+    double p_halt;
+    int32_t draw_mode;          /* GRF_DRAW_* */
+    int32_t load_mode;          /* GRF_LOAD_* */
+    uint64_t seed;              /* Philox key (native mode) */
+    /* replay mode: the reference's PCG64 draws, [walk_id*L + step], walk_id =
+     * start*W + w; trace_u = rng.random() (NaN where none was drawn), trace_k =
+     * rng.integers(deg) (-1 where none) -- sparse_sampler.py:47,51 */
+    const double *trace_u;
+    const int32_t *trace_k;
+} GrfWalkCfg;
+
+typedef struct {
+    int64_t n_rows;  /* local rows (start nodes owned by this GPU) */
+    int64_t n_cols;  /* N */
+    int64_t row_lo;  /* global index of local row 0 */
+    int32_t n_steps; /* L */
+    const int32_t *blk_ptr;   /* [n_rows*L + 1] */
+    const GrfEntry *entries;  /* col = global column */
+    const int32_t *tblk_ptr;  /* [n_cols*L + 1] */
+    const GrfEntry *tentries; /* col = LOCAL row */
+} GrfPhi;
+
+int grf_abi_version(void);
+const char *grf_last_error(void); /* host string, thread-local */
+
+/* Staging entries per row the walker may write: 1 + (L-1)*W. */
+int64_t grf_walk_stage_stride(int32_t walks_per_node, int32_t max_walk_length);
+
+/* Replaces sparse_sampler.py:26-56 (_worker_walks) and the dict merge at
+ * :110-114 (dense twin sampler.py:30-61, :148-186): runs W halting walks from
+ * every start node in [start_lo, start_hi), applies the load update in
+ * registers, and merges equal (length, node) visits of one start node in
+ * shared memory -- loads added in walk order into a double, as the reference's
+ * defaultdict does.  Writes stage_col / stage_sum (unscaled sums) and row_cnt;
+ * *visits_out (device, may be NULL) += number of walk-steps executed. */
+int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t stage_stride, int32_t *stage_col,
+             double *stage_sum, int32_t *row_cnt, unsigned long long *visits_out, void *stream);
+
+/* Exclusive prefix sum of row_cnt[n_rows][L] in row-major or step-major order;
+ * offsets has n_rows*L + 1 elements (last = total).  out_is_i64 selects
+ * int64_t / int32_t output.  workspace: grf_scan_workspace_bytes(n_rows*L). */
+int64_t grf_scan_workspace_bytes(int64_t n_items);
+int grf_scan_counts(const int32_t *row_cnt, int64_t n_rows, int32_t n_steps, int32_t order, void *offsets,
+                    int32_t out_is_i64, void *workspace, void *stream);
+
+/* Replaces sparse_sampler.py:117-130 (COO -> CSR per length, "/ num_walks") and
+ * sampler.py:188-203: staging -> L concatenated CSR matrices (step-major). */
+int grf_compact_steps(const int32_t *stage_col, const double *stage_sum, const int32_t *row_cnt,
+                      const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps, int64_t stage_stride,
+                      int32_t walks_per_node, int32_t scale_mode, int32_t *out_col, double *out_val, void *stream);
+
+/* Replaces graph_preprocessor.py:117-139 (from_scipy_csr: float32 values) for
+ * the matvec: staging -> Phi blocks.  val = (float)(sum * (1/W)). */
+int grf_compact_blocks(const int32_t *stage_col, const double *stage_sum, const int32_t *row_cnt,
+                       const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int64_t stage_stride,
+                       int32_t walks_per_node, int32_t scale_mode, GrfEntry *entries, void *stream);
+
+/* Same conversion from the reference layout (a list of L CSR matrices in
+ * device memory, e.g. loaded from one of the reference's pickle caches). */
+int grf_blocks_from_steps(const int64_t *offsets_step_major, const int32_t *col, const double *val,
+                          const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, GrfEntry *entries, void *stream);
+int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps, int32_t *row_cnt,
+                         void *stream);
+
+/* Replaces sparse_lo.py:23-25 (.t().to_sparse_csr(), redone on every forward in
+ * the reference): build Phi^T blocks once.  count -> grf_scan_counts -> fill. */
+int grf_transpose_count(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
+                        int32_t n_steps, int32_t *tcnt /* [n_cols*L], zeroed by the call */, void *stream);
+int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
+                       int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor /* [n_cols*L + 1] scratch */,
+                       GrfEntry *tentries, void *stream);
+
+/* Replaces the 2L SparseLinearOperator._matmul calls (sparse_lo.py:16-18), the
+ * ConstantMul/Sum operators (sparse_grf_kernel.py:59-61) and the row selection
+ * (sparse_grf_kernel.py:32-41) of one kernel matvec
+ *     out = Phi[x1] (Phi[x2]^T V),   Phi = sum_l f[l] M_l
+ * x1 / x2: GLOBAL row ids (int32) or NULL for "all local rows"; ids outside
+ * [row_lo, row_lo + n_rows) are not this GPU's and are skipped (their out rows
+ * are left untouched).  V [n2][ldv], out [n1][ldo], U workspace [n_cols][ldu]
+ * (= Phi[x2]^T V, this GPU's partial sum: the multi-GPU caller all-reduces it
+ * between the two halves); vfull workspace [n_rows][ldu], used when x2 != NULL.
+ * which: 1 = first half only (U), 2 = second half only (out from U), 3 = both. */
+int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t n1, const int32_t *x2,
+                   int64_t n2, const float *v, int64_t ldv, float *out, int64_t ldo, float *u, int64_t ldu,
+                   float *vfull, int32_t t, int32_t which, void *stream);
+
+/* Per-length reduction for the modulator gradient (what upstream
+ * _bilinear_derivative yields for sparse_grf_kernel.py:51-62):
+ *   grad[l] += sum_k sum_t left[k][t] * (M_l[x[k], :] @ P)[t]
+ * P [n_cols][ldp].  Call twice (left with P = Phi[x2]^T right, right with
+ * P = Phi[x1]^T left) for the full derivative.  grad: float[L], accumulated. */
+int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, const float *left, int64_t ldl, const float *p,
+                  int64_t ldp, int32_t t, float *grad, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRF_B200_H */

@@ -1,0 +1,255 @@
+"""-m gpu parity tests of the Phi blocks, the transpose and the fused Phi(Phi^T V) matvec.
+
+Tolerance: the matvec computes in fp32 (the reference's dtype on device,
+graph_preprocessor.py:131-139); results are compared with a float64 scipy
+evaluation of the same fp32-rounded Phi to fp32 round-off:
+|got - want| <= 2e-5 * max|want| (stated per test)."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from gpu_util import grid_graph, powerlaw_graph, random_graph
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a B200"
+    from grf_b200 import _lib, engine
+    from oracle import c_oracle, grf_oracle
+
+    return dict(torch=torch, lib=_lib, eng=engine, c=c_oracle, o=grf_oracle)
+
+
+@pytest.fixture(scope="module")
+def case(env):
+    """A Phi built natively on the GPU + the same step matrices on the host."""
+    eng = env["eng"]
+    lap = env["o"].normalized_laplacian_sparse(random_graph(700, 2400, 5, weighted=True))
+    g = eng.DeviceGraph.from_scipy(lap)
+    cfg = eng.WalkConfig(40, 0.1, 4, seed=11)
+    steps = eng.build_step_matrices(g, cfg)
+    phi = eng.build_phi_blocks(g, cfg)
+    return dict(lap=lap, steps=steps, mats=steps.to_scipy(), phi=phi, cfg=cfg, g=g)
+
+
+def _close(got, want, rtol=RTOL):
+    scale = max(1e-30, float(np.max(np.abs(want))))
+    return float(np.max(np.abs(got - want))) <= rtol * scale
+
+
+def test_blocks_hold_float32_rounding_of_the_step_matrices(env, case):
+    """entries == torch .float() of the float64 step matrices (graph_preprocessor.py:131-139), bit for bit,
+    whether built straight from staging or from the reference layout."""
+    eng = env["eng"]
+    via_steps = eng.PhiBlocks.from_step_matrices(case["steps"])
+    for phi in (case["phi"], via_steps):
+        back = phi.to_scipy_steps()
+        for s, m in enumerate(case["mats"]):
+            assert np.array_equal(back[s].indptr, m.indptr) and np.array_equal(back[s].indices, m.indices)
+            assert np.array_equal(back[s].data.view(np.int32), m.data.astype(np.float32).view(np.int32))
+    assert int(case["phi"].visits) == case["steps"].visits
+
+
+def test_blocks_from_scipy_and_torch_csr(env, case):
+    eng, torch = env["eng"], env["torch"]
+    a = eng.phi_blocks_from_scipy(case["mats"])
+    ts = []
+    for m in case["mats"]:
+        ts.append(torch.sparse_csr_tensor(torch.from_numpy(m.indptr).long(), torch.from_numpy(m.indices).long(),
+                                          torch.from_numpy(m.data).float(), m.shape).cuda())
+    b = eng.phi_blocks_from_torch_csr(ts)
+    for phi in (a, b):
+        assert torch.equal(phi.blk_ptr, case["phi"].blk_ptr)
+        assert torch.equal(phi.entries, case["phi"].entries)
+
+
+def test_transpose_is_exact_and_row_sorted(env, case):
+    phi = case["phi"]
+    L, n = phi.n_steps, phi.n_cols
+    tptr = phi.tblk_ptr.cpu().numpy().astype(np.int64)
+    tent = phi.tentries.cpu().numpy()
+    rows, vals = tent[:, 0], tent[:, 1].copy().view(np.float32)
+    for s, m in enumerate(case["mats"]):
+        mt = m.astype(np.float32).T.tocsr()
+        mt.sort_indices()
+        for c in range(n):
+            b, e = tptr[c * L + s], tptr[c * L + s + 1]
+            assert np.array_equal(rows[b:e], mt.indices[mt.indptr[c]:mt.indptr[c + 1]])
+            assert np.array_equal(vals[b:e], mt.data[mt.indptr[c]:mt.indptr[c + 1]])
+
+
+def test_transpose_with_hub_columns_uses_the_long_segment_sort(env):
+    eng = env["eng"]
+    lap = env["o"].normalized_laplacian_sparse(powerlaw_graph(4000, 30000, 2))
+    g = eng.DeviceGraph.from_scipy(lap)
+    phi = eng.build_phi_blocks(g, eng.WalkConfig(30, 0.1, 3, seed=3))
+    tptr = phi.tblk_ptr.cpu().numpy().astype(np.int64)
+    seg = np.diff(tptr)
+    assert seg.max() > 48, "test graph should have hub columns"
+    rows = phi.tentries.cpu().numpy()[:, 0]
+    for g0 in np.flatnonzero(seg > 1):
+        r = rows[tptr[g0]:tptr[g0 + 1]]
+        assert np.all(r[1:] > r[:-1])
+    # and it is the same multiset as Phi
+    back = phi.to_scipy_steps()
+    assert sum(m.nnz for m in back) == len(rows)
+
+
+@pytest.mark.parametrize("t", [1, 2, 3, 4, 8, 12, 16, 17, 32, 64, 65, 130])
+def test_matvec_matches_float64(env, case, t):
+    torch, o = env["torch"], env["o"]
+    phi = case["phi"]
+    rng = np.random.default_rng(t)
+    f = rng.standard_normal(phi.n_steps)
+    v = rng.standard_normal((phi.n_rows, t)).astype(np.float32)
+    got = phi.matvec(torch.tensor(f), torch.tensor(v).cuda()).cpu().numpy()
+    mats32 = [m.astype(np.float32) for m in case["mats"]]
+    want = o.phi_matvec_f64(mats32, f.astype(np.float32), v)
+    assert got.shape == (phi.n_rows, t)
+    assert _close(got, want)
+
+
+def test_matvec_vector_rhs_and_reference_op_sequence(env, case):
+    """1-D rhs; and agreement with the reference's own op sequence (torch CPU CSR, fp32)."""
+    torch, o = env["torch"], env["o"]
+    phi = case["phi"]
+    rng = np.random.default_rng(0)
+    f = rng.standard_normal(phi.n_steps).astype(np.float32)
+    v = rng.standard_normal((phi.n_rows, 16)).astype(np.float32)
+    got = phi.matvec(torch.tensor(f), torch.tensor(v).cuda()).cpu().numpy()
+    ref = o.phi_matvec_reference_torch(case["mats"], f, v)
+    assert _close(got, ref, rtol=1e-4)
+    g1 = phi.matvec(torch.tensor(f), torch.tensor(v[:, 0]).cuda()).cpu().numpy()
+    assert g1.shape == (phi.n_rows,) and _close(g1, got[:, 0], rtol=1e-6)
+
+
+@pytest.mark.parametrize("t", [1, 16, 17])
+def test_matvec_row_subsets(env, case, t):
+    """K[x1, x2] @ v with arbitrary (unsorted, repeated) index sets -- sparse_grf_kernel.py:32-41."""
+    torch, o = env["torch"], env["o"]
+    phi = case["phi"]
+    rng = np.random.default_rng(100 + t)
+    x1 = rng.integers(0, phi.n_rows, size=211)
+    x2 = np.r_[rng.permutation(phi.n_rows)[:300], [5, 5, 17]]       # with repeats
+    f = rng.standard_normal(phi.n_steps).astype(np.float32)
+    v = rng.standard_normal((x2.size, t)).astype(np.float32)
+    mats32 = [m.astype(np.float32) for m in case["mats"]]
+    want = o.phi_matvec_f64(mats32, f, v, x1=x1, x2=x2)
+    got = phi.matvec(torch.tensor(f), torch.tensor(v).cuda(), x1=torch.tensor(x1).cuda(),
+                     x2=torch.tensor(x2).cuda()).cpu().numpy()
+    assert got.shape == (211, t) and _close(got, want)
+    # x as float column tensors, the way the reference's models pass them (x.long().flatten())
+    got2 = phi.matvec(torch.tensor(f), torch.tensor(v).cuda(), x1=torch.tensor(x1, dtype=torch.float32)[:, None].cuda(),
+                      x2=torch.tensor(x2, dtype=torch.float32)[:, None].cuda()).cpu().numpy()
+    assert np.array_equal(got, got2)
+
+
+def test_apply_and_apply_t_are_the_two_halves(env, case):
+    torch = env["torch"]
+    phi = case["phi"]
+    rng = np.random.default_rng(9)
+    f = rng.standard_normal(phi.n_steps).astype(np.float32)
+    v = rng.standard_normal((phi.n_rows, 8)).astype(np.float32)
+    mats32 = [m.astype(np.float32).astype(np.float64) for m in case["mats"]]
+    dense = sum(float(fl) * m for fl, m in zip(f, mats32)).toarray()
+    u = phi.apply_t(torch.tensor(f), torch.tensor(v).cuda())
+    assert _close(u.cpu().numpy(), dense.T @ v)
+    w = phi.apply(torch.tensor(f), u)
+    assert _close(w.cpu().numpy(), dense @ (dense.T @ v))
+
+
+def test_matvec_is_linear_and_symmetric_psd(env, case):
+    """Size-independent properties: linearity in V and in f (bilinear), <v, K v> >= 0."""
+    torch = env["torch"]
+    phi = case["phi"]
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    f = torch.randn(phi.n_steps, device="cuda", generator=gen)
+    a = torch.randn(phi.n_rows, 16, device="cuda", generator=gen)
+    b = torch.randn(phi.n_rows, 16, device="cuda", generator=gen)
+    ka, kb, kab = phi.matvec(f, a).clone(), phi.matvec(f, b).clone(), phi.matvec(f, 2 * a - 3 * b).clone()
+    assert torch.allclose(kab, 2 * ka - 3 * kb, rtol=1e-4, atol=1e-4 * float(kab.abs().max()))
+    assert float((a * ka).sum()) >= 0
+    assert torch.allclose((a * kb).sum(), (b * ka).sum(), rtol=1e-3)
+
+
+def test_fgrad_matches_float64_and_finite_differences(env, case):
+    torch, o = env["torch"], env["o"]
+    phi = case["phi"]
+    rng = np.random.default_rng(4)
+    f = rng.standard_normal(phi.n_steps).astype(np.float32)
+    x1 = rng.permutation(phi.n_rows)[:250]
+    x2 = rng.permutation(phi.n_rows)[:310]
+    for t in (1, 16, 5):
+        left = rng.standard_normal((x1.size, t)).astype(np.float32)
+        right = rng.standard_normal((x2.size, t)).astype(np.float32)
+        mats32 = [m.astype(np.float32) for m in case["mats"]]
+        want = o.phi_fgrad_f64(mats32, f, left, right, x1=x1, x2=x2)
+        got = phi.fgrad(torch.tensor(f), torch.tensor(left).cuda(), torch.tensor(right).cuda(),
+                        x1=torch.tensor(x1).cuda(), x2=torch.tensor(x2).cuda()).cpu().numpy()
+        assert _close(got, want, rtol=1e-4), (t, got, want)
+    # the float64 formula itself against central differences
+    eps = 1e-6
+    left64, right64 = left.astype(np.float64), right.astype(np.float64)
+    for l in range(phi.n_steps):
+        fp, fm = f.astype(np.float64).copy(), f.astype(np.float64).copy()
+        fp[l] += eps
+        fm[l] -= eps
+        num = (np.sum(left64 * o.phi_matvec_f64(mats32, fp, right64, x1, x2))
+               - np.sum(left64 * o.phi_matvec_f64(mats32, fm, right64, x1, x2))) / (2 * eps)
+        assert abs(num - want[l]) <= 1e-5 * max(1.0, abs(want[l]))
+
+
+def test_sharded_rows_sum_to_the_full_product(env, case):
+    """Multi-GPU decomposition on one device: row shards' partial U add up, outputs concatenate."""
+    eng, torch = env["eng"], env["torch"]
+    phi, g, cfg = case["phi"], case["g"], case["cfg"]
+    rng = np.random.default_rng(12)
+    f = torch.tensor(rng.standard_normal(phi.n_steps).astype(np.float32))
+    v = torch.tensor(rng.standard_normal((phi.n_rows, 16)).astype(np.float32)).cuda()
+    want = phi.matvec(f, v).clone()
+    bounds = [0, 190, 191, 500, phi.n_rows]
+    shards = [eng.build_phi_blocks(g, cfg, lo, hi) for lo, hi in zip(bounds[:-1], bounds[1:])]
+    u = sum(s.apply_t(f, v[lo:hi]).clone() for s, lo, hi in zip(shards, bounds[:-1], bounds[1:]))
+    got = torch.cat([s.apply(f, u) for s in shards])
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+    # global ids routed to the owning shard only
+    x = torch.tensor([3, 190, 450, 699, 200]).cuda()
+    parts = torch.zeros(5, 16, device="cuda")
+    for s in shards:
+        s.apply(f, u, rows=x, out=parts)
+    assert torch.allclose(parts, want[x], rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+
+
+def test_large_grid_roundtrip_properties(env):
+    """BASELINE config-2 shape (316x316 grid, W=100, L=5): M_0 = I, transpose multiset, <a, K b> = <K a, b>."""
+    eng, torch = env["eng"], env["torch"]
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+
+    lap = get_normalized_laplacian(grid_graph(316, 316))
+    g = eng.DeviceGraph.from_scipy(lap)
+    phi = eng.build_phi_blocks(g, eng.WalkConfig(100, 0.1, 5, seed=42))
+    n = phi.n_rows
+    assert n == 99856
+    ptr = phi.blk_ptr.view(-1)[:-1].view(n, 5)
+    assert bool((ptr[:, 1] - ptr[:, 0] == 1).all())                      # one entry per row at length 0
+    first = phi.entries[ptr[:, 0].long()]
+    assert bool((first[:, 0] == torch.arange(n, device="cuda", dtype=torch.int32)).all())
+    assert bool((first[:, 1].view(torch.float32) == 1.0).all())          # M_0 = I exactly
+    visits = int(phi.visits)
+    expect = n * 100 * sum(0.9 ** k for k in range(5))
+    assert abs(visits - expect) / expect < 5e-3
+    assert int(phi.tblk_ptr[-1]) == phi.nnz
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    f = torch.randn(5, device="cuda", generator=gen)
+    a = torch.randn(n, 16, device="cuda", generator=gen)
+    b = torch.randn(n, 16, device="cuda", generator=gen)
+    ka, kb = phi.matvec(f, a).clone(), phi.matvec(f, b).clone()
+    lhs, rhs = float((b * ka).sum()), float((a * kb).sum())
+    assert abs(lhs - rhs) <= 1e-3 * max(abs(lhs), abs(rhs), 1.0)

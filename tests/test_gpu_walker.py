@@ -1,0 +1,244 @@
+"""-m gpu parity tests of the walker + compaction, through the C ABI.
+
+Bar (north star): bit-exact against the reference's Phi when both sides replay
+the same pre-drawn walk / halting trace; with native (Philox) draws, bit-exact
+against the oracle fed with the same Philox stream."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN, golden_csr, load_golden
+from gpu_util import csr_bits_equal, grid_graph, powerlaw_graph, random_graph, ring_graph
+
+pytestmark = pytest.mark.gpu
+
+SPARSE = sorted(glob.glob(os.path.join(GOLDEN, "sparse_*.npz")))
+DENSE = sorted(glob.glob(os.path.join(GOLDEN, "dense_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a B200"
+    from grf_b200 import _lib, engine
+    from oracle import c_oracle, grf_oracle
+
+    return dict(torch=torch, lib=_lib, eng=engine, c=c_oracle, o=grf_oracle)
+
+
+# ---------------------------------------------------------------- replay mode
+@pytest.mark.parametrize("path", SPARSE, ids=[os.path.basename(p)[:-4] for p in SPARSE])
+def test_replay_is_bit_exact_with_reference_sparse(env, path):
+    """GPU walker replaying the reference's PCG64 draws == the reference's own step matrices."""
+    from efficient_graph_gp_sparse.random_walk_samplers_sparse.sparse_sampler import SparseRandomWalk
+
+    z = np.load(path)
+    W, p, L = int(z["W"]), float(z["p_halt"]), int(z["L"])
+    seed = None if int(z["seed"]) < 0 else int(z["seed"])
+    graph = golden_csr(z, "graph")
+    _, trace = env["o"].sparse_step_matrices(graph, W, p, L, seed=seed, n_processes=int(z["n_processes"]),
+                                             record=True)
+    mats = SparseRandomWalk(graph, seed=seed).get_random_walk_matrices(W, p, L, trace=trace)
+    n = graph.shape[0]
+    assert len(mats) == L
+    for s in range(L):
+        assert csr_bits_equal(mats[s], golden_csr(z, f"step{s}", shape=(n, n))), (path, s)
+
+
+@pytest.mark.parametrize("path", DENSE, ids=[os.path.basename(p)[:-4] for p in DENSE])
+def test_replay_is_bit_exact_with_reference_dense(env, path):
+    from efficient_graph_gp.random_walk_samplers.sampler import Graph, RandomWalk
+
+    z = np.load(path)
+    W, p, L = int(z["W"]), float(z["p_halt"]), int(z["L"])
+    seed = None if int(z["seed"]) < 0 else int(z["seed"])
+    nproc, ablation = int(z["n_processes"]), bool(int(z["ablation"]))
+    adj = z["graph"]
+    _, trace = env["o"].dense_step_tensor(adj, W, p, L, seed=seed, n_processes=nproc, ablation=ablation, record=True)
+    sequential = nproc == 1 or adj.shape[0] < 2 * nproc
+    got = RandomWalk(Graph(adj), seed=seed).get_random_walk_matrices(
+        W, p, L, n_processes=nproc, ablation=ablation, sequential_semantics=sequential, trace=trace)
+    assert got.shape == z["tensor"].shape
+    assert np.array_equal(got.view(np.int64), z["tensor"].view(np.int64))
+
+
+def test_replay_kernels_match_reference(env):
+    """Both fast_general_grf_kernel drop-ins against the reference's K (replayed draws)."""
+    from efficient_graph_gp.graph_kernels.fast_grf_kernel_general import fast_general_grf_kernel as k_dense
+    from efficient_graph_gp_sparse.graph_kernels_sparse.fast_grf_kernel_general import fast_general_grf_kernel as k_sp
+
+    z = load_golden("kernels.npz")
+    nproc = int(z["n_processes"])
+    o = env["o"]
+    for name in ("cycle4", "grid6x4", "gnm40w"):
+        adj, f = z[name + "_adj"], z[name + "_f"]
+        lap = o.normalized_laplacian_sparse(sp.csr_matrix(adj))
+        _, trace = o.sparse_step_matrices(lap, 10, 0.2, 3, seed=None, n_processes=nproc, record=True)
+        ks = k_sp(sp.csr_matrix(adj), f, walks_per_node=10, p_halt=0.2, max_walk_length=3, trace=trace)
+        assert np.array_equal(ks.toarray(), z[name + "_K_sparse"]), name
+        _, trace = o.dense_step_tensor(o.normalized_laplacian_dense(adj), 10, 0.2, 3, seed=42, n_processes=nproc,
+                                       record=True)
+        kd = k_dense(adj, f, walks_per_node=10, p_halt=0.2, max_walk_length=3, trace=trace)
+        assert np.allclose(kd, z[name + "_K_dense"], rtol=0, atol=1e-12), name   # dgemm summation order
+
+
+# ---------------------------------------------------------------- native mode
+def _native_case(env, graph, W, p, L, seed, load_mode=0, scale_mode=0, start_lo=0, start_hi=None, **kw):
+    eng, lib, c = env["eng"], env["lib"], env["c"]
+    g = eng.DeviceGraph.from_scipy(graph)
+    cfg = eng.WalkConfig(W, p, L, seed=seed, load_mode=load_mode)
+    got = eng.build_step_matrices(g, cfg, start_lo, start_hi, scale_mode=scale_mode, **kw)
+    want, visits = c.step_matrices(graph, W, p, L, seed=seed, load_mode=load_mode, scale_mode=scale_mode,
+                                   start_lo=start_lo, start_hi=start_hi, return_visits=True)
+    mats = got.to_scipy()
+    for s in range(L):
+        assert csr_bits_equal(mats[s], want[s]), s
+    assert got.visits == visits
+    return got
+
+
+def test_native_bit_exact_grid(env):
+    lap = env["o"].normalized_laplacian_sparse(grid_graph(40, 30))
+    got = _native_case(env, lap, 100, 0.1, 5, seed=42)
+    m0 = got.to_scipy()[0]
+    assert np.array_equal(m0.toarray(), np.eye(1200))      # M_0 = I exactly
+
+
+@pytest.mark.parametrize("load_mode,scale_mode", [(0, 1), (1, 0), (2, 1)])
+def test_native_bit_exact_modes(env, load_mode, scale_mode):
+    lap = env["o"].normalized_laplacian_sparse(random_graph(500, 1500, 3, weighted=True))
+    _native_case(env, lap, 33, 0.2, 4, seed=7, load_mode=load_mode, scale_mode=scale_mode)
+
+
+def test_native_bit_exact_powerlaw_hubs(env):
+    lap = env["o"].normalized_laplacian_sparse(powerlaw_graph(3000, 20000, 1))
+    _native_case(env, lap, 64, 0.1, 5, seed=99)
+
+
+@pytest.mark.parametrize("W,L", [(1, 1), (1, 4), (2, 2), (31, 3), (32, 3), (33, 3), (128, 2), (129, 3), (256, 3)])
+def test_native_bit_exact_walk_counts(env, W, L):
+    lap = env["o"].normalized_laplacian_sparse(ring_graph(97))
+    _native_case(env, lap, W, 0.1, L, seed=5)
+
+
+@pytest.mark.parametrize("W,L", [(300, 3), (1000, 3), (2048, 2)])
+def test_native_bit_exact_block_per_node_variant(env, W, L):
+    lap = env["o"].normalized_laplacian_sparse(random_graph(60, 150, 11))
+    _native_case(env, lap, W, 0.1, L, seed=5)
+
+
+def test_native_bit_exact_wide_keys(env):
+    """node bits + walk bits > 31 -> 64-bit sort keys; only a slice of start nodes is walked."""
+    n = 9_000_000
+    ring = ring_graph(n)          # raw adjacency as the walk graph (unit weights)
+    _native_case(env, ring, 1000, 0.1, 3, seed=1, start_lo=n - 40, start_hi=n - 8)      # CTA-per-node, u64 keys
+    _native_case(env, ring, 200, 0.1, 4, seed=1, start_lo=8_500_000, start_hi=8_500_064)  # warp-per-node, u64 keys
+
+
+@pytest.mark.parametrize("p_halt", [0.0, 1.0, 0.999])
+def test_halting_extremes(env, p_halt):
+    lap = env["o"].normalized_laplacian_sparse(grid_graph(9, 7))
+    got = _native_case(env, lap, 20, p_halt, 4, seed=3)
+    if p_halt == 1.0:
+        assert got.nnz_per_step() == [63, 0, 0, 0]
+
+
+def test_graph_without_edges_and_isolated_nodes(env):
+    empty = sp.csr_matrix((50, 50))
+    got = _native_case(env, empty, 10, 0.1, 3, seed=1)
+    assert got.nnz_per_step() == [50, 0, 0]
+    iso = random_graph(200, 120, 5)       # many isolated nodes -> dead ends
+    _native_case(env, env["o"].normalized_laplacian_sparse(iso), 25, 0.05, 6, seed=2)
+
+
+def test_empty_shard_and_sharding_is_row_slicing(env):
+    lap = env["o"].normalized_laplacian_sparse(random_graph(300, 900, 8))
+    full = _native_case(env, lap, 40, 0.1, 4, seed=21).to_scipy()
+    part = _native_case(env, lap, 40, 0.1, 4, seed=21, start_lo=100, start_hi=217).to_scipy()
+    for s in range(4):
+        assert csr_bits_equal(part[s], full[s][100:217])
+    none = _native_case(env, lap, 40, 0.1, 4, seed=21, start_lo=50, start_hi=50)
+    assert none.nnz_per_step() == [0, 0, 0, 0]
+
+
+def test_row_chunking_does_not_change_the_result(env):
+    lap = env["o"].normalized_laplacian_sparse(grid_graph(20, 20))
+    _native_case(env, lap, 50, 0.1, 4, seed=4, max_stage_bytes=50_000)
+
+
+def test_argument_validation(env):
+    eng = env["eng"]
+    g = eng.DeviceGraph.from_scipy(ring_graph(10))
+    with pytest.raises(ValueError):
+        eng.build_step_matrices(g, eng.WalkConfig(0, 0.1, 3))
+    with pytest.raises(ValueError):
+        eng.build_step_matrices(g, eng.WalkConfig(5, 1.5, 3))
+    with pytest.raises(ValueError):
+        eng.build_step_matrices(g, eng.WalkConfig(5, 0.1, 3), start_lo=0, start_hi=11)
+    with pytest.raises(ValueError, match="square"):
+        eng.DeviceGraph.from_scipy(sp.csr_matrix((3, 4)))
+
+
+# ------------------------------------------------ the reference's own tests
+def test_sparse_random_walk_shapes(toy_cycle_csr):
+    """tests/test_grf_sparse.py:9-16 of the reference, verbatim expectations."""
+    from efficient_graph_gp_sparse.random_walk_samplers_sparse.sparse_sampler import SparseRandomWalk
+
+    rw = SparseRandomWalk(toy_cycle_csr, seed=0)
+    mats = rw.get_random_walk_matrices(num_walks=5, p_halt=0.2, max_walk_length=3, n_processes=1)
+    assert len(mats) == 3
+    for m in mats:
+        assert m.shape == (4, 4)
+    assert np.allclose(mats[0].diagonal(), 1.0, atol=1e-6)
+
+
+def test_fast_general_grf_kernel_sparse_psd(toy_cycle_csr):
+    """tests/test_grf_sparse.py:19-31."""
+    from efficient_graph_gp_sparse.graph_kernels_sparse.fast_grf_kernel_general import fast_general_grf_kernel
+
+    k = fast_general_grf_kernel(adj_matrix=toy_cycle_csr, modulator_vector=np.array([1.0, 0.5, 0.25]),
+                                walks_per_node=10, p_halt=0.2, max_walk_length=3)
+    k_dense = k.toarray()
+    assert np.allclose(k_dense, k_dense.T, atol=1e-8)
+    assert np.linalg.eigvalsh(k_dense).min() >= -1e-8
+
+
+def test_random_walk_shapes(toy_cycle_adj):
+    """tests/test_grf_dense.py:7-13."""
+    from efficient_graph_gp.random_walk_samplers.sampler import Graph, RandomWalk
+
+    rw = RandomWalk(Graph(toy_cycle_adj), seed=0)
+    mats = rw.get_random_walk_matrices(num_walks=5, p_halt=0.2, max_walk_length=3, n_processes=1)
+    assert mats.shape == (4, 4, 3)
+    assert np.allclose(np.diag(mats[:, :, 0]), 1.0, atol=1e-6)
+
+
+def test_fast_general_grf_kernel_psd(toy_cycle_adj):
+    """tests/test_grf_dense.py:16-29."""
+    from efficient_graph_gp.graph_kernels.fast_grf_kernel_general import fast_general_grf_kernel
+
+    k = fast_general_grf_kernel(adj_matrix=toy_cycle_adj, modulator_vector=np.array([1.0, 0.5, 0.25]),
+                                walks_per_node=10, p_halt=0.2, max_walk_length=3)
+    assert np.allclose(k, k.T, atol=1e-8)
+    assert np.linalg.eigvalsh(k).min() >= -1e-8
+
+
+# ----------------------------------------------------- statistical parity
+def test_frobenius_error_matches_reference_level(env):
+    """North star: rel. Frobenius error of K against the exact truncated series,
+    at equal walks_per_node, matches the reference's (= the oracle with PCG64
+    draws) within a stated tolerance: |err_gpu - err_ref| <= 0.25 * err_ref."""
+    from efficient_graph_gp_sparse.graph_kernels_sparse.fast_grf_kernel_general import fast_general_grf_kernel
+
+    o = env["o"]
+    adj = random_graph(300, 600, 17)
+    f = [1.0, 0.5, 0.25]
+    exact = o.exact_series(o.normalized_laplacian_sparse(adj).toarray(), f)
+    err_ref = np.mean([o.compute_fro(exact, o.grf_kernel_sparse(adj, f, 50, 0.1, 3, n_processes=2).toarray())])
+    err_gpu = o.compute_fro(exact, fast_general_grf_kernel(adj, f, 50, 0.1, 3).toarray())
+    assert abs(err_gpu - err_ref) <= 0.25 * err_ref, (err_gpu, err_ref)

@@ -123,3 +123,22 @@ def test_estimator_is_unbiased_for_matrix_powers():
     a = lap.toarray()
     assert np.allclose(mats[1].toarray(), a, atol=0.12)
     assert np.allclose(mats[2].toarray(), a @ a, atol=0.2)
+
+
+@pytest.mark.parametrize("path", SPARSE, ids=[os.path.basename(p)[:-4] for p in SPARSE])
+def test_cpu_baseline_port_matches_reference(path):
+    """The timed CPU baseline (oracle/cpu_baseline.py, fork pool) is the reference's algorithm bit for bit."""
+    from oracle import cpu_baseline
+
+    z = np.load(path)
+    W, p, L = int(z["W"]), float(z["p_halt"]), int(z["L"])
+    seed = None if int(z["seed"]) < 0 else int(z["seed"])
+    graph = golden_csr(z, "graph")
+    mats, visits = cpu_baseline.sampler_pool(graph, W, p, L, seed=seed, n_processes=int(z["n_processes"]),
+                                             return_visits=True)
+    n = graph.shape[0]
+    for s in range(L):
+        want = golden_csr(z, f"step{s}", shape=(n, n))
+        assert np.array_equal(mats[s].indptr, want.indptr) and np.array_equal(mats[s].indices, want.indices)
+        assert np.array_equal(mats[s].data, want.data)
+    assert visits >= n * W
