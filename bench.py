@@ -82,9 +82,16 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=self.out, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def wait_first_sample(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and time.perf_counter() - t0 < timeout:
+            if os.path.getsize(self.out.name) > 0:
+                return
+            time.sleep(0.01)
 
     def stop(self):
         if self.proc is None:
@@ -112,7 +119,8 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.out.name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "warm-up + timed steps (20 ms period; the timed region alone is a few ms per step)"}
 
 
 # ------------------------------------------------------------------ reference arm
@@ -227,13 +235,15 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                 # nvidia-smi needs ~0.1 s to start: launch it before warm-up
     for _ in range(args.warmup):
         r = one_step()
         del r
-    barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first_sample()
+    barrier()
     t_wall0 = time.perf_counter()
     results = [one_step() for _ in range(args.steps)]
     barrier()

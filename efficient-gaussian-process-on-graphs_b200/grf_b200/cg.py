@@ -1,0 +1,51 @@
+"""Batched conjugate gradients on the device.
+
+Restates the semantics of upstream ``linear_operator.utils.linear_cg`` as the
+reference calls it (``models/sparse_grf_model.py:43``: ``linear_cg(A._matmul,
+b.T, tolerance=cg_tolerance)``): right-hand sides normalised per column, zero
+initial guess, no preconditioner, stop when the mean residual norm falls below
+``tolerance`` after at least ``min(10, max_iter - 1)`` iterations, at most
+``max_iter`` (upstream default 1000).  The package itself is not installed
+here, so parity is against a float64 direct solve (tests), not upstream.
+
+Every iteration is one kernel matvec (two grf_b200 SpMM launches) plus O(n t)
+vector updates; the convergence check reads one scalar back every
+``check_every`` iterations instead of every iteration.
+"""
+
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+
+
+def linear_cg(matmul_closure: Callable[[torch.Tensor], torch.Tensor], rhs: torch.Tensor, tolerance: float = 1e-2,
+              max_iter: int = 1000, eps: float = 1e-10, check_every: int = 4, return_info: bool = False):
+    squeeze = rhs.dim() == 1
+    b = rhs[:, None] if squeeze else rhs
+    b = b.to(torch.float32)
+    norm = b.norm(dim=0, keepdim=True)
+    norm = torch.where(norm < eps, torch.ones_like(norm), norm)
+    b = b / norm
+    x = torch.zeros_like(b)
+    r = b.clone()
+    d = r.clone()
+    rs = (r * r).sum(dim=0, keepdim=True)
+    min_iter = min(10, max_iter - 1)
+    iters = 0
+    for k in range(max_iter):
+        ad = matmul_closure(d)
+        alpha = rs / (d * ad).sum(dim=0, keepdim=True).clamp_min(eps)
+        x = x + alpha * d
+        r = r - alpha * ad
+        rs_new = (r * r).sum(dim=0, keepdim=True)
+        iters = k + 1
+        if iters >= min_iter and (iters % check_every == 0 or iters == max_iter):
+            if float(rs_new.sqrt().mean()) < tolerance:
+                break
+        d = r + (rs_new / rs.clamp_min(eps)) * d
+        rs = rs_new
+    out = x * norm
+    out = out[:, 0] if squeeze else out
+    return (out, {"iterations": iters}) if return_info else out

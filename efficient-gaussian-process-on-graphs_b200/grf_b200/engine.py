@@ -397,30 +397,34 @@ class PhiBlocks:
         """U = Phi[x2]^T v  ([n_cols, t]) in a fresh buffer."""
         return self.apply_t(f, v, rows=x2)
 
-    def fgrad(self, f, left, right, x1=None, x2=None) -> torch.Tensor:
-        """d/df of sum(left * (Phi[x1] Phi[x2]^T right)) -- a per-length reduction.
+    def fgrad_half(self, rows, left, p, grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """grad[l] += sum_k <left[k, :], M_l[rows[k], :] @ p>  -- the per-length reduction.
 
-        left [n1, t], right [n2, t]."""
+        left [n, t], p [n_cols, t]; returns float32 [L]."""
         dev = self.device
-        L = _lib.lib()
-        left = torch.as_tensor(left, device=dev).to(torch.float32).contiguous()
-        right = torch.as_tensor(right, device=dev).to(torch.float32).contiguous()
+        left = self._rhs(left, dev)
+        p = self._rhs(p, dev)
+        rows = self._ids(rows, dev)
+        n = self.n_rows if rows is None else rows.numel()
+        if left.shape[0] != n or p.shape[0] != self.n_cols or left.shape[1] != p.shape[1]:
+            raise ValueError("fgrad_half: shape mismatch")
+        if grad is None:
+            grad = torch.zeros(self.n_steps, dtype=torch.float32, device=dev)
+        phi = self.c_struct()
+        check(_lib.lib().grf_phi_fgrad(ctypes.byref(phi), _ptr(rows), n, _ptr(left), left.stride(0), _ptr(p),
+                                       p.stride(0), left.shape[1], _ptr(grad), _stream(dev)))
+        return grad
+
+    def fgrad(self, f, left, right, x1=None, x2=None) -> torch.Tensor:
+        """d/df of sum(left * (Phi[x1] Phi[x2]^T right)): left [n1, t], right [n2, t] -> [L]."""
+        left = torch.as_tensor(left, device=self.device)
+        right = torch.as_tensor(right, device=self.device)
         if left.dim() == 1:
             left, right = left[:, None], right[:, None]
-        t = left.shape[1]
-        x1 = self._ids(x1, dev)
-        x2 = self._ids(x2, dev)
-        p = self.t_matvec(f, right, x2=x2)   # Phi[x2]^T right
-        q = self.t_matvec(f, left, x2=x1)    # Phi[x1]^T left
-        grad = torch.zeros(self.n_steps, dtype=torch.float32, device=dev)
-        phi = self.c_struct()
-        n1 = self.n_rows if x1 is None else x1.numel()
-        n2 = self.n_rows if x2 is None else x2.numel()
-        check(L.grf_phi_fgrad(ctypes.byref(phi), _ptr(x1), n1, _ptr(left), left.stride(0), _ptr(p), p.stride(0), t,
-                              _ptr(grad), _stream(dev)))
-        check(L.grf_phi_fgrad(ctypes.byref(phi), _ptr(x2), n2, _ptr(right), right.stride(0), _ptr(q), q.stride(0),
-                              t, _ptr(grad), _stream(dev)))
-        return grad
+        p = self.apply_t(f, right, rows=x2)   # Phi[x2]^T right
+        q = self.apply_t(f, left, rows=x1)    # Phi[x1]^T left
+        grad = self.fgrad_half(x1, left, p)
+        return self.fgrad_half(x2, right, q, grad=grad)
 
     # ---- construction ----------------------------------------------------
     @staticmethod

@@ -148,7 +148,7 @@ def test_matvec_row_subsets(env, case, t):
     # x as float column tensors, the way the reference's models pass them (x.long().flatten())
     got2 = phi.matvec(torch.tensor(f), torch.tensor(v).cuda(), x1=torch.tensor(x1, dtype=torch.float32)[:, None].cuda(),
                       x2=torch.tensor(x2, dtype=torch.float32)[:, None].cuda()).cpu().numpy()
-    assert np.array_equal(got, got2)
+    assert _close(got2, got, rtol=1e-6)      # repeated ids are scatter-added with atomics: order may differ
 
 
 def test_apply_and_apply_t_are_the_two_halves(env, case):

@@ -70,6 +70,8 @@ def test_replay_is_bit_exact_with_reference_dense(env, path):
 def test_replay_kernels_match_reference(env):
     """Both fast_general_grf_kernel drop-ins against the reference's K (replayed draws)."""
     from efficient_graph_gp.graph_kernels.fast_grf_kernel_general import fast_general_grf_kernel as k_dense
+    from efficient_graph_gp.graph_kernels.utils import get_normalized_laplacian as lap_dense
+    from efficient_graph_gp.random_walk_samplers.sampler import Graph, RandomWalk
     from efficient_graph_gp_sparse.graph_kernels_sparse.fast_grf_kernel_general import fast_general_grf_kernel as k_sp
 
     z = load_golden("kernels.npz")
@@ -83,7 +85,16 @@ def test_replay_kernels_match_reference(env):
         assert np.array_equal(ks.toarray(), z[name + "_K_sparse"]), name
         _, trace = o.dense_step_tensor(o.normalized_laplacian_dense(adj), 10, 0.2, 3, seed=42, n_processes=nproc,
                                        record=True)
-        kd = k_dense(adj, f, walks_per_node=10, p_halt=0.2, max_walk_length=3, trace=trace)
+        if adj.shape[0] < 2 * nproc:
+            # Here the reference silently takes _sequential_walks (sampler.py:115-116) with its non-cumulative
+            # load (sampler.py:183).  The drop-in kernel keeps the unbiased cumulative rule, so the
+            # reference's K is reproduced through the explicit sequential_semantics switch instead.
+            feats = RandomWalk(Graph(lap_dense(adj)), seed=42).get_random_walk_matrices(
+                10, 0.2, 3, sequential_semantics=True, trace=trace)
+            phi = feats @ f
+            kd = phi @ phi.T
+        else:
+            kd = k_dense(adj, f, walks_per_node=10, p_halt=0.2, max_walk_length=3, trace=trace)
         assert np.allclose(kd, z[name + "_K_dense"], rtol=0, atol=1e-12), name   # dgemm summation order
 
 
