@@ -212,23 +212,19 @@ def run_gpu(args):
     stride = lib.grf_walk_stage_stride(W, L)
 
     def one_step():
-        """walker -> Phi blocks -> Phi^T blocks -> one Phi(Phi^T V)."""
+        """walker -> Phi blocks -> Phi^T blocks -> one Phi(Phi^T V).  Returns events + the visit counter only,
+        so every step reuses the previous step's device memory (no cudaMalloc in the timed region)."""
         visits = torch.zeros(1, dtype=torch.int64, device=dev)
         st, e_walk = timed(lambda: engine.run_walker(graph, cfg, lo, hi, visits=visits))
         phi, e_comp = timed(lambda: engine._blocks_from_staging(st, cfg, graph.n_nodes, _lib.SCALE_MUL_RECIP))
+        del st
         phi.row_lo = lo
         _, e_tr = timed(lambda: phi.build_transpose())
-        u_buf = torch.empty((graph.n_nodes, T_RHS), dtype=torch.float32, device=dev)
-
-        def mv():
-            u = phi.apply_t(f, v, out=u_buf)
-            if world > 1:
-                dist.all_reduce(u_buf)                  # sum of the per-GPU partials Phi_g^T V_g
-            return phi.apply(f, u)
-
-        out, e_mv = timed(mv)
-        return dict(phi=phi, visits=visits, out=out, events=dict(walk=e_walk, compact=e_comp, transpose=e_tr,
-                                                                 matvec=e_mv))
+        plan = phi.plan(f, T_RHS, group=True if world > 1 else None)
+        out = torch.empty((hi - lo, T_RHS), dtype=torch.float32, device=dev)
+        _, e_mv = timed(lambda: plan(v, out))
+        return dict(visits=visits, nnz=phi.nnz, n_rows=phi.n_rows,
+                    events=dict(walk=e_walk, compact=e_comp, transpose=e_tr, matvec=e_mv))
 
     def barrier():
         if world > 1:
@@ -254,9 +250,8 @@ def run_gpu(args):
                 for k in ("walk", "compact", "transpose", "matvec")}
     step_ms_total = sum(phase_ms.values())
     visits_total = sum(int(r["visits"].item()) for r in results)
-    phi = results[-1]["phi"]
-    nnz = phi.nnz
-    n_rows = phi.n_rows
+    nnz = results[-1]["nnz"]
+    n_rows = results[-1]["n_rows"]
 
     # ---- e2e: the public drop-in call with HOST buffers (host CSR in, scipy CSR list out) + host matvec
     from efficient_graph_gp_sparse.random_walk_samplers_sparse.sparse_sampler import SparseRandomWalk
@@ -275,11 +270,7 @@ def run_gpu(args):
         phi_e = engine.PhiBlocks.from_step_matrices(steps)
         phi_e.row_lo = lo
         vd = v_host.to(dev, non_blocking=True)
-        u = phi_e.apply_t(f, vd)
-        if world > 1:
-            u = u.contiguous()
-            dist.all_reduce(u)
-        out_host = phi_e.apply(f, u).cpu()
+        out_host = phi_e.plan(f, T_RHS, group=True if world > 1 else None)(vd).cpu()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if i > 0:

@@ -26,6 +26,18 @@ int check_cuda(cudaError_t err, const char *what);
     } while (0)
 
 constexpr int kWarp = 32;
+// Phi / Phi^T entries carry their walk length in the top bits of `col`
+// (GRF_ENTRY_STEP_SHIFT in grf_b200.h): the matvec then needs one pointer pair
+// per row instead of one per (row, length).
+constexpr int kStepShift = GRF_ENTRY_STEP_SHIFT;
+constexpr uint32_t kColMask = (1u << GRF_ENTRY_STEP_SHIFT) - 1u;
+constexpr int kMaxSteps = 1 << (32 - GRF_ENTRY_STEP_SHIFT);
+
+__host__ __device__ __forceinline__ int32_t pack_col(int32_t col, int step) {
+    return (int32_t)(((uint32_t)step << kStepShift) | (uint32_t)col);
+}
+__host__ __device__ __forceinline__ int32_t entry_col(int32_t packed) { return (int32_t)((uint32_t)packed & kColMask); }
+__host__ __device__ __forceinline__ int entry_step(int32_t packed) { return (int)((uint32_t)packed >> kStepShift); }
 constexpr int kSmCount = 148;  // B200
 
 __host__ __device__ inline uint32_t next_pow2(uint32_t x) {

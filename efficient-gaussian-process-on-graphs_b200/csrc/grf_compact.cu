@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *stag
         const int32_t dst = blk_ptr[r * L];
         const int32_t c = blk_ptr[(r + 1) * L] - dst;  // the row's segments are contiguous on both sides
         for (int i = lane; i < c; i += 32) {
+            int step = 0;
+            while (step + 1 < L && dst + i >= blk_ptr[r * L + step + 1]) ++step;
             GrfEntry e;
-            e.col = stage_col[src + i];
+            e.col = pack_col(stage_col[src + i], step);
             e.val = (float)scale_sum(stage_sum[src + i], scale_mode, recip, (double)W);
             entries[dst + i] = e;
         }
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256) blocks_from_steps_kernel(const int64_t *o
             const int32_t dst = blk_ptr[r * L + s];
             for (int i = lane; i < c; i += 32) {
                 GrfEntry e;
-                e.col = col[src + i];
+                e.col = pack_col(col[src + i], s);
                 e.val = (float)val[src + i];  // torch .float(): round to nearest even
                 entries[dst + i] = e;
             }
@@ -214,7 +216,8 @@ __global__ void __launch_bounds__(256) transpose_count_kernel(const int32_t *blk
     for (int64_t r = warp0; r < n_rows; r += nwarps) {
         for (int s = 0; s < L; ++s) {
             const int32_t b = blk_ptr[r * L + s], e = blk_ptr[r * L + s + 1];
-            for (int32_t i = b + lane; i < e; i += 32) atomicAdd(&tcnt[(int64_t)entries[i].col * L + s], 1);
+            for (int32_t i = b + lane; i < e; i += 32)
+                atomicAdd(&tcnt[(int64_t)entry_col(entries[i].col) * L + s], 1);
         }
     }
 }
@@ -230,9 +233,9 @@ __global__ void __launch_bounds__(256) transpose_fill_kernel(const int32_t *blk_
             const int32_t b = blk_ptr[r * L + s], e = blk_ptr[r * L + s + 1];
             for (int32_t i = b + lane; i < e; i += 32) {
                 const GrfEntry src = entries[i];
-                const int32_t slot = atomicAdd(&cursor[(int64_t)src.col * L + s], 1);
+                const int32_t slot = atomicAdd(&cursor[(int64_t)entry_col(src.col) * L + s], 1);
                 GrfEntry dst;
-                dst.col = (int32_t)r;
+                dst.col = pack_col((int32_t)r, s);
                 dst.val = src.val;
                 tentries[slot] = dst;
             }

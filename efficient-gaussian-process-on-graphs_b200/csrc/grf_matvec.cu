@@ -10,10 +10,10 @@
 // Both halves are the same operation on block-CSR data ("for every row, for
 // every walk length l, f_l * sum of val * X[col, :]"), once over Phi^T blocks
 // (U = Phi[x2]^T V) and once over Phi blocks (out = Phi[x1] U):
-//   * entries are 8-byte {col, val} pairs streamed once, coalesced;
+//   * entries are 8-byte {length<<27 | col, val} pairs streamed once, coalesced;
 //   * TPR threads share a row and own 4 (or 1) of the t right-hand-side
 //     columns each, so a gather of X[col, :] is one 16*TPR-byte contiguous read;
-//   * f_l is applied once per (row, length) segment, in registers.
+//   * f_l is applied per entry in registers (f lives in shared memory).
 // HBM-bound: algorithmic bytes per matvec = 2*nnz*8 + 2*L*(rows+1)*4 + 4*N*t*4
 // (SURVEY.md 8d); the X gathers are L2/L1 traffic.  No tensor cores: this is a
 // sparse gather, not a dense contraction.
@@ -58,7 +58,31 @@ __device__ __forceinline__ GrfEntry load_entry(const GrfEntry *p) {
     return e;
 }
 
-// Y[k, :] = sum_l f[l] * sum_{e in seg(row_k, l)} e.val * X[e.col, :]
+// Y[k, :] = sum_{e in row_k} f[step(e)] * e.val * X[col(e), :]
+//
+// A row's L per-length segments are contiguous, so the whole row is ONE flat
+// run of entries [ptr[row*L], ptr[(row+1)*L]) with the length packed in the
+// top bits of `col`.  TPR lanes own a row.  Per round the group fetches
+// TPR*kEPL entries with one coalesced 8-byte load per lane and entry slot
+// (all independent), scales them by f[length] in registers, and then every
+// lane replays the group's entries through width-TPR shuffles, issuing the
+// X[col, :] gathers back to back (TPR*kEPL independent 16-byte loads per lane
+// in flight).  The next round's entries are prefetched before the gathers of
+// the current one are consumed, so entry-stream latency hides behind the
+// gather latency.  (v1 walked entry -> gather serially: ncu showed 25 warps
+// stalled on long-scoreboard per issue and 0.42 entries/cycle/SM.)
+constexpr int kEPL = 4;  // entries per lane per round
+
+template <int TPR>
+__device__ __forceinline__ unsigned group_mask() {
+    if constexpr (TPR == 32) {
+        return 0xffffffffu;
+    } else {
+        const unsigned lane = threadIdx.x & 31u;
+        return ((1u << TPR) - 1u) << (lane & ~(unsigned)(TPR - 1));
+    }
+}
+
 template <int TPR, int VEC>
 __global__ void __launch_bounds__(256) spmm_blocks_kernel(const int32_t *__restrict__ ptr,
                                                           const GrfEntry *__restrict__ ent,
@@ -67,32 +91,64 @@ __global__ void __launch_bounds__(256) spmm_blocks_kernel(const int32_t *__restr
                                                           int64_t row_lo, int64_t n_rows,
                                                           const float *__restrict__ X, int64_t ldx,
                                                           float *__restrict__ Y, int64_t ldy, int32_t t) {
+    __shared__ float fs[kMaxSteps];
+    if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
+    __syncthreads();
     const int sub = threadIdx.x % TPR;
+    const unsigned gmask = group_mask<TPR>();
     const int64_t task0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
     const int64_t task_stride = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
     for (int64_t k = task0; k < n_tasks; k += task_stride) {
         const int64_t row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
-        if (row < 0 || row >= n_rows) continue;
-        const int32_t *rp = ptr + row * L;
-        for (int c0 = sub * VEC; c0 < t; c0 += TPR * VEC) {
+        if (row < 0 || row >= n_rows) continue;  // uniform across the TPR lanes of the group
+        const int32_t b = __ldg(ptr + row * L);
+        const int32_t e = __ldg(ptr + (row + 1) * L);
+        const int n_tiles = (t + TPR * VEC - 1) / (TPR * VEC);
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            // lanes whose columns fall outside t (t not a multiple of TPR*VEC) still help with the
+            // entry loads and shuffles; they just do not gather or store
+            const int c0 = (tile * TPR + sub) * VEC;
+            const bool live = c0 < t;
             Vec<VEC> acc;
             acc.zero();
-            int32_t b = __ldg(rp);
-            for (int s = 0; s < L; ++s) {
-                const int32_t e = __ldg(rp + s + 1);
-                Vec<VEC> part;
-                part.zero();
-#pragma unroll 4
-                for (int32_t i = b; i < e; ++i) {
-                    const GrfEntry en = load_entry(ent + i);
-                    Vec<VEC> x;
-                    x.load(X + (int64_t)en.col * ldx + c0);
-                    part.fma(en.val, x);
-                }
-                acc.fma(__ldg(f + s), part);
-                b = e;
+            int2 nxt[kEPL];
+#pragma unroll
+            for (int q = 0; q < kEPL; ++q) {
+                const int32_t idx = b + q * TPR + sub;
+                nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
             }
-            acc.store(Y + k * ldy + c0);
+            for (int32_t base = b; base < e; base += TPR * kEPL) {
+                int cl[kEPL];
+                float sv[kEPL];
+#pragma unroll
+                for (int q = 0; q < kEPL; ++q) {
+                    cl[q] = (int)((uint32_t)nxt[q].x & kColMask);
+                    sv[q] = __int_as_float(nxt[q].y) * fs[(uint32_t)nxt[q].x >> kStepShift];
+                }
+                const int32_t nb = base + TPR * kEPL;
+                if (nb < e) {
+#pragma unroll
+                    for (int q = 0; q < kEPL; ++q) {
+                        const int32_t idx = nb + q * TPR + sub;
+                        nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kEPL; ++q) {
+#pragma unroll
+                    for (int j = 0; j < TPR; ++j) {
+                        const int c = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
+                        const float a = TPR == 1 ? sv[q] : __shfl_sync(gmask, sv[q], j, TPR);
+                        if (live && base + q * TPR + j < e) {
+                            Vec<VEC> x;
+                            x.load(X + (int64_t)c * ldx + c0);
+                            acc.fma(a, x);
+                        }
+                    }
+                }
+            }
+            if (live) acc.store(Y + k * ldy + c0);
         }
     }
 }
@@ -114,7 +170,6 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
 }
 
 // grad[l] += sum_k sum_c left[k, c] * (sum_{e in seg(row_k, l)} e.val * P[e.col, c])
-constexpr int kMaxSteps = 32;
 
 template <int TPR, int VEC>
 __global__ void __launch_bounds__(256) fgrad_blocks_kernel(const int32_t *__restrict__ ptr,
@@ -143,7 +198,7 @@ __global__ void __launch_bounds__(256) fgrad_blocks_kernel(const int32_t *__rest
                 for (int32_t i = b; i < e; ++i) {
                     const GrfEntry en = load_entry(ent + i);
                     Vec<VEC> x;
-                    x.load(P + (int64_t)en.col * ldp + c0);
+                    x.load(P + (int64_t)entry_col(en.col) * ldp + c0);
                     part.fma(en.val, x);
                 }
                 Vec<VEC> lv;
@@ -224,6 +279,8 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
     GRF_REQUIRE(t >= 1, "grf_phi_matvec: t must be >= 1");
     GRF_REQUIRE(which >= 1 && which <= 3, "grf_phi_matvec: which must be 1, 2 or 3");
     GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_matvec: n_steps out of range");
+    GRF_REQUIRE(phi->n_cols <= (1ll << kStepShift) && phi->n_rows <= (1ll << kStepShift),
+                "grf_phi_matvec: more than 2^27 rows or columns per GPU");
     GRF_REQUIRE(u && ldu >= t, "grf_phi_matvec: U workspace missing or ldu < t");
     GRF_REQUIRE(x1 || n1 == phi->n_rows, "grf_phi_matvec: n1 must equal n_rows when x1 is NULL");
     GRF_REQUIRE(x2 || n2 == phi->n_rows, "grf_phi_matvec: n2 must equal n_rows when x2 is NULL");

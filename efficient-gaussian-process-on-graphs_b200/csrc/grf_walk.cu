@@ -10,8 +10,9 @@
 // CSR row_ptr pair -> halting draw -> neighbour draw -> (col, val) gather, the
 // load update deg*w/(1-p) applied in registers in float64, and the visit
 // (node, load) of every length >= 1 parked in shared memory.  Phase 2: per
-// length, the <= W visits are bitonic-sorted in shared memory by (node, walk)
-// and, per distinct node, the loads are added *in walk order* into a double
+// length, the <= W visits are bitonic-sorted by (node, walk) -- in registers
+// with warp shuffles when a warp owns the node, in shared memory when a CTA
+// does -- and, per distinct node, the loads are added *in walk order* into a double
 // that starts at 0.0 -- exactly the order in which the reference's
 // defaultdict(float) accumulates them, so the sums are bit-identical when both
 // sides see the same draws.  The merged (column-sorted) per-length segments go
@@ -87,7 +88,48 @@ __device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) 
     return before + incl - v;
 }
 
-template <bool kBlock, typename KeyT>
+// Bitonic sort of 32*KPL keys held KPL per lane (element e = lane*KPL + r): exchanges at
+// distance < KPL stay in registers, larger ones are one shuffle per key.  ~4x fewer issue
+// slots than the shared-memory network it replaces (ncu: the sort was 45 % of all
+// instructions of the kernel).
+template <typename KeyT, int KPL>
+__device__ __forceinline__ void warp_bitonic_sort(KeyT (&key)[KPL], const int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * KPL; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= KPL) {
+                const int lj = j / KPL;
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    const KeyT mine = key[r];
+                    const KeyT other = __shfl_xor_sync(0xffffffffu, mine, lj);
+                    const bool up = ((lane * KPL + r) & k) == 0;
+                    const bool lower = (lane & lj) == 0;
+                    const KeyT mn = mine < other ? mine : other;
+                    const KeyT mx = mine < other ? other : mine;
+                    key[r] = (lower == up) ? mn : mx;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    if ((r & j) == 0) {
+                        const bool up = ((lane * KPL + r) & k) == 0;
+                        const KeyT a = key[r], b = key[r | j];
+                        const KeyT mn = a < b ? a : b;
+                        const KeyT mx = a < b ? b : a;
+                        key[r] = up ? mn : mx;
+                        key[r | j] = up ? mx : mn;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// KPL = keys per lane of the warp-per-node variant (sort width 32*KPL >= W); 0 for the
+// CTA-per-node variant, which sorts in shared memory.
+template <bool kBlock, typename KeyT, int KPL>
 __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int GS = kBlock ? (int)blockDim.x : 32;
@@ -167,61 +209,115 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
 
         // ---------------- phase 2: merge the visits of each length ----------
         for (int si = 0; si < L - 1; ++si) {
-            for (int i = tg; i < Wp; i += GS) {
-                KeyT key = KEY_MAX;
-                if (i < W) {
-                    const int32_t nd = nodes[si * W + i];
-                    if (nd >= 0) key = ((KeyT)(uint32_t)nd << wbits) | (KeyT)i;
+            if constexpr (!kBlock) {
+                // warp-per-node: sort in registers, park the sorted keys in shared memory
+                // for the run walks below
+                const int lane = tg;
+                KeyT key[KPL];
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    const int w = r * 32 + lane;
+                    KeyT kk = KEY_MAX;
+                    if (w < W) {
+                        const int32_t nd = nodes[si * W + w];
+                        if (nd >= 0) kk = ((KeyT)(uint32_t)nd << wbits) | (KeyT)w;
+                    }
+                    key[r] = kk;
                 }
-                keys[i] = key;
-            }
-            group_sync<kBlock>();
-            for (uint32_t k = 2; k <= (uint32_t)Wp; k <<= 1) {
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t c = tg; c < (uint32_t)Wp / 2; c += GS) {
-                        const uint32_t idx = ((c & ~(j - 1)) << 1) | (c & (j - 1));
-                        const uint32_t ixj = idx | j;
-                        const KeyT a = keys[idx], b = keys[ixj];
-                        const bool up = (idx & k) == 0;
-                        if ((a > b) == up) {
-                            keys[idx] = b;
-                            keys[ixj] = a;
+                warp_bitonic_sort<KeyT, KPL>(key, lane);
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) keys[lane * KPL + r] = key[r];
+                __syncwarp();
+                const KeyT prev_last = __shfl_up_sync(0xffffffffu, key[KPL - 1], 1);
+                int heads = 0;
+                unsigned head_bits = 0;
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    const KeyT kk = key[r];
+                    const KeyT pv = r == 0 ? prev_last : key[r > 0 ? r - 1 : 0];
+                    const bool first = (lane == 0 && r == 0);
+                    const bool h = (kk != KEY_MAX) && (first || (pv >> wbits) != (kk >> wbits));
+                    heads += h;
+                    head_bits |= (unsigned)h << r;
+                }
+                int total;
+                int rank = group_excl_scan<false>(heads, scan_scratch, total);
+                constexpr int kSortN = 32 * KPL;
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    if (head_bits & (1u << r)) {
+                        const KeyT node = key[r] >> wbits;
+                        double sum = 0.0;
+                        for (int q = lane * KPL + r; q < kSortN; ++q) {
+                            const KeyT kq = keys[q];
+                            if ((kq >> wbits) != node) break;
+                            sum = __dadd_rn(sum, loads[si * W + (int)(kq & wmask)]);
                         }
+                        out_col[off + rank] = (int32_t)node;
+                        out_sum[off + rank] = sum;
+                        ++rank;
                     }
-                    group_sync<kBlock>();
                 }
-            }
-            // distinct nodes = run heads of the sorted keys; thread tg owns a
-            // contiguous chunk so that ranks follow column order
-            const int lo = tg * chunk;
-            const int hi = min(Wp, lo + chunk);
-            int heads = 0;
-            for (int i = lo; i < hi; ++i) {
-                const KeyT key = keys[i];
-                if (key == KEY_MAX) break;
-                heads += (i == 0) || ((keys[i - 1] >> wbits) != (key >> wbits));
-            }
-            int total;
-            int rank = group_excl_scan<kBlock>(heads, scan_scratch, total);
-            for (int i = lo; i < hi; ++i) {
-                const KeyT key = keys[i];
-                if (key == KEY_MAX) break;
-                const KeyT node = key >> wbits;
-                if ((i == 0) || ((keys[i - 1] >> wbits) != node)) {
-                    double sum = 0.0;
-                    for (int q = i; q < Wp; ++q) {
-                        const KeyT kq = keys[q];
-                        if ((kq >> wbits) != node) break;
-                        sum = __dadd_rn(sum, loads[si * W + (int)(kq & wmask)]);
+                if (lane == 0) p.row_cnt[row * L + si + 1] = total;
+                off += total;
+                __syncwarp();
+            } else {
+                for (int i = tg; i < Wp; i += GS) {
+                    KeyT key = KEY_MAX;
+                    if (i < W) {
+                        const int32_t nd = nodes[si * W + i];
+                        if (nd >= 0) key = ((KeyT)(uint32_t)nd << wbits) | (KeyT)i;
                     }
-                    out_col[off + rank] = (int32_t)node;
-                    out_sum[off + rank] = sum;
-                    ++rank;
+                    keys[i] = key;
                 }
+                __syncthreads();
+                for (uint32_t k = 2; k <= (uint32_t)Wp; k <<= 1) {
+                    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                        for (uint32_t c = tg; c < (uint32_t)Wp / 2; c += GS) {
+                            const uint32_t idx = ((c & ~(j - 1)) << 1) | (c & (j - 1));
+                            const uint32_t ixj = idx | j;
+                            const KeyT a = keys[idx], b = keys[ixj];
+                            const bool up = (idx & k) == 0;
+                            if ((a > b) == up) {
+                                keys[idx] = b;
+                                keys[ixj] = a;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                // distinct nodes = run heads of the sorted keys; thread tg owns a
+                // contiguous chunk so that ranks follow column order
+                const int lo = tg * chunk;
+                const int hi = min(Wp, lo + chunk);
+                int heads = 0;
+                for (int i = lo; i < hi; ++i) {
+                    const KeyT key = keys[i];
+                    if (key == KEY_MAX) break;
+                    heads += (i == 0) || ((keys[i - 1] >> wbits) != (key >> wbits));
+                }
+                int total;
+                int rank = group_excl_scan<true>(heads, scan_scratch, total);
+                for (int i = lo; i < hi; ++i) {
+                    const KeyT key = keys[i];
+                    if (key == KEY_MAX) break;
+                    const KeyT node = key >> wbits;
+                    if ((i == 0) || ((keys[i - 1] >> wbits) != node)) {
+                        double sum = 0.0;
+                        for (int q = i; q < Wp; ++q) {
+                            const KeyT kq = keys[q];
+                            if ((kq >> wbits) != node) break;
+                            sum = __dadd_rn(sum, loads[si * W + (int)(kq & wmask)]);
+                        }
+                        out_col[off + rank] = (int32_t)node;
+                        out_sum[off + rank] = sum;
+                        ++rank;
+                    }
+                }
+                if (tg == 0) p.row_cnt[row * L + si + 1] = total;
+                off += total;
+                __syncthreads();
             }
-            if (tg == 0) p.row_cnt[row * L + si + 1] = total;
-            off += total;
-            group_sync<kBlock>();
         }
     }
 
@@ -232,9 +328,9 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
     }
 }
 
-template <bool kBlock, typename KeyT>
+template <bool kBlock, typename KeyT, int KPL>
 static int launch_walk(const WalkParams &p, size_t smem, int threads, int grid, cudaStream_t stream) {
-    auto kern = walk_merge_kernel<kBlock, KeyT>;
+    auto kern = walk_merge_kernel<kBlock, KeyT, KPL>;
     GRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(p);
     return check_cuda(cudaGetLastError(), "walk_merge_kernel launch");
@@ -306,19 +402,33 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     const size_t steps = (size_t)(p.L - 1);
     p.loads_bytes = (uint32_t)(steps * p.W * 8);
     p.nodes_bytes = (uint32_t)((steps * p.W * 4 + 7) & ~(size_t)7);
-    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + (size_t)p.Wp * key_size + 15) & ~(size_t)15;
+    const bool warp_variant = p.W <= 256;
+    const int kpl = p.Wp <= 32 ? 1 : p.Wp / 32;  // warp variant sorts 32*kpl keys
+    const size_t n_keys = warp_variant ? (size_t)32 * kpl : (size_t)p.Wp;
+    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + n_keys * key_size + 15) & ~(size_t)15;
     p.group_bytes = (uint32_t)gb;
     const size_t kMaxSmem = 227 * 1024 - 256;
     GRF_REQUIRE((uint64_t)p.W * (uint64_t)p.L < (1ull << 31), "grf_walk: W*L too large");
 
     cudaStream_t st = (cudaStream_t)stream;
-    const bool warp_variant = p.W <= 256 && 4 * gb <= 96 * 1024;
     if (warp_variant) {
         const int warps = 4;
         const int64_t want = (n_local + warps - 1) / warps;
         const int grid = (int)(want < (int64_t)kSmCount * 64 ? want : (int64_t)kSmCount * 64);
-        return key32 ? launch_walk<false, uint32_t>(p, warps * gb, warps * 32, grid, st)
-                     : launch_walk<false, unsigned long long>(p, warps * gb, warps * 32, grid, st);
+        const size_t smem = warps * gb;
+        const int threads = warps * 32;
+#define GRF_WALK_CASE(K)                                                                              \
+    case K:                                                                                           \
+        return key32 ? launch_walk<false, uint32_t, K>(p, smem, threads, grid, st)                   \
+                     : launch_walk<false, unsigned long long, K>(p, smem, threads, grid, st)
+        switch (kpl) {
+            GRF_WALK_CASE(1);
+            GRF_WALK_CASE(2);
+            GRF_WALK_CASE(4);
+            default:
+                GRF_WALK_CASE(8);
+        }
+#undef GRF_WALK_CASE
     }
     if (gb > kMaxSmem)
         return fail(GRF_ERR_UNSUPPORTED,
@@ -326,6 +436,6 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
                     kMaxSmem);
     const int64_t want = n_local;
     const int grid = (int)(want < (int64_t)kSmCount * 32 ? want : (int64_t)kSmCount * 32);
-    return key32 ? launch_walk<true, uint32_t>(p, gb, 256, grid, st)
-                 : launch_walk<true, unsigned long long>(p, gb, 256, grid, st);
+    return key32 ? launch_walk<true, uint32_t, 0>(p, gb, 256, grid, st)
+                 : launch_walk<true, unsigned long long, 0>(p, gb, 256, grid, st);
 }

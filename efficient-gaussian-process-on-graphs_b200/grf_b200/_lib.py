@@ -20,6 +20,7 @@ DRAW_PHILOX, DRAW_REPLAY = 0, 1
 LOAD_CUMULATIVE, LOAD_LAST_STEP, LOAD_ABLATION = 0, 1, 2
 SCALE_MUL_RECIP, SCALE_DIV = 0, 1
 ORDER_ROW_MAJOR, ORDER_STEP_MAJOR = 0, 1
+ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
 
 # every symbol include/grf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = (

@@ -274,6 +274,8 @@ class PhiBlocks:
     matvec time so it can be a learnable parameter."""
 
     def __init__(self, blk_ptr, entries, n_rows, n_cols, n_steps, row_lo=0, visits=0):
+        if max(n_rows, n_cols) > (1 << _lib.ENTRY_STEP_SHIFT) or n_steps > (1 << (32 - _lib.ENTRY_STEP_SHIFT)):
+            raise ValueError("Phi blocks hold at most 2^27 rows/columns per GPU and 32 walk lengths")
         self.blk_ptr, self.entries = blk_ptr, entries
         self.n_rows, self.n_cols, self.n_steps, self.row_lo = n_rows, n_cols, n_steps, row_lo
         self.tblk_ptr = None
@@ -393,6 +395,10 @@ class PhiBlocks:
         res = self.apply(f, u, rows=x1, out=out)
         return res[:, 0] if squeeze else res
 
+    def plan(self, f, t: int, x1=None, x2=None, group=None) -> "MatvecPlan":
+        """Pre-validated kernel matvec for a CG loop: one C call (two launches) per product."""
+        return MatvecPlan(self, f, t, x1, x2, group)
+
     def t_matvec(self, f, v, x2=None) -> torch.Tensor:
         """U = Phi[x2]^T v  ([n_cols, t]) in a fresh buffer."""
         return self.apply_t(f, v, rows=x2)
@@ -467,7 +473,7 @@ class PhiBlocks:
 
         ptr = self.blk_ptr.cpu().numpy().astype(np.int64)
         ent = self.entries.cpu().numpy()
-        cols = ent[:, 0] if self.nnz else np.zeros(0, np.int32)
+        cols = (ent[:, 0] & ((1 << _lib.ENTRY_STEP_SHIFT) - 1)) if self.nnz else np.zeros(0, np.int32)
         vals = ent[:, 1].copy().view(np.float32) if self.nnz else np.zeros(0, np.float32)
         L, n = self.n_steps, self.n_rows
         mats = []
@@ -559,3 +565,57 @@ def phi_blocks_from_torch_csr(tensors, row_lo: int = 0, transpose: bool = True) 
     sm = StepMatrices(torch.cat(offs).contiguous(), torch.cat(cols).contiguous(), torch.cat(vals).contiguous(),
                       n_rows, n_cols, len(tensors), row_lo)
     return PhiBlocks.from_step_matrices(sm, transpose=transpose)
+
+
+class MatvecPlan:
+    """``out = Phi[x1] (Phi[x2]^T v)`` with everything but ``v`` / ``out`` fixed.
+
+    A CG solve calls the kernel matvec hundreds of times with the same Phi, f,
+    index sets and shapes; the plan keeps the argument block,
+    the U workspace and the scatter buffer alive so that a product is a single
+    ``grf_phi_matvec`` call -- or, for a row-sharded Phi (``group``), the first
+    half, one all-reduce of U over NCCL, and the second half."""
+
+    def __init__(self, phi: PhiBlocks, f, t: int, x1=None, x2=None, group=None):
+        phi.build_transpose()
+        dev = phi.device
+        self.phi, self.t, self.group = phi, int(t), group
+        self.f = phi._f(f)
+        self.x1, self.x2 = phi._ids(x1, dev), phi._ids(x2, dev)
+        self.n1 = phi.n_rows if self.x1 is None else self.x1.numel()
+        self.n2 = phi.n_rows if self.x2 is None else self.x2.numel()
+        self.ldu = (self.t + 3) // 4 * 4
+        self.u = torch.empty((max(1, phi.n_cols), self.ldu), dtype=torch.float32, device=dev)
+        self.vfull = (torch.empty((max(1, phi.n_rows), self.ldu), dtype=torch.float32, device=dev)
+                      if self.x2 is not None else None)
+        self._c = phi.c_struct()
+        self._fn = _lib.lib().grf_phi_matvec
+        self._dev = dev
+
+    def set_modulator(self, f) -> None:
+        self.f.copy_(torch.as_tensor(f, device=self._dev).detach().to(torch.float32).reshape(-1))
+
+    def _call(self, v, out, which):
+        rc = self._fn(ctypes.byref(self._c), _ptr(self.f), _ptr(self.x1), self.n1, _ptr(self.x2), self.n2,
+                      None if v is None else ctypes.c_void_p(v.data_ptr()), 0 if v is None else v.stride(0),
+                      None if out is None else ctypes.c_void_p(out.data_ptr()), 0 if out is None else out.stride(0),
+                      _ptr(self.u), self.ldu, _ptr(self.vfull), self.t, which, _stream(self._dev))
+        if rc:
+            check(rc)
+
+    def __call__(self, v: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """v: float32 [n2, t] with unit column stride; out: float32 [n1, t] (allocated if None)."""
+        if v.dtype != torch.float32 or v.dim() != 2 or v.shape[0] != self.n2 or v.shape[1] != self.t \
+                or v.stride(1) != 1:
+            raise ValueError("plan: v must be float32 [n2, t] with unit column stride")
+        if out is None:
+            out = torch.zeros((self.n1, self.t), dtype=torch.float32, device=self._dev)
+        if self.group is None:
+            self._call(v, out, 3)
+        else:
+            import torch.distributed as dist
+
+            self._call(v, None, 1)
+            dist.all_reduce(self.u, group=None if self.group is True else self.group)
+            self._call(None, out, 2)
+        return out

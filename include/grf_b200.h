@@ -23,8 +23,10 @@
  *   step matrices   (reference layout) one CSR per walk length l, concatenated:
  *                   offsets int64[L*n_rows + 1] step-major, col int32, val double
  *   Phi blocks      (matvec layout) block CSR, row-major over (row, length):
- *                   blk_ptr int32[n_rows*L + 1], entries {int32 col; float val}
- *   Phi^T blocks    same, over (column, length), entries {int32 local_row; float val}
+ *                   blk_ptr int32[n_rows*L + 1], entries {int32 length<<27 | col; float val};
+ *                   the L segments of a row are contiguous, so blk_ptr[r*L] and
+ *                   blk_ptr[(r+1)*L] bound the whole row
+ *   Phi^T blocks    same, over (column, length), entries {int32 length<<27 | local_row; float val}
  */
 #ifndef GRF_B200_H
 #define GRF_B200_H
@@ -51,6 +53,11 @@ enum { GRF_LOAD_CUMULATIVE = 0, GRF_LOAD_LAST_STEP = 1, GRF_LOAD_ABLATION = 2 };
 enum { GRF_SCALE_MUL_RECIP = 0, GRF_SCALE_DIV = 1 };
 enum { GRF_ORDER_ROW_MAJOR = 0, GRF_ORDER_STEP_MAJOR = 1 };
 
+/* One stored element of Phi (or Phi^T) in the matvec layout: `col` holds the
+ * column (Phi) or local row (Phi^T) in its low GRF_ENTRY_STEP_SHIFT bits and
+ * the walk length l of the M_l it belongs to in the bits above, so N and the
+ * rows per GPU are limited to 2^27 and L to 32. */
+#define GRF_ENTRY_STEP_SHIFT 27
 typedef struct {
     int32_t col;
     float val;

@@ -75,13 +75,15 @@ def test_transpose_is_exact_and_row_sorted(env, case):
     L, n = phi.n_steps, phi.n_cols
     tptr = phi.tblk_ptr.cpu().numpy().astype(np.int64)
     tent = phi.tentries.cpu().numpy()
-    rows, vals = tent[:, 0], tent[:, 1].copy().view(np.float32)
+    rows, vals = tent[:, 0] & ((1 << 27) - 1), tent[:, 1].copy().view(np.float32)
+    steps_of = tent[:, 0] >> 27
     for s, m in enumerate(case["mats"]):
         mt = m.astype(np.float32).T.tocsr()
         mt.sort_indices()
         for c in range(n):
             b, e = tptr[c * L + s], tptr[c * L + s + 1]
             assert np.array_equal(rows[b:e], mt.indices[mt.indptr[c]:mt.indptr[c + 1]])
+            assert np.all(steps_of[b:e] == s)
             assert np.array_equal(vals[b:e], mt.data[mt.indptr[c]:mt.indptr[c + 1]])
 
 
@@ -93,7 +95,7 @@ def test_transpose_with_hub_columns_uses_the_long_segment_sort(env):
     tptr = phi.tblk_ptr.cpu().numpy().astype(np.int64)
     seg = np.diff(tptr)
     assert seg.max() > 48, "test graph should have hub columns"
-    rows = phi.tentries.cpu().numpy()[:, 0]
+    rows = phi.tentries.cpu().numpy()[:, 0] & ((1 << 27) - 1)
     for g0 in np.flatnonzero(seg > 1):
         r = rows[tptr[g0]:tptr[g0 + 1]]
         assert np.all(r[1:] > r[:-1])
@@ -149,6 +151,23 @@ def test_matvec_row_subsets(env, case, t):
     got2 = phi.matvec(torch.tensor(f), torch.tensor(v).cuda(), x1=torch.tensor(x1, dtype=torch.float32)[:, None].cuda(),
                       x2=torch.tensor(x2, dtype=torch.float32)[:, None].cuda()).cpu().numpy()
     assert _close(got2, got, rtol=1e-6)      # repeated ids are scatter-added with atomics: order may differ
+
+
+def test_matvec_plan_equals_matvec(env, case):
+    """The CG fast path (one C call per product) gives the same numbers as the checked path."""
+    torch = env["torch"]
+    phi = case["phi"]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    f = torch.randn(phi.n_steps, device="cuda", generator=gen)
+    for t, x1, x2 in [(16, None, None), (5, None, None), (16, torch.arange(0, 600, 3), torch.arange(100, 700, 2))]:
+        n2 = phi.n_rows if x2 is None else x2.numel()
+        v = torch.randn(n2, t, device="cuda", generator=gen)
+        want = phi.matvec(f, v, x1=x1, x2=x2).clone()
+        plan = phi.plan(f, t, x1=x1, x2=x2)
+        got = plan(v)
+        assert torch.equal(got, want)
+        plan.set_modulator(2 * f)
+        assert torch.allclose(plan(v), 4 * want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
 
 
 def test_apply_and_apply_t_are_the_two_halves(env, case):
