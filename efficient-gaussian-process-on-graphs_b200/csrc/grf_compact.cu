@@ -245,41 +245,114 @@ __global__ void __launch_bounds__(256) transpose_fill_kernel(const int32_t *blk_
 
 // Slots inside one (column, length) segment were claimed in arbitrary order;
 // order them by row so that the layout (and the fp32 summation order of
-// Phi^T V) is deterministic.  Segments are short except for hub columns, so:
-// one thread per short segment (insertion sort), one CTA per long segment
-// (bitonic sort in global memory over the next power of two).
-constexpr int kShortSeg = 48;
+// Phi^T V) is deterministic.  Three tiers by segment length:
+//   <= 32   one thread per segment: keys (row << 5 | slot) sorted by a register
+//           sorting network (rows are unique and < 2^27, so the key is 32 bits),
+//           values re-read through the sorted slot index;
+//   <= 256  one warp per segment, register bitonic sort with shuffles;
+//   longer  (hub columns) one CTA per segment, bitonic network in global memory.
+// (v1 used a per-thread insertion sort in global memory: 420 us at config 2.)
+constexpr int kTinySeg = 8;
+constexpr int kShortSeg = 32;
+constexpr int kMidSeg = 256;
 
-__global__ void __launch_bounds__(256) transpose_sort_short_kernel(const int32_t *tblk_ptr, int64_t n_segs,
-                                                                   GrfEntry *tentries, int32_t *long_list,
-                                                                   int32_t *long_count) {
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_segs;
-         g += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t b = tblk_ptr[g], e = tblk_ptr[g + 1];
-        const int32_t len = e - b;
-        if (len <= 1) continue;
-        if (len > kShortSeg) {
-            long_list[atomicAdd(long_count, 1)] = (int32_t)g;
-            continue;
-        }
-        for (int32_t i = b + 1; i < e; ++i) {
-            const GrfEntry x = tentries[i];
-            int32_t j = i - 1;
-            while (j >= b && tentries[j].col > x.col) {
-                tentries[j + 1] = tentries[j];
-                --j;
-            }
-            tentries[j + 1] = x;
+template <int C>
+__device__ __forceinline__ void sort_segment_regs(GrfEntry *seg, int len) {
+    uint32_t key[C];
+    const uint32_t step_bits = (uint32_t)seg[0].col & ~kColMask;
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+        key[i] = i < len ? ((((uint32_t)seg[i].col & kColMask) << 5) | (uint32_t)i) : 0xffffffffu;
+    sort_network_u32<C>(key);
+    float val[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) val[i] = i < len ? seg[key[i] & 31u].val : 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        if (i < len) {
+            GrfEntry e;
+            e.col = (int32_t)(step_bits | (key[i] >> 5));
+            e.val = val[i];
+            seg[i] = e;
         }
     }
 }
 
+// lists: [0] = number of mid segments, [1] = number of long segments, then the two lists
+__global__ void __launch_bounds__(128) transpose_sort_short_kernel(const int32_t *tblk_ptr, int64_t n_segs,
+                                                                   GrfEntry *tentries, int32_t *counts,
+                                                                   int32_t *mid_list, int32_t *long_list) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_segs;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t b = tblk_ptr[g];
+        const int32_t len = tblk_ptr[g + 1] - b;
+        if (len <= 1) continue;
+        if (len <= kTinySeg) {
+            sort_segment_regs<kTinySeg>(tentries + b, len);
+        } else if (len <= kShortSeg) {
+            sort_segment_regs<kShortSeg>(tentries + b, len);
+        } else if (len <= kMidSeg) {
+            mid_list[atomicAdd(&counts[0], 1)] = (int32_t)g;   // grows upwards
+        } else {
+            long_list[-atomicAdd(&counts[1], 1)] = (int32_t)g;  // grows downwards from the end
+        }
+    }
+}
+
+template <int KPL>
+__device__ __forceinline__ void sort_segment_warp(GrfEntry *seg, int len, int lane) {
+    unsigned long long key[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const int i = r * 32 + lane;
+        unsigned long long kk = ~0ull;
+        if (i < len) {
+            const GrfEntry e = seg[i];
+            kk = ((unsigned long long)(uint32_t)e.col << 32) | (unsigned long long)(uint32_t)__float_as_int(e.val);
+        }
+        key[r] = kk;
+    }
+    __syncwarp();
+    warp_bitonic_sort<unsigned long long, KPL>(key, lane);
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const int i = lane * KPL + r;
+        if (i < len) {
+            GrfEntry e;
+            e.col = (int32_t)(uint32_t)(key[r] >> 32);
+            e.val = __int_as_float((int)(uint32_t)key[r]);
+            seg[i] = e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) transpose_sort_mid_kernel(const int32_t *tblk_ptr, GrfEntry *tentries,
+                                                                 const int32_t *counts, const int32_t *mid_list) {
+    const int lane = threadIdx.x & 31;
+    const int n_mid = counts[0];
+    const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    for (int li = warp0; li < n_mid; li += nwarps) {
+        const int32_t g = mid_list[li];
+        const int32_t b = tblk_ptr[g];
+        const int len = tblk_ptr[g + 1] - b;
+        GrfEntry *seg = tentries + b;
+        if (len <= 64)
+            sort_segment_warp<2>(seg, len, lane);
+        else if (len <= 128)
+            sort_segment_warp<4>(seg, len, lane);
+        else
+            sort_segment_warp<8>(seg, len, lane);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(512) transpose_sort_long_kernel(const int32_t *tblk_ptr, GrfEntry *tentries,
-                                                                  const int32_t *long_list,
-                                                                  const int32_t *long_count) {
-    const int32_t n_long = *long_count;
+                                                                  const int32_t *counts,
+                                                                  const int32_t *long_list) {
+    const int32_t n_long = counts[1];
     for (int32_t li = blockIdx.x; li < n_long; li += gridDim.x) {
-        const int32_t g = long_list[li];
+        const int32_t g = long_list[-li];
         const int32_t b = tblk_ptr[g];
         const uint32_t len = (uint32_t)(tblk_ptr[g + 1] - b);
         const uint32_t np2 = next_pow2(len);
@@ -444,15 +517,20 @@ extern "C" int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entrie
     transpose_fill_kernel<<<grid_for_warps(n_rows, 256), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps, cursor,
                                                                         tentries);
     GRF_CUDA_OK(cudaGetLastError());
-    // deterministic order inside every segment; `cursor` is dead now and is
-    // reused as [count | list of long segments] (hence its n_cols*L + 1 ints)
-    GRF_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(int32_t), st));
+    // deterministic order inside every segment; `cursor` is dead now and is reused for the
+    // work lists: [n_mid, n_long | mid list growing up ... long list growing down]; at most
+    // n_segs segments are listed in total, which is what the n_segs + 2 ints of scratch hold
+    GRF_CUDA_OK(cudaMemsetAsync(cursor, 0, 2 * sizeof(int32_t), st));
     if (n_segs >= 2) {
-        int64_t g = (n_segs + 255) / 256;
-        if (g > (int64_t)kSmCount * 32) g = (int64_t)kSmCount * 32;
-        transpose_sort_short_kernel<<<(int)g, 256, 0, st>>>(tblk_ptr, n_segs, tentries, cursor + 1, cursor);
+        int64_t g = (n_segs + 127) / 128;
+        if (g > (int64_t)kSmCount * 64) g = (int64_t)kSmCount * 64;
+        int32_t *mid_list = cursor + 2;
+        int32_t *long_list = cursor + 2 + (n_segs - 1);
+        transpose_sort_short_kernel<<<(int)g, 128, 0, st>>>(tblk_ptr, n_segs, tentries, cursor, mid_list, long_list);
         GRF_CUDA_OK(cudaGetLastError());
-        transpose_sort_long_kernel<<<kSmCount * 2, 512, 0, st>>>(tblk_ptr, tentries, cursor + 1, cursor);
+        transpose_sort_mid_kernel<<<kSmCount * 8, 128, 0, st>>>(tblk_ptr, tentries, cursor, mid_list);
+        GRF_CUDA_OK(cudaGetLastError());
+        transpose_sort_long_kernel<<<kSmCount * 2, 512, 0, st>>>(tblk_ptr, tentries, cursor, long_list);
     }
     return check_cuda(cudaGetLastError(), "transpose kernels launch");
 }

@@ -29,6 +29,7 @@ struct Vec<4> {
     float4 v;
     __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void load(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void load_shared(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
     __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
     __device__ __forceinline__ void fma(float a, const Vec &x) {
         v.x = fmaf(a, x.v.x, v.x);
@@ -45,6 +46,7 @@ struct Vec<1> {
     float v;
     __device__ __forceinline__ void zero() { v = 0.f; }
     __device__ __forceinline__ void load(const float *p) { v = __ldg(p); }
+    __device__ __forceinline__ void load_shared(const float *p) { v = *p; }
     __device__ __forceinline__ void store(float *p) const { *p = v; }
     __device__ __forceinline__ void fma(float a, const Vec &x) { v = fmaf(a, x.v, v); }
     __device__ __forceinline__ float dot(const Vec &x) const { return v * x.v; }
@@ -73,14 +75,62 @@ __device__ __forceinline__ GrfEntry load_entry(const GrfEntry *p) {
 // stalled on long-scoreboard per issue and 0.42 entries/cycle/SM.)
 constexpr int kEPL = 4;  // entries per lane per round
 
-template <int TPR>
-__device__ __forceinline__ unsigned group_mask() {
-    if constexpr (TPR == 32) {
-        return 0xffffffffu;
-    } else {
-        const unsigned lane = threadIdx.x & 31u;
-        return ((1u << TPR) - 1u) << (lane & ~(unsigned)(TPR - 1));
+// One row for the TPR lanes that own it.  `X` is either global memory (ldx = leading
+// dimension) or, for the tiled kernel, the shared-memory copy of X[cmin .. cmax, :]
+// (then `col_off` = cmin).  Returns the accumulator of this lane's VEC columns.
+//
+// All 32 lanes of the warp call this together and run the same number of rounds (the
+// longest row of the warp's 32/TPR rows decides), so every shuffle uses the constant full
+// mask: with a per-group mask nvcc expands each __shfl_sync into a MATCH/REDUX/VOTE loop
+// (ncu: ~10 extra instructions per shuffle, 4.6 warp-instructions per entry).
+template <int TPR, int VEC, bool kShared>
+__device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int32_t b, int32_t e,
+                                             const float *__restrict__ fs, const float *X, int64_t ldx,
+                                             int32_t col_off, int c0, bool live, int sub) {
+    constexpr unsigned gmask = 0xffffffffu;
+    const int32_t b_end = b + __reduce_max_sync(0xffffffffu, e - b);  // warp-uniform trip count
+    Vec<VEC> acc;
+    acc.zero();
+    int2 nxt[kEPL];
+#pragma unroll
+    for (int q = 0; q < kEPL; ++q) {
+        const int32_t idx = b + q * TPR + sub;
+        nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
     }
+    for (int32_t base = b; base < b_end; base += TPR * kEPL) {
+        int cl[kEPL];
+        float sv[kEPL];
+#pragma unroll
+        for (int q = 0; q < kEPL; ++q) {
+            cl[q] = (int)((uint32_t)nxt[q].x & kColMask) - col_off;
+            sv[q] = __int_as_float(nxt[q].y) * fs[(uint32_t)nxt[q].x >> kStepShift];
+        }
+        const int32_t nb = base + TPR * kEPL;
+        if (nb < e) {
+#pragma unroll
+            for (int q = 0; q < kEPL; ++q) {
+                const int32_t idx = nb + q * TPR + sub;
+                nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kEPL; ++q) {
+#pragma unroll
+            for (int j = 0; j < TPR; ++j) {
+                const int c = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
+                const float a = TPR == 1 ? sv[q] : __shfl_sync(gmask, sv[q], j, TPR);
+                if (live && base + q * TPR + j < e) {
+                    Vec<VEC> x;
+                    if (kShared)
+                        x.load_shared(X + (int64_t)c * ldx + c0);
+                    else
+                        x.load(X + (int64_t)c * ldx + c0);
+                    acc.fma(a, x);
+                }
+            }
+        }
+    }
+    return acc;
 }
 
 template <int TPR, int VEC>
@@ -95,60 +145,137 @@ __global__ void __launch_bounds__(256) spmm_blocks_kernel(const int32_t *__restr
     if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
     __syncthreads();
     const int sub = threadIdx.x % TPR;
-    const unsigned gmask = group_mask<TPR>();
-    const int64_t task0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
-    const int64_t task_stride = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    constexpr int kGroupsPerWarp = 32 / TPR;
+    const int g_in_warp = (threadIdx.x & 31) / TPR;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
-    for (int64_t k = task0; k < n_tasks; k += task_stride) {
-        const int64_t row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
-        if (row < 0 || row >= n_rows) continue;  // uniform across the TPR lanes of the group
-        const int32_t b = __ldg(ptr + row * L);
-        const int32_t e = __ldg(ptr + (row + 1) * L);
-        const int n_tiles = (t + TPR * VEC - 1) / (TPR * VEC);
+    const int n_tiles = (t + TPR * VEC - 1) / (TPR * VEC);
+    // warp-uniform loop: the warp takes 32/TPR consecutive tasks per iteration
+    for (int64_t kb = warp0 * kGroupsPerWarp; kb < n_tasks; kb += warp_stride * kGroupsPerWarp) {
+        const int64_t k = kb + g_in_warp;
+        int64_t row = -1;
+        if (k < n_tasks) row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
+        const bool mine = row >= 0 && row < n_rows;  // ids outside this shard are skipped
+        int32_t b = 0, e = 0;
+        if (mine) {
+            b = __ldg(ptr + row * L);
+            e = __ldg(ptr + (row + 1) * L);
+        }
         for (int tile = 0; tile < n_tiles; ++tile) {
             // lanes whose columns fall outside t (t not a multiple of TPR*VEC) still help with the
             // entry loads and shuffles; they just do not gather or store
             const int c0 = (tile * TPR + sub) * VEC;
-            const bool live = c0 < t;
-            Vec<VEC> acc;
-            acc.zero();
-            int2 nxt[kEPL];
-#pragma unroll
-            for (int q = 0; q < kEPL; ++q) {
-                const int32_t idx = b + q * TPR + sub;
-                nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
-            }
-            for (int32_t base = b; base < e; base += TPR * kEPL) {
-                int cl[kEPL];
-                float sv[kEPL];
-#pragma unroll
-                for (int q = 0; q < kEPL; ++q) {
-                    cl[q] = (int)((uint32_t)nxt[q].x & kColMask);
-                    sv[q] = __int_as_float(nxt[q].y) * fs[(uint32_t)nxt[q].x >> kStepShift];
-                }
-                const int32_t nb = base + TPR * kEPL;
-                if (nb < e) {
-#pragma unroll
-                    for (int q = 0; q < kEPL; ++q) {
-                        const int32_t idx = nb + q * TPR + sub;
-                        nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < kEPL; ++q) {
-#pragma unroll
-                    for (int j = 0; j < TPR; ++j) {
-                        const int c = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
-                        const float a = TPR == 1 ? sv[q] : __shfl_sync(gmask, sv[q], j, TPR);
-                        if (live && base + q * TPR + j < e) {
-                            Vec<VEC> x;
-                            x.load(X + (int64_t)c * ldx + c0);
-                            acc.fma(a, x);
-                        }
-                    }
-                }
-            }
+            const bool live = mine && c0 < t;
+            const Vec<VEC> acc = spmm_row<TPR, VEC, false>(ent2, b, e, fs, X, ldx, 0, c0, live, sub);
             if (live) acc.store(Y + k * ldy + c0);
+        }
+    }
+}
+
+// Tiled variant for banded Phi (lattices, rings, any ordering with locality): a CTA owns
+// `chunk_rows` consecutive rows; the union of their column windows (precomputed per 32
+// rows by grf_block_windows) is copied once, coalesced, into shared memory -- up to
+// 224 KB of X -- and every gather of the chunk is then a shared-memory read: half the
+// L1 wavefronts per entry of a global gather, no tag lookups, no L2 round trips.  A
+// chunk whose window does not fit (long-range edges) takes the global-gather path.
+template <int TPR>
+__global__ void __launch_bounds__(1024, 1) spmm_tiled_kernel(const int32_t *__restrict__ ptr,
+                                                             const GrfEntry *__restrict__ ent,
+                                                             const float *__restrict__ f, int32_t L,
+                                                             int64_t n_rows, int32_t chunk_rows,
+                                                             const int2 *__restrict__ win, int32_t cap_rows,
+                                                             const float *__restrict__ X, int64_t ldx,
+                                                             float *__restrict__ Y, int64_t ldy, int32_t t) {
+    extern __shared__ __align__(16) float tile[];
+    __shared__ float fs[kMaxSteps];
+    __shared__ int s_min, s_max;
+    if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
+    const int sub = threadIdx.x % TPR;
+    const int gid = threadIdx.x / TPR;
+    const int ngroups = blockDim.x / TPR;
+    const int g_in_warp = (threadIdx.x & 31) / TPR;
+    const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
+    const int c0 = sub * 4;
+    const int ldt = (t + 3) & ~3;  // tile leading dimension (floats)
+    const int64_t n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t r0 = chunk * chunk_rows;
+        const int64_t r1 = min(n_rows, r0 + chunk_rows);
+        if (threadIdx.x == 0) {
+            s_min = 0x7fffffff;
+            s_max = -1;
+        }
+        __syncthreads();
+        for (int64_t g = r0 / 32 + threadIdx.x; g <= (r1 - 1) / 32; g += blockDim.x) {
+            const int2 w = __ldg(win + g);
+            if (w.y >= w.x) {
+                atomicMin(&s_min, w.x);
+                atomicMax(&s_max, w.y);
+            }
+        }
+        __syncthreads();
+        const int cmin = s_min, cmax = s_max;
+        const int width = cmax - cmin + 1;
+        const bool tiled = width > 0 && width <= cap_rows;
+        if (tiled) {
+            const int vec_per_row = ldt >> 2;
+            const int n_vec = width * vec_per_row;
+            for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+                const int r = i / vec_per_row, q = i - r * vec_per_row;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(X + (int64_t)(cmin + r) * ldx) + q);
+                reinterpret_cast<float4 *>(tile)[i] = v;
+            }
+        }
+        __syncthreads();
+        // warp-uniform loop over the chunk's rows (32/TPR consecutive rows per warp and iteration)
+        for (int64_t rb = r0 + gid - g_in_warp; rb < r1; rb += ngroups) {
+            const int64_t row = rb + g_in_warp;
+            const bool mine = row < r1;
+            int32_t b = 0, e = 0;
+            if (mine) {
+                b = __ldg(ptr + row * L);
+                e = __ldg(ptr + (row + 1) * L);
+            }
+            const bool live = mine && c0 < t;
+            Vec<4> acc;
+            if (tiled)
+                acc = spmm_row<TPR, 4, true>(ent2, b, e, fs, tile, ldt, cmin, c0, live, sub);
+            else
+                acc = spmm_row<TPR, 4, false>(ent2, b, e, fs, X, ldx, 0, c0, live, sub);
+            if (live) acc.store(Y + row * ldy + c0);
+        }
+        __syncthreads();
+    }
+}
+
+// Column window [min col, max col] of every group of 32 consecutive rows (one warp each),
+// and the widest window over all groups (atomicMax into *max_width).
+__global__ void __launch_bounds__(256) block_windows_kernel(const int32_t *__restrict__ ptr,
+                                                            const GrfEntry *__restrict__ ent, int64_t n_rows,
+                                                            int32_t L, int2 *__restrict__ win,
+                                                            int32_t *__restrict__ max_width) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_groups = (n_rows + 31) / 32;
+    for (int64_t g = warp0; g < n_groups; g += nwarps) {
+        const int64_t r0 = g * 32, r1 = min(n_rows, r0 + 32);
+        const int32_t b = __ldg(ptr + r0 * L), e = __ldg(ptr + r1 * L);
+        int lo = 0x7fffffff, hi = -1;
+        for (int32_t i = b + lane; i < e; i += 32) {
+            const int c = (int)((uint32_t)ent[i].col & kColMask);
+            lo = min(lo, c);
+            hi = max(hi, c);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+        }
+        if (lane == 0) {
+            win[g] = make_int2(lo, hi);
+            if (hi >= lo) atomicMax(max_width, hi - lo + 1);
         }
     }
 }
@@ -236,6 +363,54 @@ static Shape pick_shape(int32_t t, bool vec_ok) {
 
 static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
+constexpr size_t kTileSmemBytes = 224 * 1024;
+
+// Launch the tiled kernel if the windows say the matrix is banded enough; returns 1 if launched,
+// 0 if the caller should use the global-gather kernel, negative on error.
+static int try_launch_tiled(const int32_t *ptr, const GrfEntry *ent, const float *f, int32_t L, int64_t n_rows,
+                            const int32_t *win, int32_t max_width, const float *X, int64_t ldx, float *Y,
+                            int64_t ldy, int32_t t, cudaStream_t st) {
+    if (!win || max_width <= 0 || t % 4 != 0 || t > 128 || n_rows < 64) return 0;
+    const int ldt = (t + 3) & ~3;
+    const int64_t cap_rows = (int64_t)(kTileSmemBytes / ((size_t)ldt * sizeof(float)));
+    int tpr = 1;
+    while (tpr * 4 < t) tpr <<= 1;
+    // rows per chunk: the largest multiple of 32 such that (a) the chunk's window fits and (b) the
+    // number of chunks is a multiple of the SM count (one resident CTA per SM)
+    int64_t chunk = 0;
+    for (int k = 1; k <= 64; ++k) {
+        int64_t r = (n_rows + (int64_t)kSmCount * k - 1) / ((int64_t)kSmCount * k);
+        r = (r + 31) / 32 * 32;
+        if (r + max_width + 64 <= cap_rows) {
+            chunk = r;
+            break;
+        }
+    }
+    if (chunk < 64 || max_width > 6 * chunk) return 0;  // too little reuse per staged byte
+    const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
+    const int grid = (int)(n_chunks < kSmCount ? n_chunks : kSmCount);
+    const size_t smem = (size_t)cap_rows * ldt * sizeof(float);
+#define GRF_TILED_CASE(T)                                                                                     \
+    case T: {                                                                                                 \
+        auto kern = spmm_tiled_kernel<T>;                                                                     \
+        GRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kern<<<grid, 1024, smem, st>>>(ptr, ent, f, L, n_rows, (int32_t)chunk, (const int2 *)win,             \
+                                       (int32_t)cap_rows, X, ldx, Y, ldy, t);                                 \
+    } break
+    switch (tpr) {
+        GRF_TILED_CASE(1);
+        GRF_TILED_CASE(2);
+        GRF_TILED_CASE(4);
+        GRF_TILED_CASE(8);
+        GRF_TILED_CASE(16);
+        default:
+            GRF_TILED_CASE(32);
+    }
+#undef GRF_TILED_CASE
+    GRF_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
 static int spmm_grid(int64_t n_tasks, int tpr) {
     const int64_t threads = n_tasks * tpr;
     int64_t g = (threads + 255) / 256;
@@ -277,7 +452,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                               float *vfull, int32_t t, int32_t which, void *stream) {
     GRF_REQUIRE(phi && f, "grf_phi_matvec: null phi/f");
     GRF_REQUIRE(t >= 1, "grf_phi_matvec: t must be >= 1");
-    GRF_REQUIRE(which >= 1 && which <= 3, "grf_phi_matvec: which must be 1, 2 or 3");
+    GRF_REQUIRE((which & 3) >= 1 && which <= 7, "grf_phi_matvec: which must be 1, 2 or 3 (+4: no tiling)");
     GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_matvec: n_steps out of range");
     GRF_REQUIRE(phi->n_cols <= (1ll << kStepShift) && phi->n_rows <= (1ll << kStepShift),
                 "grf_phi_matvec: more than 2^27 rows or columns per GPU");
@@ -286,6 +461,8 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
     GRF_REQUIRE(x2 || n2 == phi->n_rows, "grf_phi_matvec: n2 must equal n_rows when x2 is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t L = phi->n_steps;
+    const int tile_mode = which >> 2;  // bit 2 of `which` set: never use the shared-memory-tiled kernel
+    which &= 3;
 
     if (which & 1) {
         GRF_REQUIRE(v && ldv >= t, "grf_phi_matvec: V missing or ldv < t");
@@ -306,24 +483,40 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         }
         if (phi->n_cols > 0) {
             const bool vec_ok = (t % 4 == 0) && (lds % 4 == 0) && (ldu % 4 == 0) && aligned16(src) && aligned16(u);
-            const Shape sh = pick_shape(t, vec_ok);
-            const int grid = spmm_grid(phi->n_cols, sh.tpr);
-            GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
-                               <<<grid, 256, 0, st>>>(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0,
-                                                      phi->n_cols, src, lds, u, ldu, t));
-            GRF_CUDA_OK(cudaGetLastError());
+            int tiled = 0;
+            if (vec_ok && !(tile_mode & 1)) {
+                tiled = try_launch_tiled(phi->tblk_ptr, phi->tentries, f, L, phi->n_cols, phi->twin,
+                                         phi->twin_max_width, src, lds, u, ldu, t, st);
+                if (tiled < 0) return tiled;
+            }
+            if (!tiled) {
+                const Shape sh = pick_shape(t, vec_ok);
+                const int grid = spmm_grid(phi->n_cols, sh.tpr);
+                GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
+                                   <<<grid, 256, 0, st>>>(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols,
+                                                          0, phi->n_cols, src, lds, u, ldu, t));
+                GRF_CUDA_OK(cudaGetLastError());
+            }
         }
     }
     if ((which & 2) && n1 > 0) {
         GRF_REQUIRE(out && ldo >= t, "grf_phi_matvec: out missing or ldo < t");
         GRF_REQUIRE(phi->blk_ptr, "grf_phi_matvec: Phi blocks missing");
         const bool vec_ok = (t % 4 == 0) && (ldo % 4 == 0) && (ldu % 4 == 0) && aligned16(out) && aligned16(u);
-        const Shape sh = pick_shape(t, vec_ok);
-        const int grid = spmm_grid(n1, sh.tpr);
-        GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
-                           <<<grid, 256, 0, st>>>(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
-                                                  u, ldu, out, ldo, t));
-        GRF_CUDA_OK(cudaGetLastError());
+        int tiled = 0;
+        if (vec_ok && !x1 && !(tile_mode & 1)) {
+            tiled = try_launch_tiled(phi->blk_ptr, phi->entries, f, L, phi->n_rows, phi->win, phi->win_max_width, u,
+                                     ldu, out, ldo, t, st);
+            if (tiled < 0) return tiled;
+        }
+        if (!tiled) {
+            const Shape sh = pick_shape(t, vec_ok);
+            const int grid = spmm_grid(n1, sh.tpr);
+            GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
+                               <<<grid, 256, 0, st>>>(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo,
+                                                      phi->n_rows, u, ldu, out, ldo, t));
+            GRF_CUDA_OK(cudaGetLastError());
+        }
     }
     return GRF_OK;
 }
@@ -344,4 +537,19 @@ extern "C" int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, con
                        <<<grid, 256, 0, (cudaStream_t)stream>>>(phi->blk_ptr, phi->entries, phi->n_steps, x, n,
                                                                 phi->row_lo, phi->n_rows, left, ldl, p, ldp, t, grad));
     return check_cuda(cudaGetLastError(), "fgrad_blocks_kernel launch");
+}
+
+extern "C" int grf_block_windows(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
+                                 int32_t *win, int32_t *max_width, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_block_windows: bad shape");
+    GRF_REQUIRE(max_width, "grf_block_windows: null max_width");
+    cudaStream_t st = (cudaStream_t)stream;
+    GRF_CUDA_OK(cudaMemsetAsync(max_width, 0, sizeof(int32_t), st));
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(blk_ptr && win, "grf_block_windows: null buffer");
+    const int64_t n_groups = (n_rows + 31) / 32;
+    int64_t g = (n_groups + 7) / 8;
+    if (g > (int64_t)kSmCount * 16) g = (int64_t)kSmCount * 16;
+    block_windows_kernel<<<(int)g, 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps, (int2 *)win, max_width);
+    return check_cuda(cudaGetLastError(), "block_windows_kernel launch");
 }

@@ -88,45 +88,6 @@ __device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) 
     return before + incl - v;
 }
 
-// Bitonic sort of 32*KPL keys held KPL per lane (element e = lane*KPL + r): exchanges at
-// distance < KPL stay in registers, larger ones are one shuffle per key.  ~4x fewer issue
-// slots than the shared-memory network it replaces (ncu: the sort was 45 % of all
-// instructions of the kernel).
-template <typename KeyT, int KPL>
-__device__ __forceinline__ void warp_bitonic_sort(KeyT (&key)[KPL], const int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32 * KPL; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= KPL) {
-                const int lj = j / KPL;
-#pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    const KeyT mine = key[r];
-                    const KeyT other = __shfl_xor_sync(0xffffffffu, mine, lj);
-                    const bool up = ((lane * KPL + r) & k) == 0;
-                    const bool lower = (lane & lj) == 0;
-                    const KeyT mn = mine < other ? mine : other;
-                    const KeyT mx = mine < other ? other : mine;
-                    key[r] = (lower == up) ? mn : mx;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    if ((r & j) == 0) {
-                        const bool up = ((lane * KPL + r) & k) == 0;
-                        const KeyT a = key[r], b = key[r | j];
-                        const KeyT mn = a < b ? a : b;
-                        const KeyT mx = a < b ? b : a;
-                        key[r] = up ? mn : mx;
-                        key[r | j] = up ? mx : mn;
-                    }
-                }
-            }
-        }
-    }
-}
-
 // KPL = keys per lane of the warp-per-node variant (sort width 32*KPL >= W); 0 for the
 // CTA-per-node variant, which sorts in shared memory.
 template <bool kBlock, typename KeyT, int KPL>

@@ -26,7 +26,7 @@ ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
 EXPORTS = (
     "grf_abi_version", "grf_last_error", "grf_walk_stage_stride", "grf_walk", "grf_scan_workspace_bytes",
     "grf_scan_counts", "grf_compact_steps", "grf_compact_blocks", "grf_blocks_from_steps", "grf_count_from_steps",
-    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad",
+    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows",
 )
 
 
@@ -43,7 +43,8 @@ class GrfWalkCfg(Structure):
 
 class GrfPhi(Structure):
     _fields_ = [("n_rows", c_int64), ("n_cols", c_int64), ("row_lo", c_int64), ("n_steps", c_int32),
-                ("blk_ptr", c_void_p), ("entries", c_void_p), ("tblk_ptr", c_void_p), ("tentries", c_void_p)]
+                ("blk_ptr", c_void_p), ("entries", c_void_p), ("tblk_ptr", c_void_p), ("tentries", c_void_p),
+                ("win", c_void_p), ("twin", c_void_p), ("win_max_width", c_int32), ("twin_max_width", c_int32)]
 
 
 def nvcc_command(out_path: str = SO_PATH):
@@ -104,6 +105,8 @@ def lib():
     L.grf_transpose_fill.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, vp]
     L.grf_phi_matvec.restype = i32
     L.grf_phi_matvec.argtypes = [POINTER(GrfPhi), vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, vp]
+    L.grf_block_windows.restype = i32
+    L.grf_block_windows.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.grf_phi_fgrad.restype = i32
     L.grf_phi_fgrad.argtypes = [POINTER(GrfPhi), vp, i64, vp, i64, vp, i64, i32, vp, vp]
     if L.grf_abi_version() != 1:

@@ -186,19 +186,40 @@ class StepMatrices:
 
     def to_scipy(self):
         """list[scipy.sparse.csr_matrix] of shape (n_rows, n_cols) -- what
-        get_random_walk_matrices returns (sparse_sampler.py:117-132)."""
+        get_random_walk_matrices returns (sparse_sampler.py:117-132).
+
+        One device->host copy per array into pinned memory (pageable destinations ran at
+        ~2 GB/s), and the matrices are assembled around views of those buffers without
+        scipy re-validating or copying the index arrays."""
         import scipy.sparse as sp
 
-        off = self.offsets.cpu().numpy()
-        col = self.col.cpu().numpy()
-        val = self.val.cpu().numpy()
-        n = self.n_rows
+        n, L = self.n_rows, self.n_steps
+        dev = self.device
+        # per-step row pointers, rebased to 0, as int32 (scipy's index dtype for nnz < 2^31)
+        starts = self.offsets[0:n * L + 1:max(1, n)][:L + 1] if n else torch.zeros(L + 1, dtype=torch.int64,
+                                                                                   device=dev)
+        bounds = starts.cpu().tolist()
+        big = any(bounds[s + 1] - bounds[s] >= 2 ** 31 for s in range(L))
+        idx_dtype = torch.int64 if big else torch.int32
+        ip_dev = torch.empty((L, n + 1), dtype=idx_dtype, device=dev)
+        for s in range(L):
+            ip_dev[s] = (self.offsets[s * n:(s + 1) * n + 1] - bounds[s]).to(idx_dtype) if n else 0
+
+        def fetch(t):
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host.copy_(t, non_blocking=True)
+            return host
+
+        ip_h, col_h, val_h = fetch(ip_dev), fetch(self.col), fetch(self.val)
+        torch.cuda.current_stream(dev).synchronize()
+        ip, col, val = ip_h.numpy(), col_h.numpy(), val_h.numpy()
+        if big:
+            col = col.astype(np.int64)
         mats = []
-        for s in range(self.n_steps):
-            ip = off[s * n: (s + 1) * n + 1]
-            b, e = int(ip[0]), int(ip[-1])
-            m = sp.csr_matrix((val[b:e], col[b:e], (ip - b).astype(np.int32 if e - b < 2 ** 31 else np.int64)),
-                              shape=(n, self.n_cols))
+        for s in range(L):
+            b, e = bounds[s], bounds[s + 1]
+            m = sp.csr_matrix((n, self.n_cols), dtype=np.float64)
+            m.data, m.indices, m.indptr = val[b:e], col[b:e], ip[s]
             m.has_sorted_indices = True
             mats.append(m)
         return mats
@@ -280,6 +301,11 @@ class PhiBlocks:
         self.n_rows, self.n_cols, self.n_steps, self.row_lo = n_rows, n_cols, n_steps, row_lo
         self.tblk_ptr = None
         self.tentries = None
+        self.win = self.twin = None
+        self.win_max_width = self.twin_max_width = 0
+        # shared-memory-tiled matvec for banded Phi: correct and tested, but measured equal to the
+        # global-gather kernel at config 2 (both are bound by L1 wavefronts per entry), so opt-in
+        self.use_tiles = False
         self.visits = visits
         self._ws = {}
 
@@ -301,17 +327,37 @@ class PhiBlocks:
         check(L.grf_transpose_count(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
                                     _ptr(tcnt), _stream(dev)))
         self.tblk_ptr = scan_counts(tcnt, self.n_cols, self.n_steps, _lib.ORDER_ROW_MAJOR, i64=False)
-        cursor = torch.empty(n_seg + 1, dtype=torch.int32, device=dev)
+        cursor = torch.empty(n_seg + 2, dtype=torch.int32, device=dev)
         self.tentries = torch.empty((max(1, self.nnz), 2), dtype=torch.int32, device=dev)[: self.nnz]
         check(L.grf_transpose_fill(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
                                    _ptr(self.tblk_ptr), _ptr(cursor), _ptr(self.tentries), _stream(dev)))
         return self
 
+    def build_windows(self) -> "PhiBlocks":
+        """Column windows per 32 rows of Phi and Phi^T (lets a banded Phi use the tiled matvec)."""
+        self.build_transpose()
+        if self.win is not None or self.nnz == 0 or not self.use_tiles:
+            return self
+        L = _lib.lib()
+        dev = self.device
+        widths = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.win = torch.empty(((self.n_rows + 31) // 32, 2), dtype=torch.int32, device=dev)
+        self.twin = torch.empty(((self.n_cols + 31) // 32, 2), dtype=torch.int32, device=dev)
+        check(L.grf_block_windows(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_steps, _ptr(self.win),
+                                  ctypes.c_void_p(widths.data_ptr()), _stream(dev)))
+        check(L.grf_block_windows(_ptr(self.tblk_ptr), _ptr(self.tentries), self.n_cols, self.n_steps,
+                                  _ptr(self.twin), ctypes.c_void_p(widths.data_ptr() + 4), _stream(dev)))
+        self.win_max_width, self.twin_max_width = (int(x) for x in widths.cpu().tolist())
+        return self
+
     def c_struct(self) -> GrfPhi:
+        tiles = self.use_tiles and self.win is not None
         return GrfPhi(self.n_rows, self.n_cols, self.row_lo, self.n_steps, self.blk_ptr.data_ptr(),
                       self.entries.data_ptr() if self.nnz else None,
                       None if self.tblk_ptr is None else self.tblk_ptr.data_ptr(),
-                      None if self.tentries is None or not self.nnz else self.tentries.data_ptr())
+                      None if self.tentries is None or not self.nnz else self.tentries.data_ptr(),
+                      self.win.data_ptr() if tiles else None, self.twin.data_ptr() if tiles else None,
+                      self.win_max_width if tiles else 0, self.twin_max_width if tiles else 0)
 
     @staticmethod
     def _ids(x, dev):
@@ -340,7 +386,7 @@ class PhiBlocks:
         """U = Phi[rows]^T v: v [n2, t] -> U [n_cols, t] (this GPU's partial sum
         when Phi is row-sharded).  ``out`` may be a [n_cols, >=t] float32 buffer."""
         dev = self.device
-        self.build_transpose()
+        self.build_windows()
         f = self._f(f)
         v = self._rhs(v, dev)
         rows = self._ids(rows, dev)
@@ -363,6 +409,7 @@ class PhiBlocks:
     def apply(self, f, u, rows=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """out = Phi[rows] u: u [n_cols, t] -> [n1, t]."""
         dev = self.device
+        self.build_windows()
         f = self._f(f)
         u = self._rhs(u, dev)
         rows = self._ids(rows, dev)
@@ -577,7 +624,7 @@ class MatvecPlan:
     half, one all-reduce of U over NCCL, and the second half."""
 
     def __init__(self, phi: PhiBlocks, f, t: int, x1=None, x2=None, group=None):
-        phi.build_transpose()
+        phi.build_windows()
         dev = phi.device
         self.phi, self.t, self.group = phi, int(t), group
         self.f = phi._f(f)

@@ -99,6 +99,12 @@ typedef struct {
     const GrfEntry *entries;  /* col = global column */
     const int32_t *tblk_ptr;  /* [n_cols*L + 1] */
     const GrfEntry *tentries; /* col = LOCAL row */
+    /* optional (NULL / 0 = absent): column window {min, max} of every 32 consecutive rows of
+     * Phi (win) and of Phi^T (twin), from grf_block_windows; with them a banded Phi is
+     * multiplied through a shared-memory tile of the right-hand side */
+    const int32_t *win;  /* [ceil(n_rows/32)][2] */
+    const int32_t *twin; /* [ceil(n_cols/32)][2] */
+    int32_t win_max_width, twin_max_width;
 } GrfPhi;
 
 int grf_abi_version(void);
@@ -148,7 +154,7 @@ int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int3
 int grf_transpose_count(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
                         int32_t n_steps, int32_t *tcnt /* [n_cols*L], zeroed by the call */, void *stream);
 int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                       int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor /* [n_cols*L + 1] scratch */,
+                       int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor /* [n_cols*L + 2] scratch */,
                        GrfEntry *tentries, void *stream);
 
 /* Replaces the 2L SparseLinearOperator._matmul calls (sparse_lo.py:16-18), the
@@ -160,10 +166,16 @@ int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t 
  * are left untouched).  V [n2][ldv], out [n1][ldo], U workspace [n_cols][ldu]
  * (= Phi[x2]^T V, this GPU's partial sum: the multi-GPU caller all-reduces it
  * between the two halves); vfull workspace [n_rows][ldu], used when x2 != NULL.
- * which: 1 = first half only (U), 2 = second half only (out from U), 3 = both. */
+ * which: 1 = first half only (U), 2 = second half only (out from U), 3 = both;
+ * add 4 to force the global-gather kernel even when column windows are present. */
 int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t n1, const int32_t *x2,
                    int64_t n2, const float *v, int64_t ldv, float *out, int64_t ldo, float *u, int64_t ldu,
                    float *vfull, int32_t t, int32_t which, void *stream);
+
+/* Column windows for the tiled matvec: win[g] = {min col, max col} over rows [32g, 32g+32)
+ * ({INT_MAX, -1} if empty); *max_width (device int32) = widest window. */
+int grf_block_windows(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
+                      int32_t *win /* [ceil(n_rows/32)][2] */, int32_t *max_width, void *stream);
 
 /* Per-length reduction for the modulator gradient (what upstream
  * _bilinear_derivative yields for sparse_grf_kernel.py:51-62):

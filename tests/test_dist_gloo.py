@@ -1,0 +1,92 @@
+"""The N > 1 path on CPU: world_size-2 gloo, host logic only (shard bounds, the U all-reduce,
+row-sharded CG dot products).  The per-rank halves of the product are played by the float64
+oracle here; on GPUs they are PhiBlocks.apply_t / apply (tests/test_gpu_matvec.py checks that
+those two decompose the same way on one device)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, PKG
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from grf_b200 import sharding
+    from oracle import c_oracle, grf_oracle as orc
+
+    # the same graph / Phi on every rank (CSR graph replicated), rows sharded
+    rng = np.random.default_rng(0)
+    n = 101
+    a = sp.random(n, n, density=0.05, random_state=1, format="csr")
+    a = (a + a.T).tocsr()
+    a.data[:] = 1.0
+    lap = orc.normalized_laplacian_sparse(a)
+    lo, hi = sharding.my_rows(n, world, rank)
+    mats = c_oracle.step_matrices(lap, 12, 0.1, 3, seed=5, start_lo=lo, start_hi=hi)   # this rank's rows only
+    f = np.array([1.0, -0.5, 0.25])
+    phi_g = sum(fl * m for fl, m in zip(f, mats)).tocsr()                               # (n_g, n)
+    v_full = rng.standard_normal((n, 4))
+    v_g = torch.tensor(v_full[lo:hi])
+
+    out_g = sharding.sharded_kernel_matvec(
+        lambda v: torch.tensor(phi_g.T @ v.numpy()), lambda u: torch.tensor(phi_g @ u.numpy()), v_g)
+    dots = sharding.sharded_dot(out_g, v_g)
+    np.save(os.path.join(out_dir, f"out{rank}.npy"), out_g.numpy())
+    np.save(os.path.join(out_dir, f"dots{rank}.npy"), dots.numpy())
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_match_array_split():
+    from grf_b200 import sharding
+
+    for n in (0, 1, 7, 100, 99856, 4_000_003):
+        for w in (1, 2, 3, 8):
+            want = [len(c) for c in np.array_split(np.arange(min(n, 50_000)), w)] if n <= 50_000 else None
+            b = sharding.shard_bounds(n, w)
+            assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0) and np.diff(b).max() - np.diff(b).min() <= 1
+            if want is not None:
+                assert list(np.diff(b)) == want
+    ids = torch.tensor([0, 49, 50, 99, 100])
+    assert sharding.owner_of(ids, 101, 2).tolist() == [0, 0, 0, 1, 1]
+
+
+def test_two_rank_sharded_matvec_equals_unsharded(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from grf_b200 import sharding
+    from oracle import c_oracle, grf_oracle as orc
+
+    rng = np.random.default_rng(0)
+    n = 101
+    a = sp.random(n, n, density=0.05, random_state=1, format="csr")
+    a = (a + a.T).tocsr()
+    a.data[:] = 1.0
+    lap = orc.normalized_laplacian_sparse(a)
+    mats = c_oracle.step_matrices(lap, 12, 0.1, 3, seed=5)
+    v = rng.standard_normal((n, 4))
+    want = orc.phi_matvec_f64(mats, [1.0, -0.5, 0.25], v)
+    got = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)])
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+    dots = [np.load(tmp_path / f"dots{r}.npy") for r in range(world)]
+    assert np.allclose(dots[0], dots[1]) and np.allclose(dots[0], (want * v).sum(0))

@@ -1,0 +1,180 @@
+"""-m gpu tests of the GPyTorch-facing drop-ins: GraphPreprocessor, SparseLinearOperator,
+SparseGRFKernel / SparseDiffusionKernel (forward, autograd through the modulator), on-device
+CG and SparseGraphGP.predict.  gpytorch / linear_operator are not installed here, so the
+kernels run on the stand-in protocol of grf_b200.linop / gp_compat (parity for this layer is
+against float64 numpy, see oracle/__init__.py)."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from gpu_util import csr_bits_equal, grid_graph, random_graph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+
+    assert torch.cuda.is_available()
+    from efficient_graph_gp_sparse.preprocessor import GraphPreprocessor
+
+    adj = random_graph(400, 1300, 21)
+    pp = GraphPreprocessor(adj, walks_per_node=30, p_halt=0.1, max_walk_length=4, random_walk_seed=7, use_tqdm=False)
+    ops = pp.preprocess_graph()
+    return dict(torch=torch, adj=adj, pp=pp, ops=ops)
+
+
+def _phi64(mats, f):
+    return sum(float(fl) * m.astype(np.float32).astype(np.float64) for fl, m in zip(f, mats)).toarray()
+
+
+def test_preprocessor_matches_sampler_and_keeps_reference_surface(setup, tmp_path):
+    from efficient_graph_gp_sparse.preprocessor import GraphPreprocessor
+    from efficient_graph_gp_sparse.random_walk_samplers_sparse import SparseRandomWalk
+    from efficient_graph_gp_sparse.utils_sparse import SparseLinearOperator, get_normalized_laplacian
+
+    pp, ops = setup["pp"], setup["ops"]
+    assert len(ops) == 4 and all(isinstance(o, SparseLinearOperator) for o in ops)
+    assert len(pp.step_matrices_scipy) == 4 and pp.step_matrices_torch is ops
+    direct = SparseRandomWalk(get_normalized_laplacian(setup["adj"]), seed=7).get_random_walk_matrices(30, 0.1, 4)
+    for a, b in zip(pp.step_matrices_scipy, direct):
+        assert csr_bits_equal(a, b)
+    t = ops[1].sparse_csr_tensor
+    assert t.is_sparse_csr and t.dtype == setup["torch"].float32 and t.crow_indices().dtype == setup["torch"].int64
+    assert ops.phi_blocks is not None
+    # pickle cache: same format as the reference (a list of scipy CSR), round trip
+    cache = str(tmp_path / "steps.pkl")
+    pp.save_step_matrices(pp.step_matrices_scipy, cache)
+    again = GraphPreprocessor(setup["adj"], 30, 0.1, 4, 7, load_from_disk=True, cache_filename=cache)
+    for a, b in zip(again.step_matrices_scipy, pp.step_matrices_scipy):
+        assert csr_bits_equal(a, b)
+    with pytest.raises(FileNotFoundError):
+        GraphPreprocessor(setup["adj"], load_from_disk=True, cache_filename=str(tmp_path / "missing.pkl"))
+    with pytest.raises(ValueError, match="square"):
+        GraphPreprocessor(sp.csr_matrix((3, 4)))
+    with pytest.raises(ValueError, match="scipy CSR"):
+        GraphPreprocessor.from_scipy_csr(np.eye(3))
+
+
+def test_sparse_linear_operator_protocol(setup):
+    """sparse_lo.py:4-25 -- _matmul, _size, _transpose_nonbatch (self-check of sparse_lo.py:53-60: SpMM == dense)."""
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.utils_sparse import SparseLinearOperator
+
+    op = setup["ops"][2]
+    dense = setup["pp"].step_matrices_scipy[2].astype(np.float32).astype(np.float64).toarray()
+    rhs = torch.randn(400, 5, device="cuda")
+    assert tuple(op._size()) == (400, 400)
+    got = op._matmul(rhs).cpu().numpy()
+    assert np.allclose(got, dense @ rhs.cpu().numpy().astype(np.float64), rtol=1e-5, atol=1e-5)
+    got_t = op._transpose_nonbatch()._matmul(rhs).cpu().numpy()
+    assert np.allclose(got_t, dense.T @ rhs.cpu().numpy().astype(np.float64), rtol=1e-5, atol=1e-5)
+    assert op._transpose_nonbatch()._transpose_nonbatch() is op
+    assert torch.allclose(op._transpose_nonbatch().sparse_csr_tensor.to_dense(), op.sparse_csr_tensor.to_dense().T)
+    with pytest.raises(ValueError, match="CSR"):
+        SparseLinearOperator(torch.eye(3).cuda())
+
+
+def test_grf_kernel_forward_and_modulator_gradient(setup):
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.gptorch_kernels_sparse import SparseGRFKernel
+
+    torch.manual_seed(42)
+    kern = SparseGRFKernel(max_walk_length=4, step_matrices_torch=setup["ops"]).cuda()
+    assert kern.raw_modulator_vector.shape == (4,) and kern.modulator_vector is kern.raw_modulator_vector
+    f = kern.modulator_vector.detach().cpu().numpy()
+    phi = _phi64(setup["pp"].step_matrices_scipy, f)
+    rng = np.random.default_rng(1)
+    x1 = torch.tensor(rng.permutation(400)[:150], dtype=torch.float32)[:, None].cuda()   # float column, as the models pass it
+    x2 = torch.tensor(rng.permutation(400)[:90], dtype=torch.float32)[:, None].cuda()
+    K = kern(x1, x2)
+    assert tuple(K.shape) == (150, 90)
+    i1, i2 = x1.long().flatten().cpu().numpy(), x2.long().flatten().cpu().numpy()
+    want = phi[i1] @ phi[i2].T
+    assert np.allclose(K.to_dense().detach().cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    # K @ v through the lazy operator, and the gradient of a scalar of it w.r.t. the modulator
+    v = torch.randn(90, 8, device="cuda")
+    g_out = torch.randn(150, 8, device="cuda")
+    loss = (g_out * (K @ v)).sum()
+    loss.backward()
+    from oracle import grf_oracle as orc
+
+    want_grad = orc.phi_fgrad_f64([m.astype(np.float32) for m in setup["pp"].step_matrices_scipy], f,
+                                  g_out.cpu().numpy(), v.cpu().numpy(), x1=i1, x2=i2)
+    got_grad = kern.raw_modulator_vector.grad.cpu().numpy()
+    assert np.allclose(got_grad, want_grad, rtol=2e-4, atol=2e-4 * np.abs(want_grad).max())
+    # full kernel (no index), diag, symmetry / PSD as the reference's tests check for K
+    Kfull = kern.forward().to_dense().detach().cpu().numpy()
+    assert np.allclose(Kfull, Kfull.T, atol=1e-4) and np.linalg.eigvalsh(Kfull.astype(np.float64)).min() > -1e-3
+    d = kern.forward(x1, x1, diag=True).detach().cpu().numpy()
+    assert np.allclose(d, np.sum(phi[i1] ** 2, axis=1), rtol=1e-4, atol=1e-4)
+
+
+def test_diffusion_kernel_modulator_and_gradients(setup):
+    torch = setup["torch"]
+    from efficient_graph_gp.modulation_functions import diffusion_modulator
+    from efficient_graph_gp_sparse.gptorch_kernels_sparse import SparseDiffusionKernel, diffusion_modulator_torch
+
+    kern = SparseDiffusionKernel(max_walk_length=4, step_matrices_torch=setup["ops"]).cuda()
+    beta, sigma = float(kern.beta), float(kern.sigma_f)
+    assert beta > 0 and sigma > 0
+    want = np.array([sigma * diffusion_modulator(l, beta) for l in range(4)])
+    assert np.allclose(kern.modulator_vector.detach().cpu().numpy(), want, rtol=1e-5)
+    assert np.allclose(diffusion_modulator_torch(torch.arange(4), torch.tensor(2.0)).numpy(),
+                       [diffusion_modulator(l, 2.0) for l in range(4)], rtol=1e-6)
+    x = torch.arange(0, 400, 3).cuda()
+    v = torch.randn(x.numel(), 4, device="cuda")
+    loss = (v * (kern(x, x) @ v)).sum()
+    loss.backward()
+    assert kern.raw_beta.grad is not None and kern.raw_sigma_f.grad is not None
+    # d loss / d sigma_f = 2 loss / sigma_f (K is quadratic in sigma_f); chain through softplus
+    dsig = 2 * float(loss) / sigma * float(torch.sigmoid(kern.raw_sigma_f))
+    assert abs(float(kern.raw_sigma_f.grad) - dsig) <= 2e-3 * abs(dsig)
+
+
+def test_cg_posterior_mean_within_1e4_of_direct_solve(setup):
+    """North star: CG posterior means agree to within 1e-4 relative in fp32 (vs a float64 direct solve)."""
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.models import SparseGraphGP
+    from grf_b200.gp_compat import GaussianLikelihood
+
+    torch.manual_seed(0)
+    rng = np.random.default_rng(3)
+    train = rng.permutation(400)[:240]
+    test = np.setdiff1d(np.arange(400), train)
+    y = np.sin(np.arange(400) / 20.0)[train] + 0.1 * rng.standard_normal(240)
+    lik = GaussianLikelihood()
+    lik.noise = 0.1
+    model = SparseGraphGP(torch.tensor(train, dtype=torch.float32)[:, None].cuda(),
+                          torch.tensor(y, dtype=torch.float32).cuda(), lik, setup["ops"], 4).cuda()
+    f = model.covar_module.modulator_vector.detach().cpu().numpy()
+    phi = _phi64(setup["pp"].step_matrices_scipy, f)
+    Ktt = phi[train] @ phi[train].T + float(lik.noise) * np.eye(240)
+    want = phi[test] @ phi[train].T @ np.linalg.solve(Ktt, y.astype(np.float32).astype(np.float64))
+    got, info = model.posterior_mean(torch.tensor(test).cuda(), cg_tolerance=1e-7, return_info=True)
+    rel = np.linalg.norm(got.cpu().numpy() - want) / np.linalg.norm(want)
+    assert rel <= 1e-4, (rel, info)
+    # pathwise samples: right shape, finite, and centred on the mean
+    samples, info = model.predict(torch.tensor(test).cuda(), n_samples=200, cg_tolerance=1e-4, return_info=True)
+    assert tuple(samples.shape) == (200, test.size) and bool(torch.isfinite(samples).all())
+    post_var = np.diag(phi[test] @ phi[test].T - phi[test] @ phi[train].T @ np.linalg.solve(Ktt, phi[train] @ phi[test].T))
+    z = (samples.mean(0).cpu().numpy() - want) / np.sqrt(np.maximum(post_var, 1e-12) / 200)
+    assert np.mean(np.abs(z) < 4) > 0.97
+
+
+def test_device_cg_matches_oracle_cg_semantics(setup):
+    torch = setup["torch"]
+    from grf_b200.cg import linear_cg
+    from oracle import grf_oracle as orc
+
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((60, 60))
+    a = a @ a.T + 60 * np.eye(60)
+    b = rng.standard_normal((60, 3))
+    want = orc.linear_cg(lambda v: a @ v, b, tolerance=1e-8)
+    at = torch.tensor(a, dtype=torch.float32).cuda()
+    got = linear_cg(lambda v: at @ v, torch.tensor(b, dtype=torch.float32).cuda(), tolerance=1e-7, check_every=1)
+    assert np.allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+    assert np.allclose(want, np.linalg.solve(a, b), rtol=1e-6, atol=1e-8)

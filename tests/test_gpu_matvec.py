@@ -94,7 +94,7 @@ def test_transpose_with_hub_columns_uses_the_long_segment_sort(env):
     phi = eng.build_phi_blocks(g, eng.WalkConfig(30, 0.1, 3, seed=3))
     tptr = phi.tblk_ptr.cpu().numpy().astype(np.int64)
     seg = np.diff(tptr)
-    assert seg.max() > 48, "test graph should have hub columns"
+    assert seg.max() > 256 and ((seg > 32) & (seg <= 256)).any(), "test graph should exercise every sort tier"
     rows = phi.tentries.cpu().numpy()[:, 0] & ((1 << 27) - 1)
     for g0 in np.flatnonzero(seg > 1):
         r = rows[tptr[g0]:tptr[g0 + 1]]
@@ -151,6 +151,47 @@ def test_matvec_row_subsets(env, case, t):
     got2 = phi.matvec(torch.tensor(f), torch.tensor(v).cuda(), x1=torch.tensor(x1, dtype=torch.float32)[:, None].cuda(),
                       x2=torch.tensor(x2, dtype=torch.float32)[:, None].cuda()).cpu().numpy()
     assert _close(got2, got, rtol=1e-6)      # repeated ids are scatter-added with atomics: order may differ
+
+
+@pytest.mark.parametrize("kind", ["grid", "ring", "periodic_grid"])
+@pytest.mark.parametrize("t", [4, 16, 32, 12])
+def test_tiled_matvec_matches_gather_matvec(env, kind, t):
+    """Banded Phi takes the shared-memory-tiled kernel; it must agree with the global-gather
+    kernel and with float64.  The periodic grid has wrap-around edges, so some chunks have a
+    window that does not fit and fall back inside the same launch."""
+    eng, torch, o = env["eng"], env["torch"], env["o"]
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+    from gpu_util import ring_graph
+
+    if kind == "grid":
+        adj = grid_graph(150, 120)
+    elif kind == "ring":
+        adj = ring_graph(30000)
+    else:
+        nx, ny = 400, 60          # rows of 400 nodes, periodic in y: node i <-> i + (ny-1)*nx
+        adj = grid_graph(nx, ny).tolil()
+        for x in range(nx):
+            adj[x, (ny - 1) * nx + x] = 1.0
+            adj[(ny - 1) * nx + x, x] = 1.0
+        adj = adj.tocsr()
+    lap = get_normalized_laplacian(adj)
+    g = eng.DeviceGraph.from_scipy(lap)
+    phi = eng.build_phi_blocks(g, eng.WalkConfig(20, 0.1, 4, seed=8))
+    phi.use_tiles = True
+    phi.build_windows()
+    assert phi.win is not None and phi.win_max_width > 0
+    gen = torch.Generator(device="cuda").manual_seed(t)
+    f = torch.randn(4, device="cuda", generator=gen)
+    v = torch.randn(phi.n_rows, t, device="cuda", generator=gen)
+    tiled = phi.matvec(f, v).clone()
+    phi.use_tiles = False
+    plain = phi.matvec(f, v).clone()
+    phi.use_tiles = True
+    scale = float(plain.abs().max())
+    assert float((tiled - plain).abs().max()) <= 1e-5 * scale
+    mats32 = phi.to_scipy_steps()
+    want = o.phi_matvec_f64(mats32, f.cpu().numpy(), v.cpu().numpy())
+    assert _close(tiled.cpu().numpy(), want)
 
 
 def test_matvec_plan_equals_matvec(env, case):
