@@ -40,7 +40,8 @@ class SparseGraphGP(ExactGP):
         with torch.no_grad():
             y = self.y_train.to(dev).to(torch.float32).reshape(-1, 1)
             alpha, info = linear_cg(lambda v: K_train_train._matmul(v) + noise_variance * v, y,
-                                    tolerance=cg_tolerance, max_iter=max_cg_iterations, return_info=True)
+                                    tolerance=cg_tolerance, max_iter=max_cg_iterations, eps=1e-30,
+                                    return_info=True)
             out = K_test_train._matmul(alpha)[:, 0]
         return (out, info) if return_info else out
 

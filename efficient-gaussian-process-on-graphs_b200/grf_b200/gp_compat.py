@@ -51,6 +51,10 @@ class _Kernel(torch.nn.Module):
     def __init__(self, **kwargs):
         super().__init__()
 
+    def register_parameter(self, name, parameter=None, param=None):
+        # gpytorch.Module.register_parameter(name, parameter); torch's keyword is `param`
+        super().register_parameter(name, parameter if parameter is not None else param)
+
     def register_constraint(self, param_name, constraint):
         setattr(self, param_name + "_constraint", constraint)
 

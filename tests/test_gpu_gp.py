@@ -173,8 +173,8 @@ def test_device_cg_matches_oracle_cg_semantics(setup):
     a = rng.standard_normal((60, 60))
     a = a @ a.T + 60 * np.eye(60)
     b = rng.standard_normal((60, 3))
-    want = orc.linear_cg(lambda v: a @ v, b, tolerance=1e-8)
+    want = orc.linear_cg(lambda v: a @ v, b, tolerance=1e-8, eps=1e-30)
     at = torch.tensor(a, dtype=torch.float32).cuda()
-    got = linear_cg(lambda v: at @ v, torch.tensor(b, dtype=torch.float32).cuda(), tolerance=1e-7, check_every=1)
+    got = linear_cg(lambda v: at @ v, torch.tensor(b, dtype=torch.float32).cuda(), tolerance=1e-7, check_every=1, eps=1e-30)
     assert np.allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
     assert np.allclose(want, np.linalg.solve(a, b), rtol=1e-6, atol=1e-8)
