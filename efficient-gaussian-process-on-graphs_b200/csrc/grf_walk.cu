@@ -48,7 +48,7 @@ struct WalkParams {
     double *stage_sum;
     int32_t *row_cnt;
     unsigned long long *visits;
-    uint32_t group_bytes, loads_bytes, nodes_bytes;
+    uint32_t group_bytes, loads_bytes, nodes_bytes, sorted_bytes;
 };
 
 template <bool kBlock>
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
     unsigned char *base = smem_raw + (size_t)group_in_cta * p.group_bytes;
     double *loads = reinterpret_cast<double *>(base);                                  // [(L-1)][W]
     int32_t *nodes = reinterpret_cast<int32_t *>(base + p.loads_bytes);                // [(L-1)][W]
-    KeyT *keys = reinterpret_cast<KeyT *>(base + p.loads_bytes + p.nodes_bytes);       // [Wp]
+    double *sorted_loads = reinterpret_cast<double *>(base + p.loads_bytes + p.nodes_bytes);  // [32*KPL], warp variant
+    KeyT *keys = reinterpret_cast<KeyT *>(base + p.loads_bytes + p.nodes_bytes + p.sorted_bytes);  // [Wp | 32*KPL]
     __shared__ int scan_scratch[32];
 
     const int W = p.W, L = p.L, Wp = p.Wp, wbits = p.wbits;
@@ -186,12 +187,18 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
                     key[r] = kk;
                 }
                 warp_bitonic_sort<KeyT, KPL>(key, lane);
+                // park the sorted keys and, in the same order, their loads: the run walk below
+                // is then two sequential shared-memory streams
+                constexpr int kSortN = 32 * KPL;
 #pragma unroll
-                for (int r = 0; r < KPL; ++r) keys[lane * KPL + r] = key[r];
+                for (int r = 0; r < KPL; ++r) {
+                    const KeyT kk = key[r];
+                    keys[lane * KPL + r] = kk;
+                    if (kk != KEY_MAX) sorted_loads[lane * KPL + r] = loads[si * W + (int)(kk & wmask)];
+                }
                 __syncwarp();
                 const KeyT prev_last = __shfl_up_sync(0xffffffffu, key[KPL - 1], 1);
-                int heads = 0;
-                unsigned head_bits = 0;
+                int heads = 0, first_head = -1;
 #pragma unroll
                 for (int r = 0; r < KPL; ++r) {
                     const KeyT kk = key[r];
@@ -199,24 +206,39 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
                     const bool first = (lane == 0 && r == 0);
                     const bool h = (kk != KEY_MAX) && (first || (pv >> wbits) != (kk >> wbits));
                     heads += h;
-                    head_bits |= (unsigned)h << r;
+                    if (h && first_head < 0) first_head = r;
                 }
                 int total;
                 int rank = group_excl_scan<false>(heads, scan_scratch, total);
-                constexpr int kSortN = 32 * KPL;
+                if (first_head >= 0) {
+                    // this lane emits every run that STARTS in its chunk: walk the elements from its
+                    // first head until a run starts in a later chunk; loads are added in walk order
+                    const int chunk_end = (lane + 1) * KPL;
+                    int q = lane * KPL + first_head;
+                    KeyT node = key[0] >> wbits;
 #pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    if (head_bits & (1u << r)) {
-                        const KeyT node = key[r] >> wbits;
-                        double sum = 0.0;
-                        for (int q = lane * KPL + r; q < kSortN; ++q) {
-                            const KeyT kq = keys[q];
-                            if ((kq >> wbits) != node) break;
-                            sum = __dadd_rn(sum, loads[si * W + (int)(kq & wmask)]);
+                    for (int r = 1; r < KPL; ++r)
+                        if (r == first_head) node = key[r] >> wbits;
+                    double sum = 0.0;
+                    for (; q < kSortN; ++q) {
+                        const KeyT kq = keys[q];
+                        const KeyT nd = kq >> wbits;
+                        if (nd != node) {
+                            out_col[off + rank] = (int32_t)node;
+                            out_sum[off + rank] = sum;
+                            ++rank;
+                            if (kq == KEY_MAX || q >= chunk_end) {
+                                node = KEY_MAX;  // nothing pending
+                                break;
+                            }
+                            node = nd;
+                            sum = 0.0;
                         }
+                        sum = __dadd_rn(sum, sorted_loads[q]);
+                    }
+                    if (node != KEY_MAX) {  // ran off the end of the array with a run pending
                         out_col[off + rank] = (int32_t)node;
                         out_sum[off + rank] = sum;
-                        ++rank;
                     }
                 }
                 if (lane == 0) p.row_cnt[row * L + si + 1] = total;
@@ -366,7 +388,8 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     const bool warp_variant = p.W <= 256;
     const int kpl = p.Wp <= 32 ? 1 : p.Wp / 32;  // warp variant sorts 32*kpl keys
     const size_t n_keys = warp_variant ? (size_t)32 * kpl : (size_t)p.Wp;
-    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + n_keys * key_size + 15) & ~(size_t)15;
+    p.sorted_bytes = warp_variant ? (uint32_t)(n_keys * 8) : 0u;
+    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + p.sorted_bytes + n_keys * key_size + 15) & ~(size_t)15;
     p.group_bytes = (uint32_t)gb;
     const size_t kMaxSmem = 227 * 1024 - 256;
     GRF_REQUIRE((uint64_t)p.W * (uint64_t)p.L < (1ull << 31), "grf_walk: W*L too large");
