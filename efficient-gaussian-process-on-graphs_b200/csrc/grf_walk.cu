@@ -18,9 +18,10 @@
 // sides see the same draws.  The merged (column-sorted) per-length segments go
 // to the row's staging region; grf_compact_* turns staging into CSR.
 //
-// Draw sources: Philox4x32-10 keyed by the seed with counter (walk id, step)
-// -- independent of how start nodes are sharded over GPUs -- or a replayed
-// trace of the reference's own PCG64 draws.
+// Draw sources: Philox4x32-10 keyed by the seed with counter (walk id, step / 2)
+// -- one block serves two steps: words (0, 1) halt / pick the even step, words
+// (2, 3) the odd one; independent of how start nodes are sharded over GPUs --
+// or a replayed trace of the reference's own PCG64 draws.
 //
 // Roofline: per executed walk-step the algorithmic traffic is row_ptr pair 8 B
 // + col 4 B + val 8 B + staging write 12 B/(merged entry); three dependent
@@ -34,6 +35,7 @@ struct WalkParams {
     const int32_t *row_ptr;
     const int32_t *col_idx;
     const double *val;
+    const double *scaled_val;
     int64_t start_lo;
     int64_t n_local;
     int32_t W, L, Wp, wbits;
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
             double load = 1.0;
             ++my_visits;  // the length-0 visit (start, 1.0)
             int step = 0;
+            uint32_t x[4] = {0u, 0u, 0u, 0u};  // one Philox block serves two consecutive steps
             for (; step < L - 1; ++step) {
                 const int32_t rs = __ldg(p.row_ptr + cur);
                 const int32_t re = __ldg(p.row_ptr + cur + 1);
@@ -133,24 +136,32 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
                     if (__ldg(p.trace_u + ti) < p.p_halt) break;
                     k = __ldg(p.trace_k + ti);
                 } else {
-                    uint32_t x[4];
-                    philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)step, 0u, p.k0, p.k1, x);
-                    if ((unsigned long long)x[0] < p.halt_thr) break;
-                    const unsigned long long r64 = ((unsigned long long)x[2] << 32) | (unsigned long long)x[1];
-                    k = (int32_t)__umul64hi(r64, (unsigned long long)deg);
+                    uint32_t xh, xk;
+                    if ((step & 1) == 0) {
+                        philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)(step >> 1), 0u, p.k0,
+                                      p.k1, x);
+                        xh = x[0];
+                        xk = x[1];
+                    } else {
+                        xh = x[2];
+                        xk = x[3];
+                    }
+                    if ((unsigned long long)xh < p.halt_thr) break;
+                    k = (int32_t)__umulhi(xk, (uint32_t)deg);
                 }
                 const int64_t e = (int64_t)rs + k;
-                const double wgt = __ldg(p.val + e);
                 const int32_t nxt = __ldg(p.col_idx + e);
-                // load *= degree * weight / (1 - p_halt), evaluated left to right in
-                // float64 with no contraction (sparse_sampler.py:54)
-                const double scaled = __ddiv_rn(__dmul_rn((double)deg, wgt), p.one_minus_p);
-                if (p.load_mode == GRF_LOAD_CUMULATIVE)
-                    load = __dmul_rn(load, scaled);
-                else if (p.load_mode == GRF_LOAD_LAST_STEP)
-                    load = scaled;
-                else
-                    load = wgt;
+                // load *= degree * weight / (1 - p_halt), evaluated left to right in float64 with
+                // no contraction (sparse_sampler.py:54).  (deg * w) / (1 - p) depends on the edge
+                // only, so grf_edge_scale may have computed it once per edge (same roundings).
+                if (p.load_mode == GRF_LOAD_ABLATION) {
+                    load = __ldg(p.val + e);
+                } else {
+                    const double scaled = p.scaled_val
+                                              ? __ldg(p.scaled_val + e)
+                                              : __ddiv_rn(__dmul_rn((double)deg, __ldg(p.val + e)), p.one_minus_p);
+                    load = p.load_mode == GRF_LOAD_CUMULATIVE ? __dmul_rn(load, scaled) : scaled;
+                }
                 cur = nxt;
                 nodes[step * W + w] = cur;  // the visit at length step+1
                 loads[step * W + w] = load;
@@ -356,6 +367,7 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     p.row_ptr = graph->row_ptr;
     p.col_idx = graph->col_idx;
     p.val = graph->val;
+    p.scaled_val = cfg->scaled_val;
     p.start_lo = cfg->start_lo;
     p.n_local = n_local;
     p.W = cfg->walks_per_node;
@@ -422,4 +434,32 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     const int grid = (int)(want < (int64_t)kSmCount * 32 ? want : (int64_t)kSmCount * 32);
     return key32 ? launch_walk<true, uint32_t, 0>(p, gb, 256, grid, st)
                  : launch_walk<true, unsigned long long, 0>(p, gb, 256, grid, st);
+}
+
+namespace grf {
+__global__ void __launch_bounds__(256) edge_scale_kernel(const int32_t *__restrict__ row_ptr,
+                                                         const double *__restrict__ val, int64_t n_nodes,
+                                                         double one_minus_p, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_nodes; r += nwarps) {
+        const int32_t b = row_ptr[r], e = row_ptr[r + 1];
+        const double deg = (double)(e - b);
+        for (int32_t i = b + lane; i < e; i += 32) out[i] = __ddiv_rn(__dmul_rn(deg, val[i]), one_minus_p);
+    }
+}
+}  // namespace grf
+
+extern "C" int grf_edge_scale(const GrfGraph *graph, double p_halt, double *scaled_val, void *stream) {
+    using namespace grf;
+    GRF_REQUIRE(graph, "grf_edge_scale: null graph");
+    GRF_REQUIRE(p_halt >= 0.0 && p_halt <= 1.0, "grf_edge_scale: p_halt must be in [0, 1]");
+    if (graph->n_nodes == 0 || graph->nnz == 0) return GRF_OK;
+    GRF_REQUIRE(graph->row_ptr && graph->val && scaled_val, "grf_edge_scale: null buffer");
+    int64_t g = (graph->n_nodes + 7) / 8;
+    if (g > (int64_t)kSmCount * 32) g = (int64_t)kSmCount * 32;
+    edge_scale_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(graph->row_ptr, graph->val, graph->n_nodes,
+                                                               1.0 - p_halt, scaled_val);
+    return check_cuda(cudaGetLastError(), "edge_scale_kernel launch");
 }

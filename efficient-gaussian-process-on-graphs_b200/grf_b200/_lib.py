@@ -26,7 +26,7 @@ ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
 EXPORTS = (
     "grf_abi_version", "grf_last_error", "grf_walk_stage_stride", "grf_walk", "grf_scan_workspace_bytes",
     "grf_scan_counts", "grf_compact_steps", "grf_compact_blocks", "grf_blocks_from_steps", "grf_count_from_steps",
-    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows",
+    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_scale",
 )
 
 
@@ -38,7 +38,7 @@ class GrfGraph(Structure):
 class GrfWalkCfg(Structure):
     _fields_ = [("start_lo", c_int64), ("start_hi", c_int64), ("walks_per_node", c_int32),
                 ("max_walk_length", c_int32), ("p_halt", c_double), ("draw_mode", c_int32), ("load_mode", c_int32),
-                ("seed", c_uint64), ("trace_u", c_void_p), ("trace_k", c_void_p)]
+                ("seed", c_uint64), ("trace_u", c_void_p), ("trace_k", c_void_p), ("scaled_val", c_void_p)]
 
 
 class GrfPhi(Structure):
@@ -105,6 +105,8 @@ def lib():
     L.grf_transpose_fill.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, vp]
     L.grf_phi_matvec.restype = i32
     L.grf_phi_matvec.argtypes = [POINTER(GrfPhi), vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, vp]
+    L.grf_edge_scale.restype = i32
+    L.grf_edge_scale.argtypes = [POINTER(GrfGraph), c_double, vp, vp]
     L.grf_block_windows.restype = i32
     L.grf_block_windows.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.grf_phi_fgrad.restype = i32

@@ -85,6 +85,7 @@ class DeviceGraph:
             raise ValueError("graph exceeds int32 index range")
         self.n_nodes = int(n_nodes)
         self.nnz = nnz
+        self._scaled = {}
         self.row_ptr = torch.from_numpy(indptr.astype(np.int32, copy=False)).to(self.device, non_blocking=True)
         self.col_idx = torch.from_numpy(np.ascontiguousarray(indices[:nnz]).astype(np.int32, copy=False)).to(
             self.device, non_blocking=True)
@@ -101,6 +102,16 @@ class DeviceGraph:
     def c_struct(self) -> GrfGraph:
         return GrfGraph(self.n_nodes, self.nnz, self.row_ptr.data_ptr(), self.col_idx.data_ptr(),
                         self.val.data_ptr())
+
+    def scaled_val(self, p_halt: float) -> torch.Tensor:
+        """(deg * w) / (1 - p_halt) per edge (cached per p_halt): the load-update factor."""
+        key = float(p_halt)
+        if key not in self._scaled:
+            out = torch.empty(max(1, self.nnz), dtype=torch.float64, device=self.device)
+            g = self.c_struct()
+            check(_lib.lib().grf_edge_scale(ctypes.byref(g), key, _ptr(out), _stream(self.device)))
+            self._scaled = {key: out}
+        return self._scaled[key]
 
 
 @dataclass
@@ -146,9 +157,13 @@ def run_walker(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi:
         if tu.numel() < need or tk.numel() < need:
             raise ValueError("trace arrays must have n_nodes * W * L entries")
     g = graph.c_struct()
+    scaled = None
+    if cfg.load_mode != _lib.LOAD_ABLATION and cfg.max_walk_length > 1 and graph.nnz > 0 and cfg.p_halt < 1.0:
+        scaled = graph.scaled_val(cfg.p_halt)
     c = GrfWalkCfg(start_lo, start_hi, cfg.walks_per_node, cfg.max_walk_length, float(cfg.p_halt), cfg.draw_mode,
                    cfg.load_mode, int(cfg.seed) & 0xFFFFFFFFFFFFFFFF,
-                   None if tu is None else tu.data_ptr(), None if tk is None else tk.data_ptr())
+                   None if tu is None else tu.data_ptr(), None if tk is None else tk.data_ptr(),
+                   None if scaled is None else scaled.data_ptr())
     check(L.grf_walk(ctypes.byref(g), ctypes.byref(c), stride, _ptr(stage_col), _ptr(stage_sum), _ptr(row_cnt),
                      _ptr(visits), _stream(dev)))
     return Staging(stage_col, stage_sum, row_cnt, stride, n_rows, start_lo, visits)

@@ -82,12 +82,16 @@ typedef struct {
     double p_halt;
     int32_t draw_mode;          /* GRF_DRAW_* */
     int32_t load_mode;          /* GRF_LOAD_* */
-    uint64_t seed;              /* Philox key (native mode) */
+    uint64_t seed;              /* Philox key (native mode): counter (walk_lo, walk_hi, step/2, 0); words
+                                 * (0,1) of the block halt / pick at the even step, (2,3) at the odd one;
+                                 * halt iff word < floor(p_halt * 2^32); neighbour = (word * deg) >> 32 */
     /* replay mode: the reference's PCG64 draws, [walk_id*L + step], walk_id =
      * start*W + w; trace_u = rng.random() (NaN where none was drawn), trace_k =
      * rng.integers(deg) (-1 where none) -- sparse_sampler.py:47,51 */
     const double *trace_u;
     const int32_t *trace_k;
+    /* optional: (deg(row) * val) / (1 - p_halt) per edge from grf_edge_scale (NULL: computed per step) */
+    const double *scaled_val;
 } GrfWalkCfg;
 
 typedef struct {
@@ -109,6 +113,10 @@ typedef struct {
 
 int grf_abi_version(void);
 const char *grf_last_error(void); /* host string, thread-local */
+
+/* Per-edge factor of the load update, (deg * w) / (1 - p_halt) with the reference's rounding
+ * order (sparse_sampler.py:54); lets the walker skip a float64 division per step. */
+int grf_edge_scale(const GrfGraph *graph, double p_halt, double *scaled_val /* [nnz] */, void *stream);
 
 /* Staging entries per row the walker may write: 1 + (L-1)*W. */
 int64_t grf_walk_stage_stride(int32_t walks_per_node, int32_t max_walk_length);

@@ -20,8 +20,9 @@
  * Draw sources: 0 = replay of a recorded trace (trace_u / trace_k indexed
  * [walk_id * L + step], walk_id = start * W + w), 1 = the native stream of the
  * CUDA walker: Philox4x32-10 (Salmon et al., SC'11), counter (walk_lo, walk_hi,
- * step, 0), key (seed_lo, seed_hi); word 0 < floor(p * 2^32) halts, words 1..2
- * form x and the neighbour index is (x * deg) >> 64.
+ * step / 2, 0), key (seed_lo, seed_hi); one block serves two steps: words (0, 1)
+ * at the even step, (2, 3) at the odd one; first word < floor(p * 2^32) halts,
+ * the neighbour index is (second word * deg) >> 32.
  *
  * Parity: pinned against reference-generated fixtures via
  * tests/test_oracle_golden.py (C path checked against the numpy path and the
@@ -137,12 +138,12 @@ GrfOracleResult *grf_oracle_build(int64_t n_nodes, const int32_t *indptr, const 
                     if (u < p_halt) break;
                     k = trace_k[walk_id * (uint64_t)L + (uint64_t)step];
                 } else {
-                    const uint32_t ctr[4] = {(uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)step, 0u};
+                    const uint32_t ctr[4] = {(uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)(step >> 1), 0u};
                     uint32_t x[4];
                     grf_oracle_philox(ctr, key, x);
-                    if ((uint64_t)x[0] < halt_thr) break;
-                    const uint64_t r64 = ((uint64_t)x[2] << 32) | (uint64_t)x[1];
-                    k = (int32_t)(((unsigned __int128)r64 * (unsigned __int128)(uint64_t)deg) >> 64);
+                    const uint32_t xh = x[2 * (step & 1)], xk = x[2 * (step & 1) + 1];
+                    if ((uint64_t)xh < halt_thr) break;
+                    k = (int32_t)(((uint64_t)xk * (uint64_t)(uint32_t)deg) >> 32);
                 }
                 const double wgt = data[s + k];
                 /* volatile keeps gcc from contracting into an FMA on any -march */

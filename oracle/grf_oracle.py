@@ -17,7 +17,7 @@ continued step come from:
   ``sparse_sampler.py:47-51``, ``sampler.py:53-56``) and can record the trace.
 * :class:`TraceDraws`     -- replays a recorded ``(trace_u, trace_k)`` pair.
 * :class:`PhiloxDraws`    -- Philox4x32-10 keyed by (seed), counter
-  (walk id, step); the published algorithm of Salmon et al., SC'11
+  (walk id, step // 2); the published algorithm of Salmon et al., SC'11
   (Random123), restated in :func:`philox4x32_10` and pinned against the
   Random123 known-answer vectors in ``tests/test_oracle_golden.py``.
 """
@@ -147,10 +147,10 @@ class TraceDraws:
 
 
 class PhiloxDraws:
-    """Native stream of the CUDA walker: one Philox4x32-10 block per
-    (walk, step): counter = (walk_lo, walk_hi, step, 0), key = (seed_lo,
-    seed_hi); word 0 decides halting, words 1..2 form a 64-bit integer x and
-    the neighbour index is ``(x * deg) >> 64``."""
+    """Native stream of the CUDA walker: one Philox4x32-10 block per walk and PAIR of steps:
+    counter = (walk_lo, walk_hi, step // 2, 0), key = (seed_lo, seed_hi); words (0, 1) serve
+    the even step, words (2, 3) the odd one: the first decides halting
+    (``< floor(p_halt * 2**32)``), the second picks the neighbour ``(word * deg) >> 32``."""
 
     def __init__(self, seed: int):
         self.key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
@@ -158,20 +158,18 @@ class PhiloxDraws:
         self._cache = None
 
     def _block(self, walk_id, step):
-        ck = (walk_id, step)
+        ck = (walk_id, step >> 1)
         if self._cache_key != ck:
-            ctr = np.array([walk_id & 0xFFFFFFFF, (walk_id >> 32) & 0xFFFFFFFF, step, 0], dtype=np.uint32)
+            ctr = np.array([walk_id & 0xFFFFFFFF, (walk_id >> 32) & 0xFFFFFFFF, step >> 1, 0], dtype=np.uint32)
             self._cache = [int(x) for x in philox4x32_10(ctr, self.key)]
             self._cache_key = ck
         return self._cache
 
     def halt(self, walk_id, step, L, p_halt):
-        return self._block(walk_id, step)[0] < halt_threshold(p_halt)
+        return self._block(walk_id, step)[2 * (step & 1)] < halt_threshold(p_halt)
 
     def pick(self, walk_id, step, L, deg):
-        r = self._block(walk_id, step)
-        x = (r[2] << 32) | r[1]
-        return (x * int(deg)) >> 64
+        return (self._block(walk_id, step)[2 * (step & 1) + 1] * int(deg)) >> 32
 
 
 # --------------------------------------------------------------------------
