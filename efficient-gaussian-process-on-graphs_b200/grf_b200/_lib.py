@@ -26,7 +26,7 @@ ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
 EXPORTS = (
     "grf_abi_version", "grf_last_error", "grf_walk_stage_stride", "grf_walk", "grf_scan_workspace_bytes",
     "grf_scan_counts", "grf_compact_steps", "grf_compact_blocks", "grf_blocks_from_steps", "grf_count_from_steps",
-    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_scale",
+    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_scale", "grf_union_rank", "grf_union_fill", "grf_union_materialize",
 )
 
 
@@ -105,6 +105,12 @@ def lib():
     L.grf_transpose_fill.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, vp]
     L.grf_phi_matvec.restype = i32
     L.grf_phi_matvec.argtypes = [POINTER(GrfPhi), vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, vp]
+    L.grf_union_rank.restype = i32
+    L.grf_union_rank.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp]
+    L.grf_union_fill.restype = i32
+    L.grf_union_fill.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    L.grf_union_materialize.restype = i32
+    L.grf_union_materialize.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
     L.grf_edge_scale.restype = i32
     L.grf_edge_scale.argtypes = [POINTER(GrfGraph), c_double, vp, vp]
     L.grf_block_windows.restype = i32

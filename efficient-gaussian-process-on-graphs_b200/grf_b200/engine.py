@@ -322,6 +322,7 @@ class PhiBlocks:
         # global-gather kernel at config 2 (both are bound by L1 wavefronts per entry), so opt-in
         self.use_tiles = False
         self.visits = visits
+        self._union = None
         self._ws = {}
 
     @property
@@ -364,6 +365,54 @@ class PhiBlocks:
                                   _ptr(self.twin), ctypes.c_void_p(widths.data_ptr() + 4), _stream(dev)))
         self.win_max_width, self.twin_max_width = (int(x) for x in widths.cpu().tolist())
         return self
+
+    # ---- union rows: Phi_f = sum_l f[l] M_l materialised on the union pattern ------------
+    def build_union(self) -> "PhiBlocks":
+        """Merge the per-length segments of every row of Phi and Phi^T (once per Phi)."""
+        if self._union is not None:
+            return self
+        self.build_transpose()
+        L = _lib.lib()
+        dev = self.device
+        sides = []
+        for ptr, ent, n in ((self.blk_ptr, self.entries, self.n_rows), (self.tblk_ptr, self.tentries, self.n_cols)):
+            mkey = torch.empty(max(1, self.nnz), dtype=torch.int32, device=dev)
+            mval = torch.empty(max(1, self.nnz), dtype=torch.float32, device=dev)
+            ucnt = torch.empty(max(1, n), dtype=torch.int32, device=dev)
+            check(L.grf_union_rank(_ptr(ptr), _ptr(ent), n, self.n_steps, _ptr(mkey), _ptr(mval), _ptr(ucnt),
+                                   _stream(dev)))
+            uptr = scan_counts(ucnt, n, 1, _lib.ORDER_ROW_MAJOR, i64=False)
+            n_union = int(uptr[-1].item())
+            uhdr = torch.empty((max(1, n_union), 2), dtype=torch.int32, device=dev)[:n_union]
+            check(L.grf_union_fill(_ptr(ptr), _ptr(mkey), n, self.n_steps, _ptr(uptr), _ptr(uhdr), _stream(dev)))
+            sides.append(dict(ptr=ptr, n=n, uptr=uptr, uhdr=uhdr, mval=mval, n_union=n_union))
+            del mkey
+        self._union = sides
+        return self
+
+    @property
+    def nnz_union(self) -> int:
+        self.build_union()
+        return self._union[0]["n_union"]
+
+    def merged(self, f, into: Optional["PhiBlocks"] = None) -> "PhiBlocks":
+        """Phi_f as a single-length PhiBlocks (multiply it with f = [1]).  ``into`` re-uses the
+        buffers of an earlier result (same Phi) when the modulator changed."""
+        self.build_union()
+        L = _lib.lib()
+        dev = self.device
+        f = self._f(f)
+        fwd, tr = self._union
+        if into is None:
+            ent = torch.empty((max(1, fwd["n_union"]), 2), dtype=torch.int32, device=dev)[:fwd["n_union"]]
+            tent = torch.empty((max(1, tr["n_union"]), 2), dtype=torch.int32, device=dev)[:tr["n_union"]]
+            into = PhiBlocks(fwd["uptr"], ent, self.n_rows, self.n_cols, 1, self.row_lo)
+            into.tblk_ptr, into.tentries = tr["uptr"], tent
+        for side, ent in ((fwd, into.entries), (tr, into.tentries)):
+            check(L.grf_union_materialize(_ptr(side["ptr"]), _ptr(side["uptr"]), _ptr(side["uhdr"]),
+                                          _ptr(side["mval"]), _ptr(f), side["n"], self.n_steps, _ptr(ent),
+                                          _stream(dev)))
+        return into
 
     def c_struct(self) -> GrfPhi:
         tiles = self.use_tiles and self.win is not None
@@ -457,9 +506,9 @@ class PhiBlocks:
         res = self.apply(f, u, rows=x1, out=out)
         return res[:, 0] if squeeze else res
 
-    def plan(self, f, t: int, x1=None, x2=None, group=None) -> "MatvecPlan":
+    def plan(self, f, t: int, x1=None, x2=None, group=None, merged: bool = True) -> "MatvecPlan":
         """Pre-validated kernel matvec for a CG loop: one C call (two launches) per product."""
-        return MatvecPlan(self, f, t, x1, x2, group)
+        return MatvecPlan(self, f, t, x1, x2, group, merged)
 
     def t_matvec(self, f, v, x2=None) -> torch.Tensor:
         """U = Phi[x2]^T v  ([n_cols, t]) in a fresh buffer."""
@@ -636,13 +685,24 @@ class MatvecPlan:
     index sets and shapes; the plan keeps the argument block,
     the U workspace and the scatter buffer alive so that a product is a single
     ``grf_phi_matvec`` call -- or, for a row-sharded Phi (``group``), the first
-    half, one all-reduce of U over NCCL, and the second half."""
+    half, one all-reduce of U over NCCL, and the second half.
 
-    def __init__(self, phi: PhiBlocks, f, t: int, x1=None, x2=None, group=None):
-        phi.build_windows()
+    ``merged=True`` (default): the products run on Phi_f materialised on the union
+    pattern of the per-length matrices (``PhiBlocks.merged``), re-materialised by
+    ``set_modulator``; ``merged=False`` applies f per entry on the per-length blocks."""
+
+    def __init__(self, phi: PhiBlocks, f, t: int, x1=None, x2=None, group=None, merged: bool = True):
         dev = phi.device
-        self.phi, self.t, self.group = phi, int(t), group
-        self.f = phi._f(f)
+        self.base, self.merged = phi, bool(merged)
+        self.t, self.group = int(t), group
+        if self.merged:
+            self.phi = phi.merged(f)
+            self.f = torch.ones(1, dtype=torch.float32, device=dev)
+        else:
+            self.phi = phi
+            self.f = phi._f(f).clone()
+        self.phi.use_tiles = phi.use_tiles
+        self.phi.build_windows()
         self.x1, self.x2 = phi._ids(x1, dev), phi._ids(x2, dev)
         self.n1 = phi.n_rows if self.x1 is None else self.x1.numel()
         self.n2 = phi.n_rows if self.x2 is None else self.x2.numel()
@@ -650,12 +710,15 @@ class MatvecPlan:
         self.u = torch.empty((max(1, phi.n_cols), self.ldu), dtype=torch.float32, device=dev)
         self.vfull = (torch.empty((max(1, phi.n_rows), self.ldu), dtype=torch.float32, device=dev)
                       if self.x2 is not None else None)
-        self._c = phi.c_struct()
+        self._c = self.phi.c_struct()
         self._fn = _lib.lib().grf_phi_matvec
         self._dev = dev
 
     def set_modulator(self, f) -> None:
-        self.f.copy_(torch.as_tensor(f, device=self._dev).detach().to(torch.float32).reshape(-1))
+        if self.merged:
+            self.base.merged(f, into=self.phi)
+        else:
+            self.f.copy_(torch.as_tensor(f, device=self._dev).detach().to(torch.float32).reshape(-1))
 
     def _call(self, v, out, which):
         rc = self._fn(ctypes.byref(self._c), _ptr(self.f), _ptr(self.x1), self.n1, _ptr(self.x2), self.n2,

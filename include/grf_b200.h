@@ -185,6 +185,22 @@ int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t
 int grf_block_windows(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
                       int32_t *win /* [ceil(n_rows/32)][2] */, int32_t *max_width, void *stream);
 
+/* Union rows (csrc/grf_union.cu): merge the L per-length segments of every row of Phi (or of
+ * Phi^T -- pass tblk_ptr / tentries and n_cols) on their union pattern, once per Phi:
+ *   grf_union_rank   mkey[nnz] = (col << 5 | length), mval[nnz] = values, both in (col, length)
+ *                    order inside each row; ucnt[r] = distinct columns of row r
+ *   (caller scans ucnt -> uptr with grf_scan_counts(n_rows, 1))
+ *   grf_union_fill   uhdr[nU] = {col, mask of lengths present}
+ * and, per modulator f, grf_union_materialize writes the plain CSR of Phi_f = sum_l f[l] M_l
+ * on that pattern, entries_f[nU] = {col, sum_l f[l] * value}; multiply it with
+ * grf_phi_matvec using n_steps = 1, blk_ptr = uptr, f = [1]. */
+int grf_union_rank(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
+                   uint32_t *mkey, float *mval, int32_t *ucnt, void *stream);
+int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int64_t n_rows, int32_t n_steps,
+                   const int32_t *uptr, int32_t *uhdr /* [nU][2] */, void *stream);
+int grf_union_materialize(const int32_t *blk_ptr, const int32_t *uptr, const int32_t *uhdr, const float *mval,
+                          const float *f, int64_t n_rows, int32_t n_steps, GrfEntry *entries_f, void *stream);
+
 /* Per-length reduction for the modulator gradient (what upstream
  * _bilinear_derivative yields for sparse_grf_kernel.py:51-62):
  *   grad[l] += sum_k sum_t left[k][t] * (M_l[x[k], :] @ P)[t]

@@ -15,7 +15,8 @@ torch.manual_seed(42)
 f = torch.randn(5).cuda()
 v = torch.randn(phi.n_rows, t, device="cuda")
 out = torch.empty_like(v)
-plan = phi.plan(f, t)
+plan = phi.plan(f, t)          # merged Phi_f on the union pattern (default)
+print('nnz per-length', phi.nnz, 'nnz union', phi.nnz_union)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(3):
     plan(v, out)
@@ -36,8 +37,7 @@ for _ in range(50):
     plan(v, out)
 b.record(); torch.cuda.synchronize()
 print(f"back-to-back (L2 warm) us per matvec: {a.elapsed_time(b)*1e3/50:.1f}")
-phi.use_tiles = False
-plan2 = phi.plan(f, t)
+plan2 = phi.plan(f, t, merged=False)
 for _ in range(3):
     plan2(v, out)
 torch.cuda.synchronize()
@@ -49,4 +49,4 @@ for _ in range(reps):
     torch.cuda.synchronize()
     times.append(a.elapsed_time(b) * 1e3)
 times.sort()
-print(f"  no tiles: matvec us: min {times[0]:.1f} median {times[len(times)//2]:.1f} max {times[-1]:.1f}")
+print(f"  per-length blocks (f applied per entry): matvec us: min {times[0]:.1f} median {times[len(times)//2]:.1f} max {times[-1]:.1f}")

@@ -195,7 +195,8 @@ def test_tiled_matvec_matches_gather_matvec(env, kind, t):
 
 
 def test_matvec_plan_equals_matvec(env, case):
-    """The CG fast path (one C call per product) gives the same numbers as the checked path."""
+    """The CG fast paths (one C call per product; per-length blocks or Phi_f merged on the union
+    pattern) give the same numbers as the checked path."""
     torch = env["torch"]
     phi = case["phi"]
     gen = torch.Generator(device="cuda").manual_seed(3)
@@ -204,11 +205,41 @@ def test_matvec_plan_equals_matvec(env, case):
         n2 = phi.n_rows if x2 is None else x2.numel()
         v = torch.randn(n2, t, device="cuda", generator=gen)
         want = phi.matvec(f, v, x1=x1, x2=x2).clone()
-        plan = phi.plan(f, t, x1=x1, x2=x2)
-        got = plan(v)
-        assert torch.equal(got, want)
+        scale = float(want.abs().max())
+        plan = phi.plan(f, t, x1=x1, x2=x2, merged=False)
+        assert torch.equal(plan(v), want)
         plan.set_modulator(2 * f)
-        assert torch.allclose(plan(v), 4 * want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+        assert torch.allclose(plan(v), 4 * want, rtol=1e-5, atol=1e-5 * scale)
+        mplan = phi.plan(f, t, x1=x1, x2=x2)            # merged (default)
+        assert torch.allclose(mplan(v), want, rtol=1e-5, atol=2e-6 * scale)
+        mplan.set_modulator(-0.5 * f)
+        assert torch.allclose(mplan(v), 0.25 * want, rtol=1e-5, atol=2e-6 * scale)
+
+
+def test_union_rows_match_scipy_union(env, case):
+    """The union pattern / merged values against scipy: Phi_f = sum_l f_l M_l (float32 values)."""
+    torch = env["torch"]
+    phi = case["phi"]
+    f = np.array([0.7, -1.3, 0.4, 2.0], dtype=np.float32)
+    mats32 = [m.astype(np.float32) for m in case["mats"]]
+    pattern = sum(abs(m).sign() for m in mats32).tocsr()
+    assert phi.nnz_union == pattern.nnz
+    merged = phi.merged(torch.tensor(f))
+    assert merged.n_steps == 1 and merged.nnz == pattern.nnz
+    want = sum(float(fl) * m.astype(np.float64) for fl, m in zip(f, mats32)).tocsr()
+    want.sort_indices()
+    got = merged.to_scipy_steps()[0]
+    assert np.array_equal(got.indptr, pattern.indptr) and np.array_equal(got.indices, pattern.indices)
+    dense_w = np.zeros(pattern.nnz)
+    wd = want.todok()
+    rows = np.repeat(np.arange(pattern.shape[0]), np.diff(pattern.indptr))
+    ref = np.array(want[rows, pattern.indices]).ravel()
+    assert np.allclose(got.data, ref, rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+    # the transposed side holds the same matrix
+    tptr = merged.tblk_ptr.cpu().numpy()
+    tent = merged.tentries.cpu().numpy()
+    mt = sp.csr_matrix((tent[:, 1].copy().view(np.float32), tent[:, 0], tptr), shape=(phi.n_cols, phi.n_rows))
+    assert abs(mt - got.T).max() == 0
 
 
 def test_apply_and_apply_t_are_the_two_halves(env, case):
