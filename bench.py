@@ -66,6 +66,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -120,7 +129,7 @@ class ClockSampler:
         os.unlink(self.out.name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons),
-                "window": "warm-up + timed steps (20 ms period; the timed region alone is a few ms per step)"}
+                "window": "warm-up + timed steps + the 20 timed CG matvecs (the timed steps alone last a few ms)"}
 
 
 # ------------------------------------------------------------------ reference arm
@@ -220,7 +229,7 @@ def run_gpu(args):
         del st
         phi.row_lo = lo
         _, e_tr = timed(lambda: phi.build_transpose())
-        plan = phi.plan(f, T_RHS, group=True if world > 1 else None)
+        plan = phi.plan(f, T_RHS, group=True if world > 1 else None, merged=False)   # f applied per entry
         out = torch.empty((hi - lo, T_RHS), dtype=torch.float32, device=dev)
         _, e_mv = timed(lambda: plan(v, out))
         return dict(visits=visits, nnz=phi.nnz, n_rows=phi.n_rows,
@@ -244,7 +253,6 @@ def run_gpu(args):
     results = [one_step() for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
 
     phase_ms = {k: sum(r["events"][k][0].elapsed_time(r["events"][k][1]) for r in results)
                 for k in ("walk", "compact", "transpose", "matvec")}
@@ -252,6 +260,26 @@ def run_gpu(args):
     visits_total = sum(int(r["visits"].item()) for r in results)
     nnz = results[-1]["nnz"]
     n_rows = results[-1]["n_rows"]
+
+    # ---- the matvec as a CG solve uses it: Phi_f merged on the union pattern once per modulator, then
+    # many products; every product timed separately with an L2 flush in front
+    st = engine.run_walker(graph, cfg, lo, hi)
+    phi_cg = engine._blocks_from_staging(st, cfg, graph.n_nodes, _lib.SCALE_MUL_RECIP)
+    del st
+    phi_cg.row_lo = lo
+    phi_cg.build_transpose()
+    _, e_union = timed(lambda: phi_cg.build_union())
+    cg_plan, e_mat = timed(lambda: phi_cg.plan(f, T_RHS, group=True if world > 1 else None, merged=True))
+    out_cg = torch.empty((hi - lo, T_RHS), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        cg_plan(v, out_cg)
+    cg_events = [timed(lambda: cg_plan(v, out_cg))[1] for _ in range(20)]
+    torch.cuda.synchronize(dev)
+    cg_ms = sorted(a.elapsed_time(b) for a, b in cg_events)
+    cg_info = {"union_build_ms": e_union[0].elapsed_time(e_union[1]), "materialize_ms": e_mat[0].elapsed_time(e_mat[1]),
+               "matvec_ms_median": cg_ms[len(cg_ms) // 2], "matvec_ms_min": cg_ms[0], "nnz_union": phi_cg.nnz_union}
+    del phi_cg, cg_plan
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the public drop-in call with HOST buffers (host CSR in, scipy CSR list out) + host matvec
     from efficient_graph_gp_sparse.random_walk_samplers_sparse.sparse_sampler import SparseRandomWalk
@@ -282,7 +310,8 @@ def run_gpu(args):
 
     # ---- reduce over ranks: max time, sum of work
     red = torch.tensor([step_ms_total, phase_ms["walk"], phase_ms["compact"], phase_ms["transpose"],
-                        phase_ms["matvec"], e2e_time], dtype=torch.float64, device=dev)
+                        phase_ms["matvec"], e2e_time, cg_info["matvec_ms_median"], cg_info["matvec_ms_min"],
+                        cg_info["union_build_ms"], cg_info["materialize_ms"]], dtype=torch.float64, device=dev)
     work = torch.tensor([visits_total, e2e_visits, nnz], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
@@ -298,6 +327,11 @@ def run_gpu(args):
         n_cols = graph.n_nodes
         mv_bytes = 2 * nnz * 8 + L * (n_rows + 1) * 4 + L * (n_cols + 1) * 4 + (2 * n_rows + 2 * n_cols) * T_RHS * 4
         mv_gbs = mv_bytes / (mv_ms * 1e-3) / 1e9
+        cg_ms_med, cg_ms_min, union_ms, mat_ms = red[6], red[7], red[8], red[9]
+        cg_gbs = mv_bytes / (cg_ms_med * 1e-3) / 1e9
+        nnz_u = cg_info["nnz_union"]
+        layout_bytes = 2 * nnz_u * 8 + (n_rows + 1) * 4 + (n_cols + 1) * 4 + (2 * n_rows + 2 * n_cols) * T_RHS * 4
+        traffic = load_traffic()
         walk_bytes = (work[0] / world / K) * WALK_BYTES_PER_STEP
         walk_gbs = walk_bytes / (walk_ms * 1e-3) / 1e9
         line = {
@@ -310,22 +344,35 @@ def run_gpu(args):
             "phi_build_ms": walk_ms + comp_ms + tr_ms,
             "walker_steps_per_sec": (work[0] / K) / (walk_ms * 1e-3),
             "matvec": {"ms": mv_ms, "algorithmic_gbs": mv_gbs, "nnz_phi_rank0": nnz, "t": T_RHS,
-                       "includes_allreduce": world > 1},
+                       "includes_allreduce": world > 1,
+                       "what": "per-length Phi blocks, modulator applied per entry (inside the timed step)"},
+            "cg_matvec": {"ms": cg_ms_med, "ms_min": cg_ms_min, "algorithmic_gbs": cg_gbs,
+                          "layout_gbs": layout_bytes / (cg_ms_med * 1e-3) / 1e9, "nnz_union_rank0": nnz_u,
+                          "union_build_ms_once_per_phi": union_ms, "materialize_ms_once_per_modulator": mat_ms,
+                          "includes_allreduce": world > 1,
+                          "what": "Phi_f merged on the union pattern (MatvecPlan default): 20 products, L2 flushed "
+                                  "before each, median"},
             "roofline": {"kernel": "walk_merge_kernel (dominant by time)", "bound": "hbm", "achieved": walk_gbs,
-                         "peak": peak, "unit": "GB/s", "frac": walk_gbs / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": walk_gbs / peak,
+                         "traffic": traffic.get("walk_merge_bytes"),
                          "peak_source": peak_src,
                          "note": "latency/sector-bound random gathers: 32 algorithmic B per walk-step, "
                                  "graph L2-resident at this size"},
-            "roofline_matvec": {"kernel": "spmm_blocks_kernel x2 (Phi^T V, Phi U)", "bound": "hbm",
-                                "achieved": mv_gbs, "peak": peak, "unit": "GB/s", "frac": mv_gbs / peak,
-                                "traffic": None, "peak_source": peak_src},
+            "roofline_matvec": {"kernel": "spmm_blocks_kernel x2 (Phi^T V, Phi U) on merged Phi_f (CG path)",
+                                "bound": "hbm", "achieved": cg_gbs, "peak": peak, "unit": "GB/s",
+                                "frac": cg_gbs / peak, "traffic": traffic.get("spmm_merged_pair_bytes"),
+                                "peak_source": peak_src, "algorithmic_bytes": mv_bytes,
+                                "layout_bytes": layout_bytes,
+                                "note": "algorithmic bytes = SURVEY 8d formula on the per-length matrices "
+                                        "(2*nnz*8 + 2*L*(n+1)*4 + 4*N*t*4); the merged layout streams fewer "
+                                        "(layout_bytes); per-length kernel: see matvec"},
             "e2e": {"value": work[1] / red[5], "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * red[5] / e2e_steps,
                     "what": "SparseRandomWalk(host scipy CSR) -> list of host scipy CSR step matrices, plus one "
                             "host-V -> Phi(Phi^T V) -> host matvec"},
-            "gpu_launches": K * 14,
-            "gpu_launches_per_step": {"walk_merge": 1, "scan": 3 + 3, "compact_blocks": 1, "transpose": 4,
-                                      "spmm_blocks": 2},
+            "gpu_launches": K * 15,
+            "gpu_launches_per_step": {"walk_merge": 1, "scan": 3 + 3, "compact_blocks": 1,
+                                      "transpose_count_fill_sort": 5, "spmm_blocks": 2},
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:

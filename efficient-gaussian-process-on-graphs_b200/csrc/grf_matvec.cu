@@ -73,7 +73,9 @@ __device__ __forceinline__ GrfEntry load_entry(const GrfEntry *p) {
 // the current one are consumed, so entry-stream latency hides behind the
 // gather latency.  (v1 walked entry -> gather serially: ncu showed 25 warps
 // stalled on long-scoreboard per issue and 0.42 entries/cycle/SM.)
-constexpr int kEPL = 4;  // entries per lane per round
+// entries per lane per round: a round covers TPR * epl(TPR) entry slots -- 16 for 4..16 lanes per
+// row (rows of the merged Phi average ~28 entries at config 2; more slots only add padding)
+__host__ __device__ constexpr int epl(int tpr) { return tpr >= 16 ? 1 : (tpr >= 4 ? 16 / tpr : 4); }
 
 // One row for the TPR lanes that own it.  `X` is either global memory (ldx = leading
 // dimension) or, for the tiled kernel, the shared-memory copy of X[cmin .. cmax, :]
@@ -85,56 +87,84 @@ constexpr int kEPL = 4;  // entries per lane per round
 // (ncu: ~10 extra instructions per shuffle, 4.6 warp-instructions per entry).
 template <int TPR, int VEC, bool kShared>
 __device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int32_t b, int32_t e,
+                                             int2 (&nxt)[epl(TPR)], int32_t next_b, int32_t next_e,
                                              const float *__restrict__ fs, const float *X, int64_t ldx,
                                              int32_t col_off, int c0, bool live, int sub) {
+    // `nxt` holds the row's first round of entries on entry; on exit it holds the first round
+    // of the NEXT row of this group ([next_b, next_e)), fetched while the last gathers of this
+    // row are in flight -- a two-deep software pipeline across rows (ncu on the one-row-at-a-
+    // time version: 10 warps stalled on long scoreboard per issue, L1 pipe only 40 % busy).
     constexpr unsigned gmask = 0xffffffffu;
+    constexpr int kEPL = epl(TPR);
     const int32_t b_end = b + __reduce_max_sync(0xffffffffu, e - b);  // warp-uniform trip count
     Vec<VEC> acc;
     acc.zero();
-    int2 nxt[kEPL];
-#pragma unroll
-    for (int q = 0; q < kEPL; ++q) {
-        const int32_t idx = b + q * TPR + sub;
-        nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
-    }
-    for (int32_t base = b; base < b_end; base += TPR * kEPL) {
+    int32_t base = b;
+    do {
         int cl[kEPL];
         float sv[kEPL];
 #pragma unroll
         for (int q = 0; q < kEPL; ++q) {
-            cl[q] = (int)((uint32_t)nxt[q].x & kColMask) - col_off;
+            // a padding slot is the all-zero pair: gather row col_off (always valid) with weight 0
+            const bool pad = (nxt[q].x | nxt[q].y) == 0;
+            cl[q] = pad ? 0 : (int)((uint32_t)nxt[q].x & kColMask) - col_off;
             sv[q] = __int_as_float(nxt[q].y) * fs[(uint32_t)nxt[q].x >> kStepShift];
         }
         const int32_t nb = base + TPR * kEPL;
-        if (nb < e) {
+        if (nb < b_end) {
 #pragma unroll
             for (int q = 0; q < kEPL; ++q) {
                 const int32_t idx = nb + q * TPR + sub;
                 nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
             }
-        }
+        } else {
 #pragma unroll
-        for (int q = 0; q < kEPL; ++q) {
-#pragma unroll
-            for (int j = 0; j < TPR; ++j) {
-                const int c = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
-                const float a = TPR == 1 ? sv[q] : __shfl_sync(gmask, sv[q], j, TPR);
-                if (live && base + q * TPR + j < e) {
-                    Vec<VEC> x;
-                    if (kShared)
-                        x.load_shared(X + (int64_t)c * ldx + c0);
-                    else
-                        x.load(X + (int64_t)c * ldx + c0);
-                    acc.fma(a, x);
-                }
+            for (int q = 0; q < kEPL; ++q) {
+                const int32_t idx = next_b + q * TPR + sub;
+                nxt[q] = idx < next_e ? __ldg(ent2 + idx) : make_int2(0, 0);
             }
         }
-    }
+        // Gathers in batches of kBatch independent loads, all unconditional and in bounds
+        // (padding slots read row `col_off` with weight 0): with the loads predicated per
+        // entry nvcc re-used one register quad and serialised load -> FMA -> load (ncu: one
+        // long-scoreboard stall per entry, 16 dependent L2 round trips per round).
+        constexpr int kSlots = TPR * kEPL;
+        constexpr int kBatch = kSlots < 8 ? kSlots : 8;
+#pragma unroll
+        for (int m0 = 0; m0 < kSlots; m0 += kBatch) {
+            Vec<VEC> x[kBatch];
+            float a[kBatch];
+#pragma unroll
+            for (int m = 0; m < kBatch; ++m) {
+                const int q = (m0 + m) / TPR, j = (m0 + m) % TPR;
+                const int c = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
+                a[m] = TPR == 1 ? sv[q] : __shfl_sync(gmask, sv[q], j, TPR);
+                if (kShared)
+                    x[m].load_shared(X + (int64_t)c * ldx + c0);
+                else
+                    x[m].load(X + (int64_t)c * ldx + c0);
+            }
+#pragma unroll
+            for (int m = 0; m < kBatch; ++m) acc.fma(a[m], x[m]);
+        }
+        base = nb;
+    } while (base < b_end);
     return acc;
 }
 
+template <int TPR>
+__device__ __forceinline__ void load_first_round(const int2 *__restrict__ ent2, int32_t b, int32_t e, int sub,
+                                                 int2 (&nxt)[epl(TPR)]) {
+    constexpr int kEPL = epl(TPR);
+#pragma unroll
+    for (int q = 0; q < kEPL; ++q) {
+        const int32_t idx = b + q * TPR + sub;
+        nxt[q] = idx < e ? __ldg(ent2 + idx) : make_int2(0, 0);
+    }
+}
+
 template <int TPR, int VEC>
-__global__ void __launch_bounds__(256) spmm_blocks_kernel(const int32_t *__restrict__ ptr,
+__global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__restrict__ ptr,
                                                           const GrfEntry *__restrict__ ent,
                                                           const float *__restrict__ f, int32_t L,
                                                           const int32_t *__restrict__ row_ids, int64_t n_tasks,
@@ -151,25 +181,42 @@ __global__ void __launch_bounds__(256) spmm_blocks_kernel(const int32_t *__restr
     const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
     const int n_tiles = (t + TPR * VEC - 1) / (TPR * VEC);
-    // warp-uniform loop: the warp takes 32/TPR consecutive tasks per iteration
-    for (int64_t kb = warp0 * kGroupsPerWarp; kb < n_tasks; kb += warp_stride * kGroupsPerWarp) {
-        const int64_t k = kb + g_in_warp;
+    // warp-uniform loop: the warp takes 32/TPR consecutive tasks per iteration; the row bounds of
+    // the next iteration are fetched one iteration ahead, its first entries by spmm_row
+    const int64_t kstride = warp_stride * kGroupsPerWarp;
+    auto bounds = [&](int64_t k, int32_t &b, int32_t &e, bool &mine) {
         int64_t row = -1;
         if (k < n_tasks) row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
-        const bool mine = row >= 0 && row < n_rows;  // ids outside this shard are skipped
-        int32_t b = 0, e = 0;
+        mine = row >= 0 && row < n_rows;  // ids outside this shard are skipped
+        b = e = 0;
         if (mine) {
             b = __ldg(ptr + row * L);
             e = __ldg(ptr + (row + 1) * L);
         }
+    };
+    int64_t kb = warp0 * kGroupsPerWarp;
+    if (kb >= n_tasks) return;
+    int32_t b, e, nb, ne;
+    bool mine, nmine;
+    bounds(kb + g_in_warp, b, e, mine);
+    int2 nxt[epl(TPR)];
+    load_first_round<TPR>(ent2, b, e, sub, nxt);
+    for (; kb < n_tasks; kb += kstride) {
+        const int64_t k = kb + g_in_warp;
+        bounds(k + kstride, nb, ne, nmine);
         for (int tile = 0; tile < n_tiles; ++tile) {
             // lanes whose columns fall outside t (t not a multiple of TPR*VEC) still help with the
             // entry loads and shuffles; they just do not gather or store
             const int c0 = (tile * TPR + sub) * VEC;
             const bool live = mine && c0 < t;
-            const Vec<VEC> acc = spmm_row<TPR, VEC, false>(ent2, b, e, fs, X, ldx, 0, c0, live, sub);
+            const bool last_tile = tile + 1 == n_tiles;
+            const Vec<VEC> acc = spmm_row<TPR, VEC, false>(ent2, b, e, nxt, last_tile ? nb : b, last_tile ? ne : e,
+                                                           fs, X, ldx, 0, c0 < t ? c0 : 0, live, sub);
             if (live) acc.store(Y + k * ldy + c0);
         }
+        b = nb;
+        e = ne;
+        mine = nmine;
     }
 }
 
@@ -196,7 +243,8 @@ __global__ void __launch_bounds__(1024, 1) spmm_tiled_kernel(const int32_t *__re
     const int ngroups = blockDim.x / TPR;
     const int g_in_warp = (threadIdx.x & 31) / TPR;
     const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
-    const int c0 = sub * 4;
+    const int c0 = sub * 4 < t ? sub * 4 : 0;  // lanes beyond t read column 0 and do not store
+    const bool col_live = sub * 4 < t;
     const int ldt = (t + 3) & ~3;  // tile leading dimension (floats)
     const int64_t n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
@@ -229,21 +277,32 @@ __global__ void __launch_bounds__(1024, 1) spmm_tiled_kernel(const int32_t *__re
         }
         __syncthreads();
         // warp-uniform loop over the chunk's rows (32/TPR consecutive rows per warp and iteration)
-        for (int64_t rb = r0 + gid - g_in_warp; rb < r1; rb += ngroups) {
-            const int64_t row = rb + g_in_warp;
-            const bool mine = row < r1;
-            int32_t b = 0, e = 0;
-            if (mine) {
+        auto bounds = [&](int64_t row, int32_t &b, int32_t &e) {
+            b = e = 0;
+            if (row < r1) {
                 b = __ldg(ptr + row * L);
                 e = __ldg(ptr + (row + 1) * L);
             }
-            const bool live = mine && c0 < t;
-            Vec<4> acc;
-            if (tiled)
-                acc = spmm_row<TPR, 4, true>(ent2, b, e, fs, tile, ldt, cmin, c0, live, sub);
-            else
-                acc = spmm_row<TPR, 4, false>(ent2, b, e, fs, X, ldx, 0, c0, live, sub);
-            if (live) acc.store(Y + row * ldy + c0);
+        };
+        int64_t rb = r0 + gid - g_in_warp;
+        if (rb < r1) {
+            int32_t b, e, nb, ne;
+            bounds(rb + g_in_warp, b, e);
+            int2 nxt[epl(TPR)];
+            load_first_round<TPR>(ent2, b, e, sub, nxt);
+            for (; rb < r1; rb += ngroups) {
+                const int64_t row = rb + g_in_warp;
+                bounds(row + ngroups, nb, ne);
+                const bool live = row < r1 && col_live;
+                Vec<4> acc;
+                if (tiled)
+                    acc = spmm_row<TPR, 4, true>(ent2, b, e, nxt, nb, ne, fs, tile, ldt, cmin, c0, live, sub);
+                else
+                    acc = spmm_row<TPR, 4, false>(ent2, b, e, nxt, nb, ne, fs, X, ldx, 0, c0, live, sub);
+                if (live) acc.store(Y + row * ldy + c0);
+                b = nb;
+                e = ne;
+            }
         }
         __syncthreads();
     }
@@ -414,7 +473,7 @@ static int try_launch_tiled(const int32_t *ptr, const GrfEntry *ent, const float
 static int spmm_grid(int64_t n_tasks, int tpr) {
     const int64_t threads = n_tasks * tpr;
     int64_t g = (threads + 255) / 256;
-    const int64_t cap = (int64_t)kSmCount * 16;
+    const int64_t cap = (int64_t)kSmCount * 4;  // 4 resident CTAs of 256 threads per SM at 64 registers
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -481,7 +540,11 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             src = vfull;
             lds = ldu;
         }
-        if (phi->n_cols > 0) {
+        if (phi->n_cols > 0 && phi->n_rows == 0) {
+            // empty shard: its partial sum is zero (and there is no row of V to read)
+            GRF_CUDA_OK(cudaMemset2DAsync(u, (size_t)ldu * sizeof(float), 0, (size_t)t * sizeof(float),
+                                          (size_t)phi->n_cols, st));
+        } else if (phi->n_cols > 0) {
             const bool vec_ok = (t % 4 == 0) && (lds % 4 == 0) && (ldu % 4 == 0) && aligned16(src) && aligned16(u);
             int tiled = 0;
             if (vec_ok && !(tile_mode & 1)) {
