@@ -170,7 +170,13 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
                                                           const int32_t *__restrict__ row_ids, int64_t n_tasks,
                                                           int64_t row_lo, int64_t n_rows,
                                                           const float *__restrict__ X, int64_t ldx,
-                                                          float *__restrict__ Y, int64_t ldy, int32_t t) {
+                                                          float *__restrict__ Y, int64_t ldy, int32_t t,
+                                                          int32_t long_thresh,
+                                                          const int2 *__restrict__ chunk_bounds) {
+    // long_thresh > 0: rows with more entries are left to the chunk launch (hub columns of a
+    // power-law Phi^T hold 10^5..10^6 entries; one 4-lane group would serialise them);
+    // chunk_bounds != NULL: this IS the chunk launch -- task k is the entry range chunk_bounds[k]
+    // and its partial sum goes to row k of Y (the caller's partial buffer).
     __shared__ float fs[kMaxSteps];
     if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
     __syncthreads();
@@ -185,13 +191,26 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
     // the next iteration are fetched one iteration ahead, its first entries by spmm_row
     const int64_t kstride = warp_stride * kGroupsPerWarp;
     auto bounds = [&](int64_t k, int32_t &b, int32_t &e, bool &mine) {
+        b = e = 0;
+        if (chunk_bounds) {
+            mine = k < n_tasks;
+            if (mine) {
+                const int2 be = __ldg(chunk_bounds + k);
+                b = be.x;
+                e = be.y;
+            }
+            return;
+        }
         int64_t row = -1;
         if (k < n_tasks) row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
         mine = row >= 0 && row < n_rows;  // ids outside this shard are skipped
-        b = e = 0;
         if (mine) {
             b = __ldg(ptr + row * L);
             e = __ldg(ptr + (row + 1) * L);
+            if (long_thresh > 0 && e - b > long_thresh) {
+                mine = false;  // split row: written by long_reduce_kernel
+                e = b;
+            }
         }
     };
     int64_t kb = warp0 * kGroupsPerWarp;
@@ -355,6 +374,23 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
     }
 }
 
+// Y[row, :] = sum over the row's chunks (in chunk order: deterministic) of partial[chunk, :]
+__global__ void __launch_bounds__(256) long_reduce_kernel(const int32_t *__restrict__ rows,
+                                                          const int32_t *__restrict__ chunk_ptr,
+                                                          const float *__restrict__ partial, int64_t ldp,
+                                                          float *__restrict__ Y, int64_t ldy, int32_t t,
+                                                          int32_t n_long) {
+    const int64_t total = (int64_t)n_long * t;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t i = (int32_t)(g / t);
+        const int c = (int)(g - (int64_t)i * t);
+        float acc = 0.f;
+        for (int32_t k = chunk_ptr[i]; k < chunk_ptr[i + 1]; ++k) acc += partial[(int64_t)k * ldp + c];
+        Y[(int64_t)rows[i] * ldy + c] = acc;
+    }
+}
+
 // grad[l] += sum_k sum_c left[k, c] * (sum_{e in seg(row_k, l)} e.val * P[e.col, c])
 
 template <int TPR, int VEC>
@@ -479,6 +515,8 @@ static int spmm_grid(int64_t n_tasks, int tpr) {
     return (int)g;
 }
 
+static inline bool aligned16(const void *p);
+
 #define GRF_DISPATCH_SHAPE(KERNEL, shape, ...)                                   \
     do {                                                                         \
         if ((shape).vec == 4) {                                                  \
@@ -505,6 +543,40 @@ static int spmm_grid(int64_t n_tasks, int tpr) {
 }  // namespace grf
 
 using namespace grf;
+
+// One half of the product on one block-CSR side: main launch (+ chunk launch and ordered
+// reduction for rows longer than the split threshold).
+static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float *f, int32_t L,
+                            const int32_t *row_ids, int64_t n_tasks, int64_t row_lo, int64_t n_rows,
+                            const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t,
+                            bool vec_ok, cudaStream_t st) {
+    const Shape sh = pick_shape(t, vec_ok);
+    const bool split = lr && lr->n_long > 0 && !row_ids;
+    if (split) {
+        GRF_REQUIRE(lr->rows && lr->chunk_ptr && lr->chunk_bounds && lr->partial && lr->ld >= t,
+                    "grf_phi_matvec: incomplete long-row metadata");
+    }
+    const int grid = spmm_grid(n_tasks, sh.tpr);
+    GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
+                       <<<grid, 256, 0, st>>>(ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy, t,
+                                              split ? lr->threshold : 0, nullptr));
+    GRF_CUDA_OK(cudaGetLastError());
+    if (split) {
+        const bool pvec = vec_ok && (lr->ld % 4 == 0) && aligned16(lr->partial);
+        const Shape shc = pick_shape(t, pvec);
+        const int gridc = spmm_grid(lr->n_chunks, shc.tpr);
+        GRF_DISPATCH_SHAPE(spmm_blocks_kernel, shc,
+                           <<<gridc, 256, 0, st>>>(ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
+                                                   lr->partial, lr->ld, t, 0, (const int2 *)lr->chunk_bounds));
+        GRF_CUDA_OK(cudaGetLastError());
+        int64_t g = ((int64_t)lr->n_long * t + 255) / 256;
+        if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
+        long_reduce_kernel<<<(int)g, 256, 0, st>>>(lr->rows, lr->chunk_ptr, lr->partial, lr->ld, Y, ldy, t,
+                                                   lr->n_long);
+        GRF_CUDA_OK(cudaGetLastError());
+    }
+    return GRF_OK;
+}
 
 extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t n1, const int32_t *x2,
                               int64_t n2, const float *v, int64_t ldv, float *out, int64_t ldo, float *u, int64_t ldu,
@@ -553,12 +625,9 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                 if (tiled < 0) return tiled;
             }
             if (!tiled) {
-                const Shape sh = pick_shape(t, vec_ok);
-                const int grid = spmm_grid(phi->n_cols, sh.tpr);
-                GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
-                                   <<<grid, 256, 0, st>>>(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols,
-                                                          0, phi->n_cols, src, lds, u, ldu, t));
-                GRF_CUDA_OK(cudaGetLastError());
+                const int rc = launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0,
+                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, st);
+                if (rc != GRF_OK) return rc;
             }
         }
     }
@@ -573,12 +642,9 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             if (tiled < 0) return tiled;
         }
         if (!tiled) {
-            const Shape sh = pick_shape(t, vec_ok);
-            const int grid = spmm_grid(n1, sh.tpr);
-            GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
-                               <<<grid, 256, 0, st>>>(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo,
-                                                      phi->n_rows, u, ldu, out, ldo, t));
-            GRF_CUDA_OK(cudaGetLastError());
+            const int rc = launch_spmm_pass(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
+                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, st);
+            if (rc != GRF_OK) return rc;
         }
     }
     return GRF_OK;

@@ -41,10 +41,16 @@ class GrfWalkCfg(Structure):
                 ("seed", c_uint64), ("trace_u", c_void_p), ("trace_k", c_void_p), ("scaled_val", c_void_p)]
 
 
+class GrfLongRows(Structure):
+    _fields_ = [("threshold", c_int32), ("n_long", c_int32), ("n_chunks", c_int32), ("rows", c_void_p),
+                ("chunk_ptr", c_void_p), ("chunk_bounds", c_void_p), ("partial", c_void_p), ("ld", c_int64)]
+
+
 class GrfPhi(Structure):
     _fields_ = [("n_rows", c_int64), ("n_cols", c_int64), ("row_lo", c_int64), ("n_steps", c_int32),
                 ("blk_ptr", c_void_p), ("entries", c_void_p), ("tblk_ptr", c_void_p), ("tentries", c_void_p),
-                ("win", c_void_p), ("twin", c_void_p), ("win_max_width", c_int32), ("twin_max_width", c_int32)]
+                ("win", c_void_p), ("twin", c_void_p), ("win_max_width", c_int32), ("twin_max_width", c_int32),
+                ("long_fwd", POINTER(GrfLongRows)), ("long_t", POINTER(GrfLongRows))]
 
 
 def nvcc_command(out_path: str = SO_PATH):

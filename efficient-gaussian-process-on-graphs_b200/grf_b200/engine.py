@@ -22,8 +22,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GrfGraph, GrfPhi, GrfWalkCfg, check
+from ._lib import GrfGraph, GrfLongRows, GrfPhi, GrfWalkCfg, check
 
+LONG_ROW_THRESHOLD = 256   # rows of Phi / Phi^T with more entries are split into chunks of this size
 _MAX_STAGE_BYTES = 6 << 30  # staging budget per walker launch; larger shards are walked in row chunks
 
 
@@ -323,6 +324,8 @@ class PhiBlocks:
         self.use_tiles = False
         self.visits = visits
         self._union = None
+        self._long = None       # [fwd, transposed] long-row metadata (dicts) or None per side
+        self._long_c = {}       # ld -> (ctypes structs, partial buffers) kept alive for the calls
         self._ws = {}
 
     @property
@@ -414,14 +417,65 @@ class PhiBlocks:
                                           _stream(dev)))
         return into
 
-    def c_struct(self) -> GrfPhi:
+    def _long_rows_of(self, ptr: torch.Tensor, n: int):
+        """Chunk table for the rows of one side that are longer than LONG_ROW_THRESHOLD (or None)."""
+        if n == 0 or self.nnz == 0:
+            return None
+        L, T = self.n_steps, LONG_ROW_THRESHOLD
+        row_b = ptr[0:n * L:L].to(torch.int64)
+        row_e = ptr[L:n * L + 1:L].to(torch.int64)
+        lens = row_e - row_b
+        rows = torch.nonzero(lens > T).flatten()
+        if rows.numel() == 0:
+            return None
+        nch = (lens[rows] + T - 1) // T
+        chunk_ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=ptr.device)
+        torch.cumsum(nch, 0, out=chunk_ptr[1:])
+        n_chunks = int(chunk_ptr[-1].item())
+        owner = torch.repeat_interleave(torch.arange(rows.numel(), device=ptr.device), nch)
+        local = torch.arange(n_chunks, device=ptr.device) - chunk_ptr[owner]
+        cb = row_b[rows][owner] + local * T
+        ce = torch.minimum(cb + T, row_e[rows][owner])
+        bounds = torch.stack([cb, ce], dim=1).to(torch.int32).contiguous()
+        return dict(rows=rows.to(torch.int32).contiguous(), chunk_ptr=chunk_ptr.to(torch.int32).contiguous(),
+                    bounds=bounds, n_long=int(rows.numel()), n_chunks=n_chunks)
+
+    def build_long_rows(self) -> "PhiBlocks":
+        if self._long is None:
+            self.build_transpose()
+            self._long = [self._long_rows_of(self.blk_ptr, self.n_rows),
+                          self._long_rows_of(self.tblk_ptr, self.n_cols)]
+        return self
+
+    def _long_structs(self, ld: int):
+        """ctypes GrfLongRows for both sides with partial buffers of leading dimension ``ld``."""
+        if self._long is None or ld <= 0:
+            return None, None
+        if ld not in self._long_c:
+            out = []
+            for side in self._long:
+                if side is None:
+                    out.append((None, None))
+                    continue
+                partial = torch.empty((side["n_chunks"], ld), dtype=torch.float32, device=self.device)
+                out.append((GrfLongRows(LONG_ROW_THRESHOLD, side["n_long"], side["n_chunks"],
+                                        side["rows"].data_ptr(), side["chunk_ptr"].data_ptr(),
+                                        side["bounds"].data_ptr(), partial.data_ptr(), ld), partial))
+            self._long_c = {ld: out}
+        (fwd, _), (tr, _) = self._long_c[ld]
+        return fwd, tr
+
+    def c_struct(self, ld: int = 0) -> GrfPhi:
         tiles = self.use_tiles and self.win is not None
+        fwd, tr = self._long_structs(ld)
         return GrfPhi(self.n_rows, self.n_cols, self.row_lo, self.n_steps, self.blk_ptr.data_ptr(),
                       self.entries.data_ptr() if self.nnz else None,
                       None if self.tblk_ptr is None else self.tblk_ptr.data_ptr(),
                       None if self.tentries is None or not self.nnz else self.tentries.data_ptr(),
                       self.win.data_ptr() if tiles else None, self.twin.data_ptr() if tiles else None,
-                      self.win_max_width if tiles else 0, self.twin_max_width if tiles else 0)
+                      self.win_max_width if tiles else 0, self.twin_max_width if tiles else 0,
+                      ctypes.pointer(fwd) if fwd is not None else None,
+                      ctypes.pointer(tr) if tr is not None else None)
 
     @staticmethod
     def _ids(x, dev):
@@ -451,6 +505,7 @@ class PhiBlocks:
         when Phi is row-sharded).  ``out`` may be a [n_cols, >=t] float32 buffer."""
         dev = self.device
         self.build_windows()
+        self.build_long_rows()
         f = self._f(f)
         v = self._rhs(v, dev)
         rows = self._ids(rows, dev)
@@ -464,7 +519,7 @@ class PhiBlocks:
         vfull = None
         if rows is not None:
             vfull = torch.empty((max(1, self.n_rows), u.stride(0)), dtype=torch.float32, device=dev)
-        phi = self.c_struct()
+        phi = self.c_struct((t + 3) // 4 * 4)
         check(_lib.lib().grf_phi_matvec(
             ctypes.byref(phi), _ptr(f), None, self.n_rows, _ptr(rows), n2, _ptr(v), v.stride(0), None, 0,
             _ptr(u), u.stride(0), _ptr(vfull), t, 1, _stream(dev)))
@@ -474,6 +529,7 @@ class PhiBlocks:
         """out = Phi[rows] u: u [n_cols, t] -> [n1, t]."""
         dev = self.device
         self.build_windows()
+        self.build_long_rows()
         f = self._f(f)
         u = self._rhs(u, dev)
         rows = self._ids(rows, dev)
@@ -485,7 +541,7 @@ class PhiBlocks:
             out = torch.zeros((n1, t), dtype=torch.float32, device=dev)
         elif out.shape != (n1, t) or out.dtype != torch.float32 or out.stride(1) != 1:
             raise ValueError("out must be a float32 [n1, t] tensor with unit column stride")
-        phi = self.c_struct()
+        phi = self.c_struct((t + 3) // 4 * 4)
         check(_lib.lib().grf_phi_matvec(
             ctypes.byref(phi), _ptr(f), _ptr(rows), n1, None, self.n_rows, None, 0, _ptr(out), out.stride(0),
             _ptr(u), u.stride(0), None, t, 2, _stream(dev)))
@@ -703,6 +759,7 @@ class MatvecPlan:
             self.f = phi._f(f).clone()
         self.phi.use_tiles = phi.use_tiles
         self.phi.build_windows()
+        self.phi.build_long_rows()
         self.x1, self.x2 = phi._ids(x1, dev), phi._ids(x2, dev)
         self.n1 = phi.n_rows if self.x1 is None else self.x1.numel()
         self.n2 = phi.n_rows if self.x2 is None else self.x2.numel()
@@ -710,7 +767,7 @@ class MatvecPlan:
         self.u = torch.empty((max(1, phi.n_cols), self.ldu), dtype=torch.float32, device=dev)
         self.vfull = (torch.empty((max(1, phi.n_rows), self.ldu), dtype=torch.float32, device=dev)
                       if self.x2 is not None else None)
-        self._c = self.phi.c_struct()
+        self._c = self.phi.c_struct(self.ldu)
         self._fn = _lib.lib().grf_phi_matvec
         self._dev = dev
 

@@ -94,6 +94,20 @@ typedef struct {
     const double *scaled_val;
 } GrfWalkCfg;
 
+/* Optional split of long rows (hub columns of a power-law Phi^T hold 10^5..10^6 entries): rows
+ * with more than `threshold` entries are cut into chunks that are multiplied by separate
+ * thread groups into `partial` and then summed per row in chunk order (deterministic). */
+typedef struct {
+    int32_t threshold;
+    int32_t n_long;
+    int32_t n_chunks;
+    const int32_t *rows;         /* [n_long] ids of the long rows (device) */
+    const int32_t *chunk_ptr;    /* [n_long + 1] first chunk of each long row (device) */
+    const int32_t *chunk_bounds; /* [n_chunks][2] entry range {begin, end} of each chunk (device) */
+    float *partial;              /* [n_chunks][ld] workspace (device) */
+    int64_t ld;                  /* >= t */
+} GrfLongRows;
+
 typedef struct {
     int64_t n_rows;  /* local rows (start nodes owned by this GPU) */
     int64_t n_cols;  /* N */
@@ -109,6 +123,8 @@ typedef struct {
     const int32_t *win;  /* [ceil(n_rows/32)][2] */
     const int32_t *twin; /* [ceil(n_cols/32)][2] */
     int32_t win_max_width, twin_max_width;
+    const GrfLongRows *long_fwd; /* host pointers, NULL = no row of that side is split */
+    const GrfLongRows *long_t;
 } GrfPhi;
 
 int grf_abi_version(void);

@@ -194,6 +194,33 @@ def test_tiled_matvec_matches_gather_matvec(env, kind, t):
     assert _close(tiled.cpu().numpy(), want)
 
 
+def test_hub_rows_are_split_and_still_exact(env):
+    """Power-law Phi: hub columns give Phi^T rows with thousands of entries; they are cut into chunks
+    multiplied by separate groups and summed in order.  Same numbers as float64, with and without the split."""
+    eng, torch, o = env["eng"], env["torch"], env["o"]
+    lap = o.normalized_laplacian_sparse(powerlaw_graph(5000, 40000, 4))
+    g = eng.DeviceGraph.from_scipy(lap)
+    phi = eng.build_phi_blocks(g, eng.WalkConfig(40, 0.1, 3, seed=9))
+    phi.build_long_rows()
+    assert phi._long[1] is not None and phi._long[1]["n_long"] > 0, "test graph should have hub columns"
+    n_long, n_chunks = phi._long[1]["n_long"], phi._long[1]["n_chunks"]
+    assert n_chunks > n_long
+    rng = np.random.default_rng(2)
+    f = rng.standard_normal(3).astype(np.float32)
+    mats32 = phi.to_scipy_steps()
+    for t in (16, 3):
+        v = rng.standard_normal((phi.n_rows, t)).astype(np.float32)
+        want = o.phi_matvec_f64(mats32, f, v)
+        got = phi.matvec(torch.tensor(f), torch.tensor(v).cuda()).cpu().numpy()
+        assert _close(got, want)
+        got_m = phi.plan(torch.tensor(f), t)(torch.tensor(v).cuda()).cpu().numpy()       # merged Phi_f, own chunks
+        assert _close(got_m, want, rtol=5e-5)
+    saved, phi._long, phi._long_c = phi._long, [None, None], {}
+    unsplit = phi.matvec(torch.tensor(f), torch.tensor(v).cuda()).cpu().numpy()
+    phi._long, phi._long_c = saved, {}
+    assert _close(unsplit, want) and _close(unsplit, got, rtol=1e-5)
+
+
 def test_matvec_plan_equals_matvec(env, case):
     """The CG fast paths (one C call per product; per-length blocks or Phi_f merged on the union
     pattern) give the same numbers as the checked path."""
