@@ -39,9 +39,8 @@ class SparseGraphGP(ExactGP):
         noise_variance = float(self.likelihood.noise.item())
         with torch.no_grad():
             y = self.y_train.to(dev).to(torch.float32).reshape(-1, 1)
-            alpha, info = linear_cg(lambda v: K_train_train._matmul(v) + noise_variance * v, y,
-                                    tolerance=cg_tolerance, max_iter=max_cg_iterations, eps=1e-30,
-                                    return_info=True)
+            alpha, info = K_train_train.solve(y, noise_variance, tolerance=cg_tolerance,
+                                              max_iter=max_cg_iterations, eps=1e-30, return_info=True)
             out = K_test_train._matmul(alpha)[:, 0]
         return (out, info) if return_info else out
 
@@ -69,11 +68,8 @@ class SparseGraphGP(ExactGP):
             f_train_prior = eps1_batch @ phi_train.T          # (n_samples, n_train)
             b_batch = self.y_train.to(dev).unsqueeze(0) - (f_train_prior + eps2_batch)
 
-            def a_matmul(v):                                   # (K + sigma^2 I) v
-                return K_train_train._matmul(v) + noise_variance * v
-
             tol = settings.cg_tolerance.value() if cg_tolerance is None else cg_tolerance
-            v_batch, info = linear_cg(a_matmul, b_batch.T.contiguous(), tolerance=tol, max_iter=max_cg_iterations,
-                                      return_info=True)
+            v_batch, info = K_train_train.solve(b_batch.T.contiguous(), noise_variance, tolerance=tol,
+                                                max_iter=max_cg_iterations, return_info=True)
             out = f_test_prior + K_test_train._matmul(v_batch).T
         return (out, info) if return_info else out

@@ -49,3 +49,60 @@ def linear_cg(matmul_closure: Callable[[torch.Tensor], torch.Tensor], rhs: torch
     out = x * norm
     out = out[:, 0] if squeeze else out
     return (out, {"iterations": iters}) if return_info else out
+
+
+def linear_cg_fused(plan, rhs: torch.Tensor, sigma2: float = 0.0, tolerance: float = 1e-2, max_iter: int = 1000,
+                    eps: float = 1e-10, check_every: int = 4, return_info: bool = False):
+    """Solve ``(K + sigma2 I) X = rhs`` with ``K`` = a square :class:`~grf_b200.engine.MatvecPlan`.
+
+    Same iteration and stopping rule as :func:`linear_cg`; every iteration is the two spmm
+    launches of the plan plus three fused CUDA launches (``csrc/grf_cg.cu``) instead of a dozen
+    elementwise / reduction launches, and the dot products are reduced in a fixed order."""
+    import ctypes
+
+    from . import _lib
+    from ._lib import check
+
+    if plan.n1 != plan.n2:
+        raise ValueError("linear_cg_fused needs a square operator (x1 and x2 of equal length)")
+    if plan.group is not None:
+        raise ValueError("linear_cg_fused is the single-GPU path; use linear_cg with a sharded matvec")
+    L = _lib.lib()
+    dev = plan._dev
+    squeeze = rhs.dim() == 1
+    b = (rhs[:, None] if squeeze else rhs).to(device=dev, dtype=torch.float32)
+    n, t = b.shape
+    if t != plan.t or n != plan.n2:
+        raise ValueError("rhs shape does not match the plan")
+    norm = b.norm(dim=0, keepdim=True)
+    norm = torch.where(norm < eps, torch.ones_like(norm), norm)
+    b = (b / norm).contiguous()
+    x = torch.zeros_like(b)
+    r = b.clone()
+    d = b.clone()
+    kd = torch.empty_like(b)
+    rs = (r * r).sum(dim=0).contiguous()
+    rs_next = torch.empty_like(rs)
+    n_part = L.grf_cg_num_partials(n, t)
+    pa = torch.empty((n_part, t), dtype=torch.float32, device=dev)
+    pb = torch.empty((n_part, t), dtype=torch.float32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def P(tensor):
+        return ctypes.c_void_p(tensor.data_ptr())
+
+    min_iter = min(10, max_iter - 1)
+    iters = 0
+    for k in range(max_iter):
+        plan(d, kd)
+        check(L.grf_cg_dot(P(kd), t, P(d), t, float(sigma2), n, t, P(pa), stream))
+        check(L.grf_cg_update(P(x), t, P(r), t, P(d), t, P(kd), t, P(rs), P(pa), n, t, float(eps), P(pb), stream))
+        check(L.grf_cg_direction(P(d), t, P(r), t, P(rs), P(pb), n, t, float(eps), P(rs_next), stream))
+        rs, rs_next = rs_next, rs
+        iters = k + 1
+        if iters >= min_iter and (iters % check_every == 0 or iters == max_iter):
+            if float(rs.sqrt().mean()) < tolerance:
+                break
+    out = x * norm
+    out = out[:, 0] if squeeze else out
+    return (out, {"iterations": iters}) if return_info else out

@@ -155,6 +155,26 @@ class GRFKernelOperator(LinearOperator):
     def _transpose_nonbatch(self):
         return GRFKernelOperator(self.blocks, self.modulator, self.x2, self.x1, self.group)
 
+    def plan(self, t: int, merged: bool = True):
+        """A fixed-shape fast path for CG: ``plan(v, out)`` = K v with the current modulator value."""
+        return self.blocks.plan(self.modulator.detach(), t, x1=self.x1, x2=self.x2, group=self.group, merged=merged)
+
+    def solve(self, rhs, sigma2: float = 0.0, tolerance: float = 1e-2, max_iter: int = 1000, eps: float = 1e-10,
+              return_info: bool = False):
+        """(K + sigma2 I)^-1 rhs by conjugate gradients (no gradient tracking)."""
+        from .cg import linear_cg, linear_cg_fused
+
+        with torch.no_grad():
+            rhs2 = rhs[:, None] if rhs.dim() == 1 else rhs
+            if self.group is None:
+                out, info = linear_cg_fused(self.plan(rhs2.shape[1]), rhs2, sigma2, tolerance, max_iter, eps,
+                                            return_info=True)
+            else:
+                out, info = linear_cg(lambda v: self._matmul(v) + sigma2 * v, rhs2, tolerance, max_iter, eps,
+                                      return_info=True)
+            out = out[:, 0] if rhs.dim() == 1 else out
+        return (out, info) if return_info else out
+
     def _bilinear_derivative(self, left_vecs, right_vecs):
         """Upstream protocol: gradients of sum(left * (K right)) w.r.t. the representation (= the modulator)."""
         if left_vecs.dim() == 1:

@@ -225,6 +225,22 @@ int grf_union_materialize(const int32_t *blk_ptr, const int32_t *uptr, const int
 int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, const float *left, int64_t ldl, const float *p,
                   int64_t ldp, int32_t t, float *grad, void *stream);
 
+/* Fused vector kernels of batched CG on (K + sigma2 I) X = B (csrc/grf_cg.cu); replace the
+ * elementwise / reduction launches of upstream linear_cg as called at
+ * models/sparse_grf_model.py:43.  Per iteration, after Kd = grf_phi_matvec(d):
+ *   grf_cg_dot        ad = Kd + sigma2 * d (in place); partial[b][c] = block b's share of <d, ad>
+ *   grf_cg_update     alpha = rs / <d, ad>; x += alpha d; r -= alpha ad; rr_partial = shares of <r, r>
+ *   grf_cg_direction  rs_out = <r, r>; d = r + (rs_out / rs) d
+ * partial buffers: grf_cg_num_partials(n, t) rows of t floats.  All matrices n x t row-major. */
+int32_t grf_cg_num_partials(int64_t n, int32_t t);
+int grf_cg_dot(float *ad, int64_t ldad, const float *d, int64_t ldd, float sigma2, int64_t n, int32_t t,
+               float *partial, void *stream);
+int grf_cg_update(float *x, int64_t ldx, float *r, int64_t ldr, const float *d, int64_t ldd, const float *ad,
+                  int64_t ldad, const float *rs, const float *dad_partial, int64_t n, int32_t t, float eps,
+                  float *rr_partial, void *stream);
+int grf_cg_direction(float *d, int64_t ldd, const float *r, int64_t ldr, const float *rs, const float *rr_partial,
+                     int64_t n, int32_t t, float eps, float *rs_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

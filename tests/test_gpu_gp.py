@@ -164,6 +164,35 @@ def test_cg_posterior_mean_within_1e4_of_direct_solve(setup):
     assert np.mean(np.abs(z) < 4) > 0.97
 
 
+def test_fused_cg_matches_unfused_cg_and_direct_solve(setup):
+    """csrc/grf_cg.cu: same iterates as the torch-op CG, same answer as a float64 direct solve."""
+    torch = setup["torch"]
+    from grf_b200.cg import linear_cg, linear_cg_fused
+
+    blocks = setup["ops"].phi_blocks
+    rng = np.random.default_rng(8)
+    f = torch.tensor(rng.standard_normal(4).astype(np.float32)).cuda()
+    x = torch.tensor(rng.permutation(400)[:230]).cuda()
+    sigma2 = 0.3
+    phi = _phi64(setup["pp"].step_matrices_scipy, f.cpu().numpy())
+    idx = x.cpu().numpy()
+    a = phi[idx] @ phi[idx].T + sigma2 * np.eye(230)
+    for t in (1, 5, 16, 40):
+        b = rng.standard_normal((230, t)).astype(np.float32)
+        plan = blocks.plan(f, t, x1=x, x2=x)
+        got, info = linear_cg_fused(plan, torch.tensor(b).cuda(), sigma2, tolerance=1e-6, eps=1e-30, check_every=1,
+                                    return_info=True)
+        ref, info2 = linear_cg(lambda v: plan(v) + sigma2 * v, torch.tensor(b).cuda(), tolerance=1e-6, eps=1e-30,
+                               check_every=1, return_info=True)
+        want = np.linalg.solve(a, b.astype(np.float64))
+        scale = np.abs(want).max()
+        assert np.abs(got.cpu().numpy() - want).max() <= 2e-4 * scale, (t, info)
+        assert np.abs(got.cpu().numpy() - ref.cpu().numpy()).max() <= 2e-4 * scale
+        assert abs(info["iterations"] - info2["iterations"]) <= 3
+    with pytest.raises(ValueError, match="square"):
+        linear_cg_fused(blocks.plan(f, 4, x1=x, x2=x[:100]), torch.zeros(100, 4).cuda())
+
+
 def test_device_cg_matches_oracle_cg_semantics(setup):
     torch = setup["torch"]
     from grf_b200.cg import linear_cg
