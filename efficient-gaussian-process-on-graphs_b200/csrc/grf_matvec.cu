@@ -31,6 +31,17 @@ struct Vec<4> {
     __device__ __forceinline__ void load(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
     __device__ __forceinline__ void load_shared(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
     __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+    // first `ncols` (1..4) columns; vector store only when all four are valid and p is 16-byte aligned
+    __device__ __forceinline__ void store_cols(float *p, int ncols, bool vec_ok) const {
+        if (ncols >= 4 && vec_ok) {
+            store(p);
+        } else {
+            p[0] = v.x;
+            if (ncols > 1) p[1] = v.y;
+            if (ncols > 2) p[2] = v.z;
+            if (ncols > 3) p[3] = v.w;
+        }
+    }
     __device__ __forceinline__ void fma(float a, const Vec &x) {
         v.x = fmaf(a, x.v.x, v.x);
         v.y = fmaf(a, x.v.y, v.y);
@@ -48,6 +59,7 @@ struct Vec<1> {
     __device__ __forceinline__ void load(const float *p) { v = __ldg(p); }
     __device__ __forceinline__ void load_shared(const float *p) { v = *p; }
     __device__ __forceinline__ void store(float *p) const { *p = v; }
+    __device__ __forceinline__ void store_cols(float *p, int, bool) const { *p = v; }
     __device__ __forceinline__ void fma(float a, const Vec &x) { v = fmaf(a, x.v, v); }
     __device__ __forceinline__ float dot(const Vec &x) const { return v * x.v; }
 };
@@ -171,8 +183,10 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
                                                           int64_t row_lo, int64_t n_rows,
                                                           const float *__restrict__ X, int64_t ldx,
                                                           float *__restrict__ Y, int64_t ldy, int32_t t,
-                                                          int32_t long_thresh,
+                                                          int32_t t_store, int32_t vec_store, int32_t long_thresh,
                                                           const int2 *__restrict__ chunk_bounds) {
+    // t = columns computed (a multiple of VEC; the operands are padded to it), t_store <= t = columns
+    // that exist in Y; vec_store: rows of Y are 16-byte aligned (16-byte stores allowed).
     // long_thresh > 0: rows with more entries are left to the chunk launch (hub columns of a
     // power-law Phi^T hold 10^5..10^6 entries; one 4-lane group would serialise them);
     // chunk_bounds != NULL: this IS the chunk launch -- task k is the entry range chunk_bounds[k]
@@ -231,7 +245,7 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
             const bool last_tile = tile + 1 == n_tiles;
             const Vec<VEC> acc = spmm_row<TPR, VEC, false>(ent2, b, e, nxt, last_tile ? nb : b, last_tile ? ne : e,
                                                            fs, X, ldx, 0, c0 < t ? c0 : 0, live, sub);
-            if (live) acc.store(Y + k * ldy + c0);
+            if (live && c0 < t_store) acc.store_cols(Y + k * ldy + c0, t_store - c0, vec_store != 0);
         }
         b = nb;
         e = ne;
@@ -371,6 +385,23 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
         const int64_t row = (int64_t)__ldg(x2 + k) - row_lo;
         if (row < 0 || row >= n_rows) continue;
         atomicAdd(vfull + row * ldu + c, __ldg(v + k * ldv + c));
+    }
+}
+
+// same without atomics, for index sets without repeated ids (rows outside x2 keep their zeros)
+__global__ void __launch_bounds__(256) scatter_rows_unique_kernel(const int32_t *__restrict__ x2, int64_t n2,
+                                                                  int64_t row_lo, int64_t n_rows,
+                                                                  const float *__restrict__ v, int64_t ldv,
+                                                                  float *__restrict__ vfull, int64_t ldu,
+                                                                  int32_t t) {
+    const int64_t total = n2 * t;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = g / t;
+        const int c = (int)(g - k * t);
+        const int64_t row = (int64_t)__ldg(x2 + k) - row_lo;
+        if (row < 0 || row >= n_rows) continue;
+        vfull[row * ldu + c] = __ldg(v + k * ldv + c);
     }
 }
 
@@ -548,8 +579,12 @@ using namespace grf;
 // reduction for rows longer than the split threshold).
 static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float *f, int32_t L,
                             const int32_t *row_ids, int64_t n_tasks, int64_t row_lo, int64_t n_rows,
-                            const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t,
+                            const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t_valid,
                             bool vec_ok, cudaStream_t st) {
+    // vec_ok: X rows are 16-byte aligned and padded to a multiple of 4 columns -> compute the padded
+    // column count with float4 gathers; only the t_valid real columns are stored to Y
+    const int32_t t = vec_ok ? (t_valid + 3) & ~3 : t_valid;
+    const int32_t vec_store = (ldy % 4 == 0) && aligned16(Y);
     const Shape sh = pick_shape(t, vec_ok);
     const bool split = lr && lr->n_long > 0 && !row_ids;
     if (split) {
@@ -559,20 +594,21 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
     const int grid = spmm_grid(n_tasks, sh.tpr);
     GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
                        <<<grid, 256, 0, st>>>(ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy, t,
-                                              split ? lr->threshold : 0, nullptr));
+                                              ldy >= t ? t : t_valid, vec_store, split ? lr->threshold : 0, nullptr));
     GRF_CUDA_OK(cudaGetLastError());
     if (split) {
-        const bool pvec = vec_ok && (lr->ld % 4 == 0) && aligned16(lr->partial);
-        const Shape shc = pick_shape(t, pvec);
-        const int gridc = spmm_grid(lr->n_chunks, shc.tpr);
-        GRF_DISPATCH_SHAPE(spmm_blocks_kernel, shc,
+        GRF_REQUIRE(lr->ld >= t, "grf_phi_matvec: long-row partial buffer narrower than the padded column count");
+        const int32_t pvec = (lr->ld % 4 == 0) && aligned16(lr->partial);
+        const int gridc = spmm_grid(lr->n_chunks, sh.tpr);
+        GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
                            <<<gridc, 256, 0, st>>>(ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
-                                                   lr->partial, lr->ld, t, 0, (const int2 *)lr->chunk_bounds));
+                                                   lr->partial, lr->ld, t, t, pvec, 0,
+                                                   (const int2 *)lr->chunk_bounds));
         GRF_CUDA_OK(cudaGetLastError());
         int64_t g = ((int64_t)lr->n_long * t + 255) / 256;
         if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
-        long_reduce_kernel<<<(int)g, 256, 0, st>>>(lr->rows, lr->chunk_ptr, lr->partial, lr->ld, Y, ldy, t,
-                                                   lr->n_long);
+        long_reduce_kernel<<<(int)g, 256, 0, st>>>(lr->rows, lr->chunk_ptr, lr->partial, lr->ld, Y, ldy,
+                                                   ldy >= t ? t : t_valid, lr->n_long);
         GRF_CUDA_OK(cudaGetLastError());
     }
     return GRF_OK;
@@ -583,7 +619,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                               float *vfull, int32_t t, int32_t which, void *stream) {
     GRF_REQUIRE(phi && f, "grf_phi_matvec: null phi/f");
     GRF_REQUIRE(t >= 1, "grf_phi_matvec: t must be >= 1");
-    GRF_REQUIRE((which & 3) >= 1 && which <= 7, "grf_phi_matvec: which must be 1, 2 or 3 (+4: no tiling)");
+    GRF_REQUIRE((which & 3) >= 1 && which <= 15, "grf_phi_matvec: which must be 1, 2 or 3 (+4, +8 flags)");
     GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_matvec: n_steps out of range");
     GRF_REQUIRE(phi->n_cols <= (1ll << kStepShift) && phi->n_rows <= (1ll << kStepShift),
                 "grf_phi_matvec: more than 2^27 rows or columns per GPU");
@@ -592,7 +628,8 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
     GRF_REQUIRE(x2 || n2 == phi->n_rows, "grf_phi_matvec: n2 must equal n_rows when x2 is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t L = phi->n_steps;
-    const int tile_mode = which >> 2;  // bit 2 of `which` set: never use the shared-memory-tiled kernel
+    const int tile_mode = (which >> 2) & 1;  // +4: never use the shared-memory-tiled kernel
+    const bool x2_unique = (which >> 3) & 1;  // +8: x2 has no repeated ids and vfull was zeroed once
     which &= 3;
 
     if (which & 1) {
@@ -602,13 +639,27 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         int64_t lds = ldv;
         if (x2) {
             GRF_REQUIRE(vfull, "grf_phi_matvec: vfull workspace needed when x2 is given");
-            GRF_CUDA_OK(cudaMemsetAsync(vfull, 0, (size_t)phi->n_rows * ldu * sizeof(float), st));
+            // x2_unique: the caller guarantees no repeated ids and a vfull that was zeroed once; rows
+            // outside x2 then stay zero across calls and the scatter needs neither memset nor atomics
+            if (!x2_unique) GRF_CUDA_OK(cudaMemsetAsync(vfull, 0, (size_t)phi->n_rows * ldu * sizeof(float), st));
             if (n2 > 0 && phi->n_rows > 0) {
                 int64_t g = (n2 * t + 255) / 256;
                 if (g > (int64_t)kSmCount * 16) g = (int64_t)kSmCount * 16;
-                scatter_rows_kernel<<<(int)g, 256, 0, st>>>(x2, n2, phi->row_lo, phi->n_rows, v, ldv, vfull, ldu, t);
+                if (x2_unique)
+                    scatter_rows_unique_kernel<<<(int)g, 256, 0, st>>>(x2, n2, phi->row_lo, phi->n_rows, v, ldv,
+                                                                      vfull, ldu, t);
+                else
+                    scatter_rows_kernel<<<(int)g, 256, 0, st>>>(x2, n2, phi->row_lo, phi->n_rows, v, ldv, vfull,
+                                                               ldu, t);
                 GRF_CUDA_OK(cudaGetLastError());
             }
+            src = vfull;
+            lds = ldu;
+        } else if (vfull && phi->n_rows > 0 && (ldv % 4 != 0 || !aligned16(v)) && ldu % 4 == 0) {
+            // V is not laid out for 16-byte gathers (e.g. t = 17): stage it in the padded buffer
+            GRF_CUDA_OK(cudaMemcpy2DAsync(vfull, (size_t)ldu * sizeof(float), v, (size_t)ldv * sizeof(float),
+                                          (size_t)t * sizeof(float), (size_t)phi->n_rows,
+                                          cudaMemcpyDeviceToDevice, st));
             src = vfull;
             lds = ldu;
         }
@@ -617,9 +668,11 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             GRF_CUDA_OK(cudaMemset2DAsync(u, (size_t)ldu * sizeof(float), 0, (size_t)t * sizeof(float),
                                           (size_t)phi->n_cols, st));
         } else if (phi->n_cols > 0) {
-            const bool vec_ok = (t % 4 == 0) && (lds % 4 == 0) && (ldu % 4 == 0) && aligned16(src) && aligned16(u);
+            const int32_t t4 = (t + 3) & ~3;
+            const bool vec_ok = (lds % 4 == 0) && (ldu % 4 == 0) && lds >= t4 && ldu >= t4 && aligned16(src) &&
+                                aligned16(u);
             int tiled = 0;
-            if (vec_ok && !(tile_mode & 1)) {
+            if (vec_ok && t % 4 == 0 && !(tile_mode & 1)) {
                 tiled = try_launch_tiled(phi->tblk_ptr, phi->tentries, f, L, phi->n_cols, phi->twin,
                                          phi->twin_max_width, src, lds, u, ldu, t, st);
                 if (tiled < 0) return tiled;
@@ -634,9 +687,10 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
     if ((which & 2) && n1 > 0) {
         GRF_REQUIRE(out && ldo >= t, "grf_phi_matvec: out missing or ldo < t");
         GRF_REQUIRE(phi->blk_ptr, "grf_phi_matvec: Phi blocks missing");
-        const bool vec_ok = (t % 4 == 0) && (ldo % 4 == 0) && (ldu % 4 == 0) && aligned16(out) && aligned16(u);
+        const int32_t t4 = (t + 3) & ~3;
+        const bool vec_ok = (ldu % 4 == 0) && ldu >= t4 && aligned16(u);   // gathers come from U
         int tiled = 0;
-        if (vec_ok && !x1 && !(tile_mode & 1)) {
+        if (vec_ok && t % 4 == 0 && (ldo % 4 == 0) && aligned16(out) && !x1 && !(tile_mode & 1)) {
             tiled = try_launch_tiled(phi->blk_ptr, phi->entries, f, L, phi->n_rows, phi->win, phi->win_max_width, u,
                                      ldu, out, ldo, t, st);
             if (tiled < 0) return tiled;

@@ -517,8 +517,9 @@ class PhiBlocks:
             out = torch.empty((self.n_cols, ldu), dtype=torch.float32, device=dev)
         u = out
         vfull = None
-        if rows is not None:
-            vfull = torch.empty((max(1, self.n_rows), u.stride(0)), dtype=torch.float32, device=dev)
+        if rows is not None or t % 4 != 0 or v.stride(0) % 4 != 0:
+            # scatter target for a row subset / staging buffer for a V that is not 16-byte friendly
+            vfull = torch.zeros((max(1, self.n_rows), u.stride(0)), dtype=torch.float32, device=dev)
         phi = self.c_struct((t + 3) // 4 * 4)
         check(_lib.lib().grf_phi_matvec(
             ctypes.byref(phi), _ptr(f), None, self.n_rows, _ptr(rows), n2, _ptr(v), v.stride(0), None, 0,
@@ -765,8 +766,11 @@ class MatvecPlan:
         self.n2 = phi.n_rows if self.x2 is None else self.x2.numel()
         self.ldu = (self.t + 3) // 4 * 4
         self.u = torch.empty((max(1, phi.n_cols), self.ldu), dtype=torch.float32, device=dev)
-        self.vfull = (torch.empty((max(1, phi.n_rows), self.ldu), dtype=torch.float32, device=dev)
-                      if self.x2 is not None else None)
+        self.vfull = (torch.zeros((max(1, phi.n_rows), self.ldu), dtype=torch.float32, device=dev)
+                      if (self.x2 is not None or self.t % 4 != 0) else None)
+        # no repeated ids in x2 (the usual case: a training set) -> scatter without memset / atomics
+        self._flags = 8 if (self.x2 is not None and self.x2.numel() > 0
+                            and int(torch.unique(self.x2).numel()) == self.x2.numel()) else 0
         self._c = self.phi.c_struct(self.ldu)
         self._fn = _lib.lib().grf_phi_matvec
         self._dev = dev
@@ -781,7 +785,7 @@ class MatvecPlan:
         rc = self._fn(ctypes.byref(self._c), _ptr(self.f), _ptr(self.x1), self.n1, _ptr(self.x2), self.n2,
                       None if v is None else ctypes.c_void_p(v.data_ptr()), 0 if v is None else v.stride(0),
                       None if out is None else ctypes.c_void_p(out.data_ptr()), 0 if out is None else out.stride(0),
-                      _ptr(self.u), self.ldu, _ptr(self.vfull), self.t, which, _stream(self._dev))
+                      _ptr(self.u), self.ldu, _ptr(self.vfull), self.t, which | self._flags, _stream(self._dev))
         if rc:
             check(rc)
 

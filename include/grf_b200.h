@@ -191,7 +191,10 @@ int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t 
  * (= Phi[x2]^T V, this GPU's partial sum: the multi-GPU caller all-reduces it
  * between the two halves); vfull workspace [n_rows][ldu], used when x2 != NULL.
  * which: 1 = first half only (U), 2 = second half only (out from U), 3 = both;
- * add 4 to force the global-gather kernel even when column windows are present. */
+ * add 4 to force the global-gather kernel even when column windows are present; add 8 when x2
+ * holds no repeated ids and vfull was zero-filled once by the caller (the scatter then needs no
+ * memset and no atomics).  When V is not 16-byte friendly (e.g. t = 17) and vfull is given, V is
+ * staged there and the product runs on the column count padded to a multiple of 4. */
 int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t n1, const int32_t *x2,
                    int64_t n2, const float *v, int64_t ldv, float *out, int64_t ldo, float *u, int64_t ldu,
                    float *vfull, int32_t t, int32_t which, void *stream);
