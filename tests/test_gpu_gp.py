@@ -164,6 +164,60 @@ def test_cg_posterior_mean_within_1e4_of_direct_solve(setup):
     assert np.mean(np.abs(z) < 4) > 0.97
 
 
+def test_mll_gradient_matches_dense_float64(setup):
+    """-mll/n gradient w.r.t. the modulator and the noise: CG + per-length reductions vs a dense float64
+    evaluation.  Probes = sqrt(n) e_j (p = n) make the trace estimator exact, so the comparison is tight."""
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.gptorch_kernels_sparse import SparseGRFKernel
+    from grf_b200.gp_compat import GaussianLikelihood
+    from grf_b200.mll import neg_mll_backward
+
+    torch.manual_seed(1)
+    rng = np.random.default_rng(11)
+    kern = SparseGRFKernel(4, setup["ops"]).cuda()
+    with torch.no_grad():
+        kern.raw_modulator_vector.copy_(torch.tensor([1.0, -0.4, 0.2, -0.05]))
+    lik = GaussianLikelihood()
+    lik.noise = 0.5
+    idx = np.sort(rng.permutation(400)[:120])
+    y = np.sin(idx / 15.0) + 0.1 * rng.standard_normal(120)
+    n = 120
+    probes = torch.eye(n) * np.sqrt(n)
+    out = neg_mll_backward(kern, lik, torch.tensor(idx), torch.tensor(y), probes=probes, cg_tolerance=1e-7,
+                           cg_eps=1e-30)
+    # dense float64 reference
+    f = kern.modulator_vector.detach().cpu().numpy().astype(np.float64)
+    mats = [m.astype(np.float32).astype(np.float64)[idx].toarray() for m in setup["pp"].step_matrices_scipy]
+    phi = sum(fl * m for fl, m in zip(f, mats))
+    s2 = float(lik.noise)
+    Kh = phi @ phi.T + s2 * np.eye(n)
+    Kinv = np.linalg.inv(Kh)
+    a = Kinv @ y.astype(np.float32).astype(np.float64)
+    want_f = []
+    for l in range(4):
+        dK = mats[l] @ phi.T + phi @ mats[l].T
+        want_f.append(-(0.5 * a @ dK @ a - 0.5 * np.trace(Kinv @ dK)) / n)
+    want_s2 = -(0.5 * a @ a - 0.5 * np.trace(Kinv)) / n
+    got_f = kern.raw_modulator_vector.grad.cpu().numpy()
+    assert np.allclose(got_f, want_f, rtol=2e-3, atol=2e-3 * np.abs(want_f).max()), (got_f, want_f)
+    # noise gradient reaches raw_noise through the softplus constraint
+    raw = float(lik.raw_noise)
+    dnoise_draw = 1.0 / (1.0 + np.exp(-raw))
+    assert abs(float(lik.raw_noise.grad) - want_s2 * dnoise_draw) <= 2e-3 * abs(want_s2 * dnoise_draw) + 1e-6
+    assert abs(out["datafit"] - 0.5 * y.astype(np.float32) @ a) <= 1e-3 * abs(0.5 * y @ a)
+    # with random probes the estimate is unbiased: average of a few draws lands near the exact value
+    kern.raw_modulator_vector.grad = None
+    lik.raw_noise.grad = None
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acc = np.zeros(4)
+    for _ in range(8):
+        kern.raw_modulator_vector.grad = None
+        neg_mll_backward(kern, lik, torch.tensor(idx), torch.tensor(y), num_probes=64, cg_tolerance=1e-6,
+                         generator=gen, cg_eps=1e-30)
+        acc += kern.raw_modulator_vector.grad.cpu().numpy() / 8
+    assert np.allclose(acc, want_f, rtol=0.15, atol=0.1 * np.abs(want_f).max()), (acc, want_f)
+
+
 def test_fused_cg_matches_unfused_cg_and_direct_solve(setup):
     """csrc/grf_cg.cu: same iterates as the torch-op CG, same answer as a float64 direct solve."""
     torch = setup["torch"]
