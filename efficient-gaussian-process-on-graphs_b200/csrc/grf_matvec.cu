@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
                                                           const float *__restrict__ X, int64_t ldx,
                                                           float *__restrict__ Y, int64_t ldy, int32_t t,
                                                           int32_t t_store, int32_t vec_store, int32_t long_thresh,
-                                                          const int2 *__restrict__ chunk_bounds) {
+                                                          const int2 *__restrict__ chunk_bounds,
+                                                          int32_t out_by_row) {
+    // out_by_row: row_ids lists the non-empty rows and task k writes Y[row_ids[k]] (Phi^T of a row
+    // shard touches only a fraction of the N columns); otherwise task k writes Y[k].
     // t = columns computed (a multiple of VEC; the operands are padded to it), t_store <= t = columns
     // that exist in Y; vec_store: rows of Y are 16-byte aligned (16-byte stores allowed).
     // long_thresh > 0: rows with more entries are left to the chunk launch (hub columns of a
@@ -204,8 +207,9 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
     // warp-uniform loop: the warp takes 32/TPR consecutive tasks per iteration; the row bounds of
     // the next iteration are fetched one iteration ahead, its first entries by spmm_row
     const int64_t kstride = warp_stride * kGroupsPerWarp;
-    auto bounds = [&](int64_t k, int32_t &b, int32_t &e, bool &mine) {
+    auto bounds = [&](int64_t k, int32_t &b, int32_t &e, bool &mine, int64_t &orow) {
         b = e = 0;
+        orow = k;
         if (chunk_bounds) {
             mine = k < n_tasks;
             if (mine) {
@@ -218,6 +222,7 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
         int64_t row = -1;
         if (k < n_tasks) row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
         mine = row >= 0 && row < n_rows;  // ids outside this shard are skipped
+        if (out_by_row) orow = row;
         if (mine) {
             b = __ldg(ptr + row * L);
             e = __ldg(ptr + (row + 1) * L);
@@ -231,12 +236,13 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
     if (kb >= n_tasks) return;
     int32_t b, e, nb, ne;
     bool mine, nmine;
-    bounds(kb + g_in_warp, b, e, mine);
+    int64_t orow, norow;
+    bounds(kb + g_in_warp, b, e, mine, orow);
     int2 nxt[epl(TPR)];
     load_first_round<TPR>(ent2, b, e, sub, nxt);
     for (; kb < n_tasks; kb += kstride) {
         const int64_t k = kb + g_in_warp;
-        bounds(k + kstride, nb, ne, nmine);
+        bounds(k + kstride, nb, ne, nmine, norow);
         for (int tile = 0; tile < n_tiles; ++tile) {
             // lanes whose columns fall outside t (t not a multiple of TPR*VEC) still help with the
             // entry loads and shuffles; they just do not gather or store
@@ -245,11 +251,12 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
             const bool last_tile = tile + 1 == n_tiles;
             const Vec<VEC> acc = spmm_row<TPR, VEC, false>(ent2, b, e, nxt, last_tile ? nb : b, last_tile ? ne : e,
                                                            fs, X, ldx, 0, c0 < t ? c0 : 0, live, sub);
-            if (live && c0 < t_store) acc.store_cols(Y + k * ldy + c0, t_store - c0, vec_store != 0);
+            if (live && c0 < t_store) acc.store_cols(Y + orow * ldy + c0, t_store - c0, vec_store != 0);
         }
         b = nb;
         e = ne;
         mine = nmine;
+        orow = norow;
     }
 }
 
@@ -580,13 +587,13 @@ using namespace grf;
 static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float *f, int32_t L,
                             const int32_t *row_ids, int64_t n_tasks, int64_t row_lo, int64_t n_rows,
                             const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t_valid,
-                            bool vec_ok, cudaStream_t st) {
+                            bool vec_ok, bool out_by_row, cudaStream_t st) {
     // vec_ok: X rows are 16-byte aligned and padded to a multiple of 4 columns -> compute the padded
     // column count with float4 gathers; only the t_valid real columns are stored to Y
     const int32_t t = vec_ok ? (t_valid + 3) & ~3 : t_valid;
     const int32_t vec_store = (ldy % 4 == 0) && aligned16(Y);
     const Shape sh = pick_shape(t, vec_ok);
-    const bool split = lr && lr->n_long > 0 && !row_ids;
+    const bool split = lr && lr->n_long > 0 && (!row_ids || out_by_row);
     if (split) {
         GRF_REQUIRE(lr->rows && lr->chunk_ptr && lr->chunk_bounds && lr->partial && lr->ld >= t,
                     "grf_phi_matvec: incomplete long-row metadata");
@@ -594,7 +601,8 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
     const int grid = spmm_grid(n_tasks, sh.tpr);
     GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
                        <<<grid, 256, 0, st>>>(ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy, t,
-                                              ldy >= t ? t : t_valid, vec_store, split ? lr->threshold : 0, nullptr));
+                                              ldy >= t ? t : t_valid, vec_store, split ? lr->threshold : 0, nullptr,
+                                              out_by_row ? 1 : 0));
     GRF_CUDA_OK(cudaGetLastError());
     if (split) {
         GRF_REQUIRE(lr->ld >= t, "grf_phi_matvec: long-row partial buffer narrower than the padded column count");
@@ -603,7 +611,7 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
         GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
                            <<<gridc, 256, 0, st>>>(ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
                                                    lr->partial, lr->ld, t, t, pvec, 0,
-                                                   (const int2 *)lr->chunk_bounds));
+                                                   (const int2 *)lr->chunk_bounds, 0));
         GRF_CUDA_OK(cudaGetLastError());
         int64_t g = ((int64_t)lr->n_long * t + 255) / 256;
         if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
@@ -678,8 +686,18 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                 if (tiled < 0) return tiled;
             }
             if (!tiled) {
-                const int rc = launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0,
-                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, st);
+                int rc;
+                if (phi->tcols && phi->n_tcols < phi->n_cols) {
+                    // only the columns this shard touches; the others are zero
+                    GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
+                    rc = phi->n_tcols == 0
+                             ? GRF_OK
+                             : launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, phi->tcols, phi->n_tcols, 0,
+                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, st);
+                } else {
+                    rc = launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0, phi->n_cols,
+                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, st);
+                }
                 if (rc != GRF_OK) return rc;
             }
         }
@@ -697,7 +715,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         }
         if (!tiled) {
             const int rc = launch_spmm_pass(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
-                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, st);
+                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, st);
             if (rc != GRF_OK) return rc;
         }
     }

@@ -50,7 +50,8 @@ class GrfPhi(Structure):
     _fields_ = [("n_rows", c_int64), ("n_cols", c_int64), ("row_lo", c_int64), ("n_steps", c_int32),
                 ("blk_ptr", c_void_p), ("entries", c_void_p), ("tblk_ptr", c_void_p), ("tentries", c_void_p),
                 ("win", c_void_p), ("twin", c_void_p), ("win_max_width", c_int32), ("twin_max_width", c_int32),
-                ("long_fwd", POINTER(GrfLongRows)), ("long_t", POINTER(GrfLongRows))]
+                ("long_fwd", POINTER(GrfLongRows)), ("long_t", POINTER(GrfLongRows)),
+                ("tcols", c_void_p), ("n_tcols", c_int64)]
 
 
 def nvcc_command(out_path: str = SO_PATH):

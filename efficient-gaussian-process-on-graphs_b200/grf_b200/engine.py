@@ -324,6 +324,7 @@ class PhiBlocks:
         self.use_tiles = False
         self.visits = visits
         self._union = None
+        self._tcols = None      # non-empty columns of this shard (int32) when that is a small fraction of N
         self._long = None       # [fwd, transposed] long-row metadata (dicts) or None per side
         self._long_c = {}       # ld -> (ctypes structs, partial buffers) kept alive for the calls
         self._ws = {}
@@ -445,6 +446,13 @@ class PhiBlocks:
             self.build_transpose()
             self._long = [self._long_rows_of(self.blk_ptr, self.n_rows),
                           self._long_rows_of(self.tblk_ptr, self.n_cols)]
+            # columns this (row) shard touches: worth a list when most of the N columns are empty
+            if self.n_cols > 0 and self.nnz > 0:
+                L = self.n_steps
+                lens = self.tblk_ptr[L:self.n_cols * L + 1:L] - self.tblk_ptr[0:self.n_cols * L:L]
+                cols = torch.nonzero(lens > 0).flatten()
+                if cols.numel() < 0.75 * self.n_cols:
+                    self._tcols = cols.to(torch.int32).contiguous()
         return self
 
     def _long_structs(self, ld: int):
@@ -475,7 +483,9 @@ class PhiBlocks:
                       self.win.data_ptr() if tiles else None, self.twin.data_ptr() if tiles else None,
                       self.win_max_width if tiles else 0, self.twin_max_width if tiles else 0,
                       ctypes.pointer(fwd) if fwd is not None else None,
-                      ctypes.pointer(tr) if tr is not None else None)
+                      ctypes.pointer(tr) if tr is not None else None,
+                      None if self._tcols is None else self._tcols.data_ptr(),
+                      0 if self._tcols is None else self._tcols.numel())
 
     @staticmethod
     def _ids(x, dev):

@@ -125,6 +125,10 @@ typedef struct {
     int32_t win_max_width, twin_max_width;
     const GrfLongRows *long_fwd; /* host pointers, NULL = no row of that side is split */
     const GrfLongRows *long_t;
+    /* optional: ids of the columns that have at least one entry in this shard (device, ascending);
+     * Phi^T V then visits only those and zero-fills the rest of U */
+    const int32_t *tcols;
+    int64_t n_tcols;
 } GrfPhi;
 
 int grf_abi_version(void);

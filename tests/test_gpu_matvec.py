@@ -337,6 +337,23 @@ def test_sharded_rows_sum_to_the_full_product(env, case):
     u = sum(s.apply_t(f, v[lo:hi]).clone() for s, lo, hi in zip(shards, bounds[:-1], bounds[1:]))
     got = torch.cat([s.apply(f, u) for s in shards])
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+    # a narrow shard of a banded Phi touches few columns: the non-empty-column list path
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+    lapg = get_normalized_laplacian(grid_graph(60, 50))
+    gg = eng.DeviceGraph.from_scipy(lapg)
+    cfg2 = eng.WalkConfig(20, 0.1, 3, seed=3)
+    full = eng.build_phi_blocks(gg, cfg2)
+    part = eng.build_phi_blocks(gg, cfg2, 1000, 1400)
+    part.build_long_rows()
+    assert part._tcols is not None and part._tcols.numel() < 0.5 * part.n_cols
+    vv = torch.tensor(rng.standard_normal((400, 8)).astype(np.float32)).cuda()
+    f3 = torch.tensor(rng.standard_normal(3).astype(np.float32))
+    vfull_rows = torch.zeros(3000, 8, device="cuda")
+    vfull_rows[1000:1400] = vv
+    u_part = part.apply_t(f3, vv)
+    others = [eng.build_phi_blocks(gg, cfg2, 0, 1000), eng.build_phi_blocks(gg, cfg2, 1400, 3000)]
+    u_ref = full.apply_t(f3, vfull_rows)
+    assert torch.allclose(u_part, u_ref, rtol=1e-4, atol=1e-5 * float(u_ref.abs().max()))
     # global ids routed to the owning shard only
     x = torch.tensor([3, 190, 450, 699, 200]).cuda()
     parts = torch.zeros(5, 16, device="cuda")

@@ -131,6 +131,94 @@ def test_native_bit_exact_powerlaw_hubs(env):
     _native_case(env, lap, 64, 0.1, 5, seed=99)
 
 
+def _rmat(scale, m, seed=0, a=0.57, b=0.19, c=0.19):
+    """R-MAT (0.57, 0.19, 0.19, 0.05), symmetrised, de-duplicated, no self-loops, unit weights."""
+    rng = np.random.default_rng(seed)
+    n = 1 << scale
+    src = np.zeros(m, dtype=np.int64)
+    dst = np.zeros(m, dtype=np.int64)
+    for bit in range(scale):
+        r = rng.random(m)
+        src |= (r >= a + b).astype(np.int64) << bit
+        dst |= (((r >= a) & (r < a + b)) | (r >= a + b + c)).astype(np.int64) << bit
+    keep = src != dst
+    lo, hi = np.minimum(src[keep], dst[keep]), np.maximum(src[keep], dst[keep])
+    key = np.unique(lo * n + hi)
+    lo, hi = key // n, key % n
+    return sp.csr_matrix((np.ones(2 * key.size), (np.r_[lo, hi], np.r_[hi, lo])), shape=(n, n))
+
+
+def test_config4_shape_rmat_bit_exact(env):
+    """BASELINE config 4 in miniature: R-MAT power-law graph (65 k nodes, ~1 M edges, hubs, isolated nodes),
+    W = 100, L = 5 -- every M_l bit-identical to the oracle, walk-step counts equal."""
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+
+    adj = _rmat(16, 1_100_000)
+    assert np.diff(adj.indptr).max() > 2000 and (np.diff(adj.indptr) == 0).sum() > 1000
+    _native_case(env, get_normalized_laplacian(adj), 100, 0.1, 5, seed=42)
+
+
+def test_config5_shape_weighted_periodic_grid_bit_exact(env):
+    """BASELINE config 5 (wind-shaped): lat-lon grid, 4-neighbour, periodic in longitude, edge weight =
+    great-circle distance (wind_experiment.py:75-125) -- non-unit weights, W = 200, L = 3."""
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+
+    nlat, nlon = 60, 120
+    lat = np.deg2rad(np.linspace(-59, 59, nlat))
+    lon = np.deg2rad(np.arange(nlon) * 360.0 / nlon)
+
+    def gc(la1, lo1, la2, lo2):
+        return 2 * np.arcsin(np.sqrt(np.sin((la2 - la1) / 2) ** 2
+                                     + np.cos(la1) * np.cos(la2) * np.sin((lo2 - lo1) / 2) ** 2))
+
+    rows, cols, vals = [], [], []
+    for i in range(nlat):
+        for j in range(nlon):
+            u = i * nlon + j
+            v = i * nlon + (j + 1) % nlon                       # periodic in longitude
+            w = gc(lat[i], lon[j], lat[i], lon[(j + 1) % nlon])
+            rows += [u, v]; cols += [v, u]; vals += [w, w]
+            if i + 1 < nlat:
+                v = (i + 1) * nlon + j
+                w = gc(lat[i], lon[j], lat[i + 1], lon[j])
+                rows += [u, v]; cols += [v, u]; vals += [w, w]
+    adj = sp.csr_matrix((vals, (rows, cols)), shape=(nlat * nlon, nlat * nlon))
+    _native_case(env, get_normalized_laplacian(adj), 200, 0.1, 3, seed=7)
+
+
+def test_config3_shape_ring_properties(env):
+    """BASELINE config 3: ring of 2^20 nodes, W = 100, L = 3 -- size-independent properties at full size:
+    M_0 = I, exact walk-step count vs the C oracle on a slice, <a, K b> = <K a, b>."""
+    eng, torch = env["eng"], env["torch"]
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+
+    n = 1 << 20
+    lap = get_normalized_laplacian(ring_graph(n))
+    g = eng.DeviceGraph.from_scipy(lap)
+    cfg = eng.WalkConfig(100, 0.1, 3, seed=42)
+    phi = eng.build_phi_blocks(g, cfg)
+    ptr = phi.blk_ptr.view(-1)[:-1].view(n, 3)
+    first = phi.entries[ptr[:, 0].long()]
+    assert bool((ptr[:, 1] - ptr[:, 0] == 1).all())
+    assert bool((first[:, 0] == torch.arange(n, device="cuda", dtype=torch.int32)).all())
+    assert bool((first[:, 1].view(torch.float32) == 1.0).all())
+    assert abs(int(phi.visits) - n * 100 * 2.71) / (n * 271) < 2e-3
+    # a slice of rows against the oracle, bit for bit (float32 rounding of the float64 sums)
+    lo, hi = 777_000, 777_512
+    want = env["c"].step_matrices(lap, 100, 0.1, 3, seed=42, start_lo=lo, start_hi=hi)
+    part = eng.build_step_matrices(g, cfg, lo, hi).to_scipy()
+    for s in range(3):
+        assert csr_bits_equal(part[s], want[s])
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    f = torch.randn(3, device="cuda", generator=gen)
+    a = torch.randn(n, 16, device="cuda", generator=gen)
+    b = torch.randn(n, 16, device="cuda", generator=gen)
+    plan = phi.plan(f, 16)
+    ka, kb = plan(a).clone(), plan(b).clone()
+    lhs, rhs = float((b * ka).sum()), float((a * kb).sum())
+    assert abs(lhs - rhs) <= 1e-3 * max(abs(lhs), abs(rhs), 1.0)
+
+
 @pytest.mark.parametrize("W,L", [(1, 1), (1, 4), (2, 2), (31, 3), (32, 3), (33, 3), (128, 2), (129, 3), (256, 3)])
 def test_native_bit_exact_walk_counts(env, W, L):
     lap = env["o"].normalized_laplacian_sparse(ring_graph(97))
