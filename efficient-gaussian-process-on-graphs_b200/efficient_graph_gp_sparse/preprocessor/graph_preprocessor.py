@@ -1,10 +1,14 @@
 """Drop-in for ``preprocessor/graph_preprocessor.py:10-165``.
 
 Same constructor, attributes (``step_matrices_scipy``, ``step_matrices_torch``),
-``preprocess_graph``, ``from_scipy_csr`` and pickle cache format.  The step
-matrices are computed on the GPU; ``step_matrices_torch`` is a list of
-``SparseLinearOperator`` like the reference's, and additionally carries the
-fused Phi blocks (``.phi_blocks``) so that the kernels never rebuild them.
+``preprocess_graph``, ``from_scipy_csr`` and pickle cache format.  Everything
+between the adjacency and the operators stays on the GPU: the normalized
+Laplacian (``grf_laplacian_*``, bit-identical to graph_utils.py:5-30), the walks,
+the step matrices and the torch CSR tensors wrapped by the
+``SparseLinearOperator``s (int64 indices, float32 values, as :117-139).
+``step_matrices_scipy`` is copied to the host only when it is read (or saved);
+``step_matrices_torch`` additionally carries the fused Phi blocks
+(``.phi_blocks``) so that the kernels never rebuild them.
 """
 
 import hashlib
@@ -15,9 +19,9 @@ from typing import List, Optional
 import scipy.sparse as sp
 import torch
 
-from grf_b200.engine import PhiBlocks
-from efficient_graph_gp_sparse.random_walk_samplers_sparse import SparseRandomWalk
-from efficient_graph_gp_sparse.utils_sparse import SparseLinearOperator, get_normalized_laplacian
+from grf_b200 import _lib
+from grf_b200.engine import DeviceGraph, PhiBlocks, WalkConfig, build_step_matrices
+from efficient_graph_gp_sparse.utils_sparse import SparseLinearOperator
 
 
 class StepOperatorList(list):
@@ -57,6 +61,8 @@ class GraphPreprocessor:
         self.cache_filename = cache_filename or self._generate_cache_filename()
         self.n_processes = n_processes
         self.device = device
+        self._scipy = None
+        self._steps_device = None
 
         if load_from_disk:
             if os.path.exists(self.cache_filename):
@@ -74,22 +80,54 @@ class GraphPreprocessor:
         params = f"{graph_size}_{self.walks_per_node}_{self.p_halt}_{self.max_walk_length}_{self.random_walk_seed}"
         return f"experiments_sparse/step_matrices/step_matrices_{adj_hash}_{params}.pkl"
 
+    def _target_device(self) -> torch.device:
+        if self.device is not None:
+            return torch.device(self.device)
+        return (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available()
+                else torch.device("cpu"))
+
     def _wrap(self, mats, blocks) -> StepOperatorList:
-        dev = torch.device(self.device) if self.device is not None else (
-            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        dev = self._target_device()
         ops = StepOperatorList(SparseLinearOperator(self.from_scipy_csr(m).to(dev)) for m in mats)
         ops.phi_blocks = blocks
         return ops
 
+    def _wrap_device(self, steps, blocks) -> StepOperatorList:
+        """torch sparse-CSR tensors straight from the device step matrices (no host round trip)."""
+        n, L = steps.n_rows, steps.n_steps
+        bounds = steps.offsets[0:n * L + 1:max(1, n)][:L + 1].cpu().tolist() if n else [0] * (L + 1)
+        ops = StepOperatorList()
+        for s in range(L):
+            b, e = bounds[s], bounds[s + 1]
+            crow = (steps.offsets[s * n:(s + 1) * n + 1] - b) if n else torch.zeros(1, dtype=torch.int64,
+                                                                                   device=steps.device)
+            t = torch.sparse_csr_tensor(crow, steps.col[b:e].long(), steps.val[b:e].float(),
+                                        (n, steps.n_cols), dtype=torch.float32)
+            ops.append(SparseLinearOperator(t))
+        ops.phi_blocks = blocks
+        return ops
+
+    @property
+    def step_matrices_scipy(self) -> List[sp.csr_matrix]:
+        if self._scipy is None and self._steps_device is not None:
+            self._scipy = self._steps_device.to_scipy()
+        return self._scipy
+
+    @step_matrices_scipy.setter
+    def step_matrices_scipy(self, mats) -> None:
+        self._scipy = mats
+
     def preprocess_graph(self, save_to_disk: bool = False, *, trace=None) -> List[SparseLinearOperator]:
-        laplacian = get_normalized_laplacian(self.adj_matrix)
-        random_walk = SparseRandomWalk(laplacian, seed=self.random_walk_seed, device=self.device)
-        steps = random_walk.get_step_matrices_device(self.walks_per_node, self.p_halt, self.max_walk_length,
-                                                     trace=trace)
-        self.step_matrices_scipy = steps.to_scipy()
+        graph = DeviceGraph.laplacian_of(self.adj_matrix, self.device)
+        cfg = WalkConfig(int(self.walks_per_node), float(self.p_halt), int(self.max_walk_length),
+                         seed=self.random_walk_seed or 42,
+                         draw_mode=_lib.DRAW_PHILOX if trace is None else _lib.DRAW_REPLAY, trace=trace)
+        self._steps_device = build_step_matrices(graph, cfg, scale_mode=_lib.SCALE_MUL_RECIP)
+        self._scipy = None
         if save_to_disk:
             self.save_step_matrices(self.step_matrices_scipy, self.cache_filename)
-        self.step_matrices_torch = self._wrap(self.step_matrices_scipy, PhiBlocks.from_step_matrices(steps))
+        self.step_matrices_torch = self._wrap_device(self._steps_device,
+                                                     PhiBlocks.from_step_matrices(self._steps_device))
         return self.step_matrices_torch
 
     @staticmethod

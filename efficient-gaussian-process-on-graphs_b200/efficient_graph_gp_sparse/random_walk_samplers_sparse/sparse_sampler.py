@@ -37,6 +37,20 @@ class SparseRandomWalk:
         self._device = device
         self._graph = None
 
+    @classmethod
+    def on_normalized_laplacian(cls, adjacency_matrix: sp.spmatrix, seed: Optional[int] = None,
+                                device=None) -> "SparseRandomWalk":
+        """Walker on D^-1/2 (D - A) D^-1/2 of ``adjacency_matrix``, normalised on the device
+        (same values and structure as ``get_normalized_laplacian``, graph_utils.py:5-30)."""
+        self = cls.__new__(cls)
+        self._graph = DeviceGraph.laplacian_of(adjacency_matrix, device)
+        self.adjacency = None
+        self.num_nodes = adjacency_matrix.shape[0]
+        self.seed = seed or 42
+        self.indptr = self.indices = self.data = None
+        self._device = device
+        return self
+
     @property
     def graph(self) -> DeviceGraph:
         if self._graph is None:

@@ -26,7 +26,7 @@ ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
 EXPORTS = (
     "grf_abi_version", "grf_last_error", "grf_walk_stage_stride", "grf_walk", "grf_scan_workspace_bytes",
     "grf_scan_counts", "grf_compact_steps", "grf_compact_blocks", "grf_blocks_from_steps", "grf_count_from_steps",
-    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_scale", "grf_union_rank", "grf_union_fill", "grf_union_materialize", "grf_cg_num_partials", "grf_cg_dot", "grf_cg_update", "grf_cg_direction",
+    "grf_transpose_count", "grf_transpose_fill", "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_scale", "grf_union_rank", "grf_union_fill", "grf_union_materialize", "grf_cg_num_partials", "grf_cg_dot", "grf_cg_update", "grf_cg_direction", "grf_laplacian_count", "grf_laplacian_fill",
 )
 
 
@@ -126,6 +126,10 @@ def lib():
     L.grf_cg_update.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, c_float, vp, vp]
     L.grf_cg_direction.restype = i32
     L.grf_cg_direction.argtypes = [vp, i64, vp, i64, vp, vp, i64, i32, c_float, vp, vp]
+    L.grf_laplacian_count.restype = i32
+    L.grf_laplacian_count.argtypes = [POINTER(GrfGraph), vp, vp, vp, vp]
+    L.grf_laplacian_fill.restype = i32
+    L.grf_laplacian_fill.argtypes = [POINTER(GrfGraph), vp, vp, vp, vp, vp, vp]
     L.grf_edge_scale.restype = i32
     L.grf_edge_scale.argtypes = [POINTER(GrfGraph), c_double, vp, vp]
     L.grf_block_windows.restype = i32

@@ -104,6 +104,47 @@ class DeviceGraph:
         return GrfGraph(self.n_nodes, self.nnz, self.row_ptr.data_ptr(), self.col_idx.data_ptr(),
                         self.val.data_ptr())
 
+    @classmethod
+    def _from_device(cls, row_ptr, col_idx, val, n_nodes) -> "DeviceGraph":
+        g = cls.__new__(cls)
+        g.device = row_ptr.device
+        g.n_nodes, g.nnz = int(n_nodes), int(col_idx.numel())
+        g._scaled = {}
+        g.row_ptr, g.col_idx, g.val = row_ptr, col_idx, val
+        return g
+
+    @classmethod
+    def laplacian_of(cls, adj, device=None) -> "DeviceGraph":
+        """The walk graph D^-1/2 (D - A) D^-1/2 of a scipy adjacency, normalised on the device
+        (graph_utils.py:5-30, bit-identical values and structure)."""
+        if adj.shape[0] != adj.shape[1]:
+            raise ValueError("Adjacency matrix must be square.")
+        a = adj.tocsr()
+        if not a.has_canonical_format:
+            a = a.copy()
+            a.sum_duplicates()
+        A = cls(a.indptr, a.indices, a.data.astype(float, copy=False), a.shape[0], device)
+        L = _lib.lib()
+        dev, n = A.device, A.n_nodes
+        deg = torch.empty(max(1, n), dtype=torch.float64, device=dev)
+        dis = torch.empty(max(1, n), dtype=torch.float64, device=dev)
+        cnt = torch.empty(max(1, n), dtype=torch.int32, device=dev)
+        g = A.c_struct()
+        check(L.grf_laplacian_count(ctypes.byref(g), _ptr(deg), _ptr(dis), _ptr(cnt), _stream(dev)))
+        ptr = scan_counts(cnt, n, 1, _lib.ORDER_ROW_MAJOR, i64=False)
+        total = int(ptr[-1].item()) if n else 0
+        col = torch.empty(max(1, total), dtype=torch.int32, device=dev)[:total]
+        val = torch.empty(max(1, total), dtype=torch.float64, device=dev)[:total]
+        check(L.grf_laplacian_fill(ctypes.byref(g), _ptr(deg), _ptr(dis), _ptr(ptr), _ptr(col), _ptr(val),
+                                   _stream(dev)))
+        return cls._from_device(ptr, col, val, n)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((self.val.cpu().numpy(), self.col_idx.cpu().numpy(), self.row_ptr.cpu().numpy()),
+                             shape=(self.n_nodes, self.n_nodes))
+
     def scaled_val(self, p_halt: float) -> torch.Tensor:
         """(deg * w) / (1 - p_halt) per edge (cached per p_halt): the load-update factor."""
         key = float(p_halt)

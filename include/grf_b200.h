@@ -134,6 +134,14 @@ typedef struct {
 int grf_abi_version(void);
 const char *grf_last_error(void); /* host string, thread-local */
 
+/* Replaces utils_sparse/graph_utils.py:5-30: normalized Laplacian D^-1/2 (D - A) D^-1/2 of a canonical
+ * CSR adjacency (sorted columns, no duplicates) on the device, bit-identical to the reference's scipy
+ * result.  count: deg / dis (double[n]) and the entries per output row; caller scans
+ * (grf_scan_counts(n, 1)) and allocates; fill writes the output CSR (sorted columns). */
+int grf_laplacian_count(const GrfGraph *adj, double *deg, double *dis, int32_t *out_cnt, void *stream);
+int grf_laplacian_fill(const GrfGraph *adj, const double *deg, const double *dis, const int32_t *out_ptr,
+                       int32_t *out_col, double *out_val, void *stream);
+
 /* Per-edge factor of the load update, (deg * w) / (1 - p_halt) with the reference's rounding
  * order (sparse_sampler.py:54); lets the walker skip a float64 division per step. */
 int grf_edge_scale(const GrfGraph *graph, double p_halt, double *scaled_val /* [nnz] */, void *stream);

@@ -270,6 +270,34 @@ def test_row_chunking_does_not_change_the_result(env):
     _native_case(env, lap, 50, 0.1, 4, seed=4, max_stage_bytes=50_000)
 
 
+def test_device_laplacian_is_bit_exact(env):
+    """grf_laplacian_* == the reference's scipy Laplacian (graph_utils.py:5-30): structure and float64 bits,
+    with isolated nodes, self-loops, explicit zeros, weights, rows of every length around the 32-lane batches."""
+    eng, o = env["eng"], env["o"]
+    rng = np.random.default_rng(0)
+    cases = [grid_graph(13, 7), ring_graph(64), random_graph(300, 200, 3, weighted=True),
+             powerlaw_graph(2000, 15000, 5), sp.csr_matrix((5, 5))]
+    for trial in range(6):
+        n = 97
+        m = sp.random(n, n, density=0.12 if trial % 2 else 0.45, random_state=trial, format="csr")
+        m = (m + m.T).tocsr()
+        if trial >= 2:
+            m = (m + sp.diags(rng.uniform(0.1, 1, n) * (rng.uniform(size=n) < 0.3))).tocsr()   # self-loops
+        if trial >= 4:
+            m.data[rng.integers(0, m.nnz, 20)] = 0.0                                            # explicit zeros
+        cases.append(m)
+    for a in cases:
+        a = a.tocsr()
+        a.sum_duplicates()
+        a.sort_indices()
+        want = o.normalized_laplacian_sparse(a).tocsr()
+        want.sort_indices()
+        got = eng.DeviceGraph.laplacian_of(a).to_scipy()
+        assert np.array_equal(got.indptr, want.indptr), a.shape
+        assert np.array_equal(got.indices, want.indices)
+        assert np.array_equal(got.data.view(np.int64), want.data.view(np.int64))
+
+
 def test_argument_validation(env):
     eng = env["eng"]
     g = eng.DeviceGraph.from_scipy(ring_graph(10))
