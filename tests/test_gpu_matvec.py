@@ -362,6 +362,53 @@ def test_sharded_rows_sum_to_the_full_product(env, case):
     assert torch.allclose(parts, want[x], rtol=1e-4, atol=1e-5 * float(want.abs().max()))
 
 
+@pytest.mark.parametrize("kind", ["grid", "powerlaw", "isolated", "ring_bigW", "no_edges"])
+def test_every_path_on_small_and_degenerate_graphs(env, kind):
+    """Device Laplacian -> walker (chunked staging) -> step matrices / Phi blocks -> every matvec variant
+    (per-length, merged plan, row subsets, tiled, fused CG) on small graphs incl. an edgeless one; all
+    against float64."""
+    eng, torch, o = env["eng"], env["torch"], env["o"]
+    from grf_b200.cg import linear_cg_fused
+    from gpu_util import ring_graph
+
+    adj, W, L = {"grid": (grid_graph(23, 17), 20, 4), "powerlaw": (powerlaw_graph(1500, 12000, 1), 40, 3),
+                 "isolated": (random_graph(200, 90, 2, weighted=True), 7, 5), "ring_bigW": (ring_graph(333), 300, 3),
+                 "no_edges": (sp.csr_matrix((40, 40)), 5, 3)}[kind]
+    g = eng.DeviceGraph.laplacian_of(adj)
+    cfg = eng.WalkConfig(W, 0.1, L, seed=3)
+    mats = eng.build_step_matrices(g, cfg, max_stage_bytes=200_000).to_scipy()
+    want_mats = env["c"].step_matrices(o.normalized_laplacian_sparse(adj), W, 0.1, L, seed=3)
+    for a, b in zip(mats, want_mats):
+        assert (abs(a - b)).max() == 0 if a.nnz else b.nnz == 0
+    phi = eng.build_phi_blocks(g, cfg)
+    n = phi.n_rows
+    rng = np.random.default_rng(1)
+    f = rng.standard_normal(L).astype(np.float32)
+    mats32 = [m.astype(np.float32) for m in mats]
+    ft = torch.tensor(f)
+    for t in (1, 3, 16, 17, 40):
+        v = rng.standard_normal((n, t)).astype(np.float32)
+        want = o.phi_matvec_f64(mats32, f, v)
+        vt = torch.tensor(v).cuda()
+        assert _close(phi.matvec(ft, vt).cpu().numpy(), want, rtol=5e-5)
+        assert _close(phi.plan(ft, t)(vt).cpu().numpy(), want, rtol=5e-5)
+        x = rng.permutation(n)[: max(1, n // 3)]
+        xt = torch.tensor(x).cuda()
+        want_s = o.phi_matvec_f64(mats32, f, v[: x.size], x1=x, x2=x)
+        assert _close(phi.plan(ft, t, x1=xt, x2=xt)(vt[: x.size].contiguous()).cpu().numpy(), want_s, rtol=5e-5)
+    phi.use_tiles = True
+    phi.build_windows()
+    v = rng.standard_normal((n, 16)).astype(np.float32)
+    assert _close(phi.matvec(ft, torch.tensor(v).cuda()).cpu().numpy(), o.phi_matvec_f64(mats32, f, v), rtol=5e-5)
+    x = np.sort(rng.permutation(n)[: max(2, n // 2)])
+    plan = phi.plan(ft, 8, x1=torch.tensor(x).cuda(), x2=torch.tensor(x).cuda())
+    b = rng.standard_normal((x.size, 8)).astype(np.float32)
+    sol = linear_cg_fused(plan, torch.tensor(b).cuda(), 0.5, tolerance=1e-6, eps=1e-30, max_iter=400)
+    dense = sum(float(fl) * m.astype(np.float64) for fl, m in zip(f, mats32)).toarray()[x]
+    want = np.linalg.solve(dense @ dense.T + 0.5 * np.eye(x.size), b.astype(np.float64))
+    assert np.abs(sol.cpu().numpy() - want).max() <= 5e-4 * np.abs(want).max()
+
+
 def test_large_grid_roundtrip_properties(env):
     """BASELINE config-2 shape (316x316 grid, W=100, L=5): M_0 = I, transpose multiset, <a, K b> = <K a, b>."""
     eng, torch = env["eng"], env["torch"]
