@@ -412,6 +412,45 @@ __global__ void __launch_bounds__(256) scatter_rows_unique_kernel(const int32_t 
     }
 }
 
+// U[col, :] += f[l] * val * V[k, :] for every entry of row x2[k] -- the first half of the product
+// when x2 is a small subset of the rows (a BO training set of 10^2..10^3 nodes out of 10^5..10^6):
+// work proportional to the selected rows instead of one pass over all of Phi^T.  fp32 atomics:
+// the summation order, hence the last bits, can differ between runs.
+template <int TPR, int VEC>
+__global__ void __launch_bounds__(256) spmm_scatter_kernel(const int32_t *__restrict__ ptr,
+                                                           const GrfEntry *__restrict__ ent,
+                                                           const float *__restrict__ f, int32_t L,
+                                                           const int32_t *__restrict__ x2, int64_t n2,
+                                                           int64_t row_lo, int64_t n_rows,
+                                                           const float *__restrict__ V, int64_t ldv,
+                                                           float *__restrict__ U, int64_t ldu, int32_t t) {
+    __shared__ float fs[kMaxSteps];
+    if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
+    __syncthreads();
+    const int sub = threadIdx.x % TPR;
+    const int64_t task0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+    const int64_t task_stride = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
+    for (int64_t k = task0; k < n2; k += task_stride) {
+        const int64_t row = (int64_t)__ldg(x2 + k) - row_lo;
+        if (row < 0 || row >= n_rows) continue;
+        const int32_t b = __ldg(ptr + row * L), e = __ldg(ptr + (row + 1) * L);
+        for (int c0 = sub * VEC; c0 < t; c0 += TPR * VEC) {
+            float v[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] = c0 + j < t ? __ldg(V + k * ldv + c0 + j) : 0.f;
+            for (int32_t i = b; i < e; ++i) {
+                const int2 raw = __ldg(ent2 + i);
+                const float a = __int_as_float(raw.y) * fs[(uint32_t)raw.x >> kStepShift];
+                float *dst = U + (int64_t)((uint32_t)raw.x & kColMask) * ldu + c0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (c0 + j < t) atomicAdd(dst + j, a * v[j]);
+            }
+        }
+    }
+}
+
 // Y[row, :] = sum over the row's chunks (in chunk order: deterministic) of partial[chunk, :]
 __global__ void __launch_bounds__(256) long_reduce_kernel(const int32_t *__restrict__ rows,
                                                           const int32_t *__restrict__ chunk_ptr,
@@ -645,7 +684,19 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         GRF_REQUIRE(phi->tblk_ptr, "grf_phi_matvec: Phi^T blocks missing");
         const float *src = v;
         int64_t lds = ldv;
-        if (x2) {
+        const bool scatter_half = x2 && phi->blk_ptr && n2 * 16 < phi->n_rows;
+        if (scatter_half) {
+            // small row subset: scatter from the selected rows of Phi instead of a pass over Phi^T
+            GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
+            if (n2 > 0) {
+                const Shape sh = pick_shape(t, true);
+                const int grid = spmm_grid(n2, sh.tpr);
+                GRF_DISPATCH_SHAPE(spmm_scatter_kernel, sh,
+                                   <<<grid, 256, 0, st>>>(phi->blk_ptr, phi->entries, f, L, x2, n2, phi->row_lo,
+                                                          phi->n_rows, v, ldv, u, ldu, t));
+                GRF_CUDA_OK(cudaGetLastError());
+            }
+        } else if (x2) {
             GRF_REQUIRE(vfull, "grf_phi_matvec: vfull workspace needed when x2 is given");
             // x2_unique: the caller guarantees no repeated ids and a vfull that was zeroed once; rows
             // outside x2 then stay zero across calls and the scatter needs neither memset nor atomics
@@ -671,7 +722,9 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             src = vfull;
             lds = ldu;
         }
-        if (phi->n_cols > 0 && phi->n_rows == 0) {
+        if (scatter_half) {
+            // done above
+        } else if (phi->n_cols > 0 && phi->n_rows == 0) {
             // empty shard: its partial sum is zero (and there is no row of V to read)
             GRF_CUDA_OK(cudaMemset2DAsync(u, (size_t)ldu * sizeof(float), 0, (size_t)t * sizeof(float),
                                           (size_t)phi->n_cols, st));

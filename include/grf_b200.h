@@ -202,6 +202,9 @@ int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t 
  * are left untouched).  V [n2][ldv], out [n1][ldo], U workspace [n_cols][ldu]
  * (= Phi[x2]^T V, this GPU's partial sum: the multi-GPU caller all-reduces it
  * between the two halves); vfull workspace [n_rows][ldu], used when x2 != NULL.
+ * When x2 selects fewer than 1/16 of the local rows (a BO training set), the first half scatters
+ * from those rows of Phi with fp32 atomics instead of passing over Phi^T (cost proportional to the
+ * selected rows; summation order not fixed).
  * which: 1 = first half only (U), 2 = second half only (out from U), 3 = both;
  * add 4 to force the global-gather kernel even when column windows are present; add 8 when x2
  * holds no repeated ids and vfull was zero-filled once by the caller (the scatter then needs no

@@ -269,6 +269,30 @@ def test_union_rows_match_scipy_union(env, case):
     assert abs(mt - got.T).max() == 0
 
 
+def test_small_training_set_takes_the_scatter_half(env, case):
+    """n2 << n_rows (a BO training set): the first half scatters from the selected rows (atomics)."""
+    torch, o = env["torch"], env["o"]
+    phi = case["phi"]
+    rng = np.random.default_rng(21)
+    f = rng.standard_normal(phi.n_steps).astype(np.float32)
+    mats32 = [m.astype(np.float32) for m in case["mats"]]
+    for n2, t in [(30, 1), (30, 16), (7, 5), (1, 3), (40, 20)]:
+        assert n2 * 16 < phi.n_rows
+        x2 = rng.integers(0, phi.n_rows, size=n2)            # repeats allowed
+        x1 = rng.permutation(phi.n_rows)[:333]
+        v = rng.standard_normal((n2, t)).astype(np.float32)
+        want = o.phi_matvec_f64(mats32, f, v, x1=x1, x2=x2)
+        ft, vt = torch.tensor(f), torch.tensor(v).cuda()
+        got = phi.matvec(ft, vt, x1=torch.tensor(x1).cuda(), x2=torch.tensor(x2).cuda()).cpu().numpy()
+        assert _close(got, want, rtol=5e-5)
+        got_p = phi.plan(ft, t, x1=torch.tensor(x1).cuda(), x2=torch.tensor(x2).cuda())(vt).cpu().numpy()
+        assert _close(got_p, want, rtol=5e-5)
+        # square K[x, x] as in predict(): CG operator
+        want_sq = o.phi_matvec_f64(mats32, f, v, x1=x2, x2=x2)
+        got_sq = phi.plan(ft, t, x1=torch.tensor(x2).cuda(), x2=torch.tensor(x2).cuda(), merged=False)(vt)
+        assert _close(got_sq.cpu().numpy(), want_sq, rtol=5e-5)
+
+
 def test_apply_and_apply_t_are_the_two_halves(env, case):
     torch = env["torch"]
     phi = case["phi"]
