@@ -379,6 +379,91 @@ __global__ void __launch_bounds__(256) block_windows_kernel(const int32_t *__res
     }
 }
 
+// Few right-hand sides (t <= 4: Thompson sampling draws one posterior sample, bo_utils.py:272): G lanes
+// share a row and take DIFFERENT entries (CSR-vector), each gathering all t columns of X[col, :], and
+// reduce with shuffles at the end.  Entry loads are coalesced across the group and a long row (a BO
+// training row holds up to 1 + (L-1) W entries) is spread over 8 or 32 lanes instead of one.
+template <int G, int T>
+__global__ void __launch_bounds__(256) spmv_coop_kernel(const int32_t *__restrict__ ptr,
+                                                        const GrfEntry *__restrict__ ent,
+                                                        const float *__restrict__ f, int32_t L,
+                                                        const int32_t *__restrict__ row_ids, int64_t n_tasks,
+                                                        int64_t row_lo, int64_t n_rows, const float *__restrict__ X,
+                                                        int64_t ldx, float *__restrict__ Y, int64_t ldy,
+                                                        int32_t long_thresh, const int2 *__restrict__ chunk_bounds,
+                                                        int32_t out_by_row) {
+    __shared__ float fs[kMaxSteps];
+    if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
+    __syncthreads();
+    const int sub = threadIdx.x % G;
+    constexpr int kGroupsPerWarp = 32 / G;
+    const int g_in_warp = (threadIdx.x & 31) / G;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
+    for (int64_t kb = warp0 * kGroupsPerWarp; kb < n_tasks; kb += warp_stride * kGroupsPerWarp) {
+        const int64_t k = kb + g_in_warp;
+        int32_t b = 0, e = 0;
+        bool mine = false;
+        int64_t orow = k;
+        if (chunk_bounds) {
+            mine = k < n_tasks;
+            if (mine) {
+                const int2 be = __ldg(chunk_bounds + k);
+                b = be.x;
+                e = be.y;
+            }
+        } else {
+            int64_t row = -1;
+            if (k < n_tasks) row = row_ids ? (int64_t)__ldg(row_ids + k) - row_lo : k;
+            mine = row >= 0 && row < n_rows;
+            if (out_by_row) orow = row;
+            if (mine) {
+                b = __ldg(ptr + row * L);
+                e = __ldg(ptr + (row + 1) * L);
+                if (long_thresh > 0 && e - b > long_thresh) {
+                    mine = false;
+                    e = b;
+                }
+            }
+        }
+        float acc[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) acc[j] = 0.f;
+        constexpr int kU = 4;  // entries in flight per lane
+        for (int32_t i0 = b + sub; i0 < e; i0 += G * kU) {
+            int2 raw[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int32_t i = i0 + u * G;
+                raw[u] = i < e ? __ldg(ent2 + i) : make_int2(0, 0);
+            }
+            float x[kU][T];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const float *src = X + (int64_t)((uint32_t)raw[u].x & kColMask) * ldx;  // padding reads row 0
+#pragma unroll
+                for (int j = 0; j < T; ++j) x[u][j] = __ldg(src + j);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const float a = __int_as_float(raw[u].y) * fs[(uint32_t)raw[u].x >> kStepShift];
+#pragma unroll
+                for (int j = 0; j < T; ++j) acc[j] = fmaf(a, x[u][j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) {
+#pragma unroll
+            for (int j = 0; j < T; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], d);
+        }
+        if (mine && sub == 0) {
+#pragma unroll
+            for (int j = 0; j < T; ++j) Y[orow * ldy + j] = acc[j];
+        }
+    }
+}
+
 // vfull[(x2[k] - row_lo), :] += v[k, :]   (vfull zeroed by the caller)
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__restrict__ x2, int64_t n2,
                                                            int64_t row_lo, int64_t n_rows,
@@ -416,7 +501,6 @@ __global__ void __launch_bounds__(256) scatter_rows_unique_kernel(const int32_t 
 // when x2 is a small subset of the rows (a BO training set of 10^2..10^3 nodes out of 10^5..10^6):
 // work proportional to the selected rows instead of one pass over all of Phi^T.  fp32 atomics:
 // the summation order, hence the last bits, can differ between runs.
-template <int TPR, int VEC>
 __global__ void __launch_bounds__(256) spmm_scatter_kernel(const int32_t *__restrict__ ptr,
                                                            const GrfEntry *__restrict__ ent,
                                                            const float *__restrict__ f, int32_t L,
@@ -424,29 +508,24 @@ __global__ void __launch_bounds__(256) spmm_scatter_kernel(const int32_t *__rest
                                                            int64_t row_lo, int64_t n_rows,
                                                            const float *__restrict__ V, int64_t ldv,
                                                            float *__restrict__ U, int64_t ldu, int32_t t) {
+    // one warp per selected row; lanes take different entries (coalesced), each adds all t columns
     __shared__ float fs[kMaxSteps];
     if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
     __syncthreads();
-    const int sub = threadIdx.x % TPR;
-    const int64_t task0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
-    const int64_t task_stride = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
-    for (int64_t k = task0; k < n2; k += task_stride) {
+    for (int64_t k = warp0; k < n2; k += nwarps) {
         const int64_t row = (int64_t)__ldg(x2 + k) - row_lo;
         if (row < 0 || row >= n_rows) continue;
         const int32_t b = __ldg(ptr + row * L), e = __ldg(ptr + (row + 1) * L);
-        for (int c0 = sub * VEC; c0 < t; c0 += TPR * VEC) {
-            float v[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) v[j] = c0 + j < t ? __ldg(V + k * ldv + c0 + j) : 0.f;
-            for (int32_t i = b; i < e; ++i) {
-                const int2 raw = __ldg(ent2 + i);
-                const float a = __int_as_float(raw.y) * fs[(uint32_t)raw.x >> kStepShift];
-                float *dst = U + (int64_t)((uint32_t)raw.x & kColMask) * ldu + c0;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                    if (c0 + j < t) atomicAdd(dst + j, a * v[j]);
-            }
+        const float *vk = V + k * ldv;
+        for (int32_t i = b + lane; i < e; i += 32) {
+            const int2 raw = __ldg(ent2 + i);
+            const float a = __int_as_float(raw.y) * fs[(uint32_t)raw.x >> kStepShift];
+            float *dst = U + (int64_t)((uint32_t)raw.x & kColMask) * ldu;
+            for (int c = 0; c < t; ++c) atomicAdd(dst + c, a * __ldg(vk + c));
         }
     }
 }
@@ -626,17 +705,59 @@ using namespace grf;
 static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float *f, int32_t L,
                             const int32_t *row_ids, int64_t n_tasks, int64_t row_lo, int64_t n_rows,
                             const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t_valid,
-                            bool vec_ok, bool out_by_row, cudaStream_t st) {
+                            bool vec_ok, bool out_by_row, int64_t avg_row_len, cudaStream_t st) {
     // vec_ok: X rows are 16-byte aligned and padded to a multiple of 4 columns -> compute the padded
     // column count with float4 gathers; only the t_valid real columns are stored to Y
+    const bool split = lr && lr->n_long > 0 && (!row_ids || out_by_row);
+    if (split) {
+        GRF_REQUIRE(lr->rows && lr->chunk_ptr && lr->chunk_bounds && lr->partial && lr->ld >= t_valid,
+                    "grf_phi_matvec: incomplete long-row metadata");
+    }
+    if (t_valid <= 4 && avg_row_len > 64) {
+        // CSR-vector path for long rows (a row subset of a W = 1000 Phi): 32 lanes per row.  Short rows
+        // (config 2: 28..64 entries) are faster with one row per lane group in the kernel below.
+        const bool wide = true;
+        const int groups_per_cta = 256 / (wide ? 32 : 8);
+        auto grid_of = [&](int64_t tasks) {
+            int64_t g = (tasks + groups_per_cta - 1) / groups_per_cta;
+            if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
+            return (int)(g < 1 ? 1 : g);
+        };
+#define GRF_COOP(G, T, GRID, ...) spmv_coop_kernel<G, T><<<GRID, 256, 0, st>>>(__VA_ARGS__)
+#define GRF_COOP_T(G, GRID, ...)                                  \
+    switch (t_valid) {                                             \
+        case 1: GRF_COOP(G, 1, GRID, __VA_ARGS__); break;          \
+        case 2: GRF_COOP(G, 2, GRID, __VA_ARGS__); break;          \
+        case 3: GRF_COOP(G, 3, GRID, __VA_ARGS__); break;          \
+        default: GRF_COOP(G, 4, GRID, __VA_ARGS__); break;         \
+    }
+#define GRF_COOP_LAUNCH(GRID, ...)              \
+    if (wide) {                                 \
+        GRF_COOP_T(32, GRID, __VA_ARGS__)       \
+    } else {                                    \
+        GRF_COOP_T(8, GRID, __VA_ARGS__)        \
+    }
+        GRF_COOP_LAUNCH(grid_of(n_tasks), ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy,
+                        split ? lr->threshold : 0, nullptr, out_by_row ? 1 : 0);
+        GRF_CUDA_OK(cudaGetLastError());
+        if (split) {
+            GRF_COOP_LAUNCH(grid_of(lr->n_chunks), ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
+                            lr->partial, lr->ld, 0, (const int2 *)lr->chunk_bounds, 0);
+            GRF_CUDA_OK(cudaGetLastError());
+            int64_t g = ((int64_t)lr->n_long * t_valid + 255) / 256;
+            if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
+            long_reduce_kernel<<<(int)g, 256, 0, st>>>(lr->rows, lr->chunk_ptr, lr->partial, lr->ld, Y, ldy, t_valid,
+                                                       lr->n_long);
+            GRF_CUDA_OK(cudaGetLastError());
+        }
+#undef GRF_COOP_LAUNCH
+#undef GRF_COOP_T
+#undef GRF_COOP
+        return GRF_OK;
+    }
     const int32_t t = vec_ok ? (t_valid + 3) & ~3 : t_valid;
     const int32_t vec_store = (ldy % 4 == 0) && aligned16(Y);
     const Shape sh = pick_shape(t, vec_ok);
-    const bool split = lr && lr->n_long > 0 && (!row_ids || out_by_row);
-    if (split) {
-        GRF_REQUIRE(lr->rows && lr->chunk_ptr && lr->chunk_bounds && lr->partial && lr->ld >= t,
-                    "grf_phi_matvec: incomplete long-row metadata");
-    }
     const int grid = spmm_grid(n_tasks, sh.tpr);
     GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
                        <<<grid, 256, 0, st>>>(ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy, t,
@@ -675,6 +796,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
     GRF_REQUIRE(x2 || n2 == phi->n_rows, "grf_phi_matvec: n2 must equal n_rows when x2 is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t L = phi->n_steps;
+    const int64_t avg_len = phi->nnz > 0 && phi->n_rows > 0 ? phi->nnz / phi->n_rows : 0;  // entries per row of Phi
     const int tile_mode = (which >> 2) & 1;  // +4: never use the shared-memory-tiled kernel
     const bool x2_unique = (which >> 3) & 1;  // +8: x2 has no repeated ids and vfull was zeroed once
     which &= 3;
@@ -689,11 +811,10 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             // small row subset: scatter from the selected rows of Phi instead of a pass over Phi^T
             GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
             if (n2 > 0) {
-                const Shape sh = pick_shape(t, true);
-                const int grid = spmm_grid(n2, sh.tpr);
-                GRF_DISPATCH_SHAPE(spmm_scatter_kernel, sh,
-                                   <<<grid, 256, 0, st>>>(phi->blk_ptr, phi->entries, f, L, x2, n2, phi->row_lo,
-                                                          phi->n_rows, v, ldv, u, ldu, t));
+                int64_t g = (n2 + 7) / 8;
+                if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
+                spmm_scatter_kernel<<<(int)g, 256, 0, st>>>(phi->blk_ptr, phi->entries, f, L, x2, n2, phi->row_lo,
+                                                            phi->n_rows, v, ldv, u, ldu, t);
                 GRF_CUDA_OK(cudaGetLastError());
             }
         } else if (x2) {
@@ -746,10 +867,10 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                     rc = phi->n_tcols == 0
                              ? GRF_OK
                              : launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, phi->tcols, phi->n_tcols, 0,
-                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, st);
+                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, avg_len, st);
                 } else {
                     rc = launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0, phi->n_cols,
-                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, st);
+                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, avg_len, st);
                 }
                 if (rc != GRF_OK) return rc;
             }
@@ -768,7 +889,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         }
         if (!tiled) {
             const int rc = launch_spmm_pass(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
-                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, st);
+                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, avg_len, st);
             if (rc != GRF_OK) return rc;
         }
     }

@@ -51,7 +51,7 @@ class GrfPhi(Structure):
                 ("blk_ptr", c_void_p), ("entries", c_void_p), ("tblk_ptr", c_void_p), ("tentries", c_void_p),
                 ("win", c_void_p), ("twin", c_void_p), ("win_max_width", c_int32), ("twin_max_width", c_int32),
                 ("long_fwd", POINTER(GrfLongRows)), ("long_t", POINTER(GrfLongRows)),
-                ("tcols", c_void_p), ("n_tcols", c_int64)]
+                ("tcols", c_void_p), ("n_tcols", c_int64), ("nnz", c_int64)]
 
 
 def nvcc_command(out_path: str = SO_PATH):

@@ -52,7 +52,7 @@ def linear_cg(matmul_closure: Callable[[torch.Tensor], torch.Tensor], rhs: torch
 
 
 def linear_cg_fused(plan, rhs: torch.Tensor, sigma2: float = 0.0, tolerance: float = 1e-2, max_iter: int = 1000,
-                    eps: float = 1e-10, check_every: int = 4, return_info: bool = False):
+                    eps: float = 1e-10, check_every: int = 4, return_info: bool = False, use_graph: bool = True):
     """Solve ``(K + sigma2 I) X = rhs`` with ``K`` = a square :class:`~grf_b200.engine.MatvecPlan`.
 
     Same iteration and stopping rule as :func:`linear_cg`; every iteration is the two spmm
@@ -86,22 +86,54 @@ def linear_cg_fused(plan, rhs: torch.Tensor, sigma2: float = 0.0, tolerance: flo
     n_part = L.grf_cg_num_partials(n, t)
     pa = torch.empty((n_part, t), dtype=torch.float32, device=dev)
     pb = torch.empty((n_part, t), dtype=torch.float32, device=dev)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
     def P(tensor):
         return ctypes.c_void_p(tensor.data_ptr())
 
     min_iter = min(10, max_iter - 1)
+    state = {"rs": rs, "rs_next": rs_next}
+
+    def iterate(count):
+        for _ in range(count):
+            plan(d, kd)
+            check(L.grf_cg_dot(P(kd), t, P(d), t, float(sigma2), n, t, P(pa), stream_of()))
+            check(L.grf_cg_update(P(x), t, P(r), t, P(d), t, P(kd), t, P(state["rs"]), P(pa), n, t, float(eps),
+                                  P(pb), stream_of()))
+            check(L.grf_cg_direction(P(d), t, P(r), t, P(state["rs"]), P(pb), n, t, float(eps),
+                                     P(state["rs_next"]), stream_of()))
+            state["rs"], state["rs_next"] = state["rs_next"], state["rs"]
+
+    def stream_of():
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def converged():
+        return float(state["rs"].sqrt().mean()) < tolerance
+
     iters = 0
-    for k in range(max_iter):
-        plan(d, kd)
-        check(L.grf_cg_dot(P(kd), t, P(d), t, float(sigma2), n, t, P(pa), stream))
-        check(L.grf_cg_update(P(x), t, P(r), t, P(d), t, P(kd), t, P(rs), P(pa), n, t, float(eps), P(pb), stream))
-        check(L.grf_cg_direction(P(d), t, P(r), t, P(rs), P(pb), n, t, float(eps), P(rs_next), stream))
-        rs, rs_next = rs_next, rs
-        iters = k + 1
-        if iters >= min_iter and (iters % check_every == 0 or iters == max_iter):
-            if float(rs.sqrt().mean()) < tolerance:
+    block = max(2, check_every + (check_every & 1))  # even: the rs ping-pong returns to its start
+    # capturing costs a few ms: worth it only where launches dominate (small systems, many iterations)
+    if use_graph and max_iter >= 4 * block and n * t <= 262144:
+        # a CG iteration here is ~5 short launches; replaying a captured block of them removes the
+        # Python / launch overhead that otherwise dominates small systems (a BO training set)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            iterate(block)                      # real iterations 1..block (also the warm-up)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        iters = block
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            iterate(block)                      # captured, not executed
+        while iters < max_iter:
+            if iters >= min_iter and converged():
+                break
+            graph.replay()
+            iters += block
+    else:
+        while iters < max_iter:
+            step = min(block, max_iter - iters)
+            iterate(step)
+            iters += step
+            if iters >= min_iter and converged():
                 break
     out = x * norm
     out = out[:, 0] if squeeze else out

@@ -526,7 +526,7 @@ class PhiBlocks:
                       ctypes.pointer(fwd) if fwd is not None else None,
                       ctypes.pointer(tr) if tr is not None else None,
                       None if self._tcols is None else self._tcols.data_ptr(),
-                      0 if self._tcols is None else self._tcols.numel())
+                      0 if self._tcols is None else self._tcols.numel(), self.nnz)
 
     @staticmethod
     def _ids(x, dev):
@@ -547,7 +547,7 @@ class PhiBlocks:
         if x.dim() != 2:
             raise ValueError("right-hand side must be 2-D [rows, t]")
         x = x.to(torch.float32)
-        if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        if (x.stride(1) != 1 and x.shape[1] != 1) or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
             x = x.contiguous()
         return x
 
@@ -843,7 +843,7 @@ class MatvecPlan:
     def __call__(self, v: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """v: float32 [n2, t] with unit column stride; out: float32 [n1, t] (allocated if None)."""
         if v.dtype != torch.float32 or v.dim() != 2 or v.shape[0] != self.n2 or v.shape[1] != self.t \
-                or v.stride(1) != 1:
+                or (v.stride(1) != 1 and v.shape[1] != 1) or (v.shape[0] > 1 and v.stride(0) < self.t):
             raise ValueError("plan: v must be float32 [n2, t] with unit column stride")
         if out is None:
             out = torch.zeros((self.n1, self.t), dtype=torch.float32, device=self._dev)

@@ -129,6 +129,7 @@ typedef struct {
      * Phi^T V then visits only those and zero-fills the rest of U */
     const int32_t *tcols;
     int64_t n_tcols;
+    int64_t nnz; /* stored entries (0 = unknown); picks the lanes-per-row of the few-column kernels */
 } GrfPhi;
 
 int grf_abi_version(void);

@@ -157,6 +157,8 @@ def test_cg_posterior_mean_within_1e4_of_direct_solve(setup):
     rel = np.linalg.norm(got.cpu().numpy() - want) / np.linalg.norm(want)
     assert rel <= 1e-4, (rel, info)
     # pathwise samples: right shape, finite, and centred on the mean
+    one, _ = model.predict(torch.tensor(test).cuda(), n_samples=1, cg_tolerance=1e-4, return_info=True)   # Thompson
+    assert tuple(one.shape) == (1, test.size) and bool(torch.isfinite(one).all())
     samples, info = model.predict(torch.tensor(test).cuda(), n_samples=200, cg_tolerance=1e-4, return_info=True)
     assert tuple(samples.shape) == (200, test.size) and bool(torch.isfinite(samples).all())
     post_var = np.diag(phi[test] @ phi[test].T - phi[test] @ phi[train].T @ np.linalg.solve(Ktt, phi[train] @ phi[test].T))
