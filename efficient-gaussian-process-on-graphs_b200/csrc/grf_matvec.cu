@@ -200,7 +200,15 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
     const int sub = threadIdx.x % TPR;
     constexpr int kGroupsPerWarp = 32 / TPR;
     const int g_in_warp = (threadIdx.x & 31) / TPR;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // CTAs are handed to the SMs round-robin, so blockIdx = s, s + 148, s + 296 ... share an SM (and
+    // its L1).  Give those CTAs NEIGHBOURING rows: for a banded Phi their gathers then hit the same
+    // lines of X.  (Only a locality hint: correctness does not depend on the placement.)
+    int logical_block = blockIdx.x;
+    if (gridDim.x % kSmCount == 0) {
+        const int per_sm = gridDim.x / kSmCount;
+        logical_block = (blockIdx.x % kSmCount) * per_sm + blockIdx.x / kSmCount;
+    }
+    const int64_t warp0 = ((int64_t)logical_block * blockDim.x + threadIdx.x) >> 5;
     const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
     const int n_tiles = (t + TPR * VEC - 1) / (TPR * VEC);
@@ -665,7 +673,7 @@ static int try_launch_tiled(const int32_t *ptr, const GrfEntry *ent, const float
 static int spmm_grid(int64_t n_tasks, int tpr) {
     const int64_t threads = n_tasks * tpr;
     int64_t g = (threads + 255) / 256;
-    const int64_t cap = (int64_t)kSmCount * 4;  // 4 resident CTAs of 256 threads per SM at 64 registers
+    const int64_t cap = (int64_t)kSmCount * 3;  // 3 resident CTAs of 256 threads per SM at 80 registers
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
