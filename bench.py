@@ -298,7 +298,7 @@ def run_gpu(args):
         phi_e = engine.PhiBlocks.from_step_matrices(steps)
         phi_e.row_lo = lo
         vd = v_host.to(dev, non_blocking=True)
-        out_host = phi_e.plan(f, T_RHS, group=True if world > 1 else None)(vd).cpu()
+        out_host = phi_e.plan(f, T_RHS, group=True if world > 1 else None, merged=False)(vd).cpu()   # one product
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if i > 0:
