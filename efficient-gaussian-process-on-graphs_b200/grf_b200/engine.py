@@ -825,6 +825,18 @@ class MatvecPlan:
         self._c = self.phi.c_struct(self.ldu)
         self._fn = _lib.lib().grf_phi_matvec
         self._dev = dev
+        self._shared = self._shared_buf = None
+        if group is not None:
+            # exchange only the columns that more than one row shard touches (sharding.shared_columns)
+            from . import sharding
+
+            touched = torch.ones(phi.n_cols, dtype=torch.bool, device=dev)
+            if self.phi._tcols is not None:
+                touched.zero_()
+                touched[self.phi._tcols.long()] = True
+            self._shared = sharding.shared_columns(touched, None if group is True else group)
+            if self._shared is not None and self._shared.numel():
+                self._shared_buf = torch.empty((self._shared.numel(), self.ldu), dtype=torch.float32, device=dev)
 
     def set_modulator(self, f) -> None:
         if self.merged:
@@ -850,9 +862,9 @@ class MatvecPlan:
         if self.group is None:
             self._call(v, out, 3)
         else:
-            import torch.distributed as dist
+            from . import sharding
 
             self._call(v, None, 1)
-            dist.all_reduce(self.u, group=None if self.group is True else self.group)
+            sharding.reduce_shared(self.u, self._shared, self._shared_buf, None if self.group is True else self.group)
             self._call(None, out, 2)
         return out

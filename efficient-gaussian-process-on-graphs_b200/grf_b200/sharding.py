@@ -58,3 +58,43 @@ def sharded_dot(a: torch.Tensor, b: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(d, group=group)
     return d
+
+
+def shared_columns(touched: torch.Tensor, group=None, max_fraction: float = 0.5) -> Optional[torch.Tensor]:
+    """Columns of Phi touched by at least two row shards (same result on every rank), or None when
+    they are more than ``max_fraction`` of all columns (then a plain all-reduce of U is cheaper).
+
+    ``touched``: bool / int [N], this shard's non-empty columns.  A column touched by ONE shard needs
+    no communication at all: its sum is that shard's partial, and only that shard reads it in the
+    second half of the product.  For a banded Phi the shared columns are just the bands around the
+    shard boundaries, so the exchange shrinks from N x t to O(bandwidth x t)."""
+    import torch.distributed as dist
+
+    count = touched.to(torch.int32).contiguous()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(count, group=group)
+    else:
+        return torch.zeros(0, dtype=torch.int64, device=touched.device)
+    shared = torch.nonzero(count >= 2).flatten()
+    if shared.numel() > max_fraction * touched.numel():
+        return None
+    return shared
+
+
+def reduce_shared(u: torch.Tensor, shared: Optional[torch.Tensor], buf: Optional[torch.Tensor] = None, group=None):
+    """Sum the per-shard partials ``u`` [N, ld] over the ranks, exchanging only the shared columns."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return u
+    if shared is None:
+        dist.all_reduce(u, group=group)
+        return u
+    if shared.numel() == 0:
+        return u
+    if buf is None:
+        buf = torch.empty((shared.numel(), u.shape[1]), dtype=u.dtype, device=u.device)
+    torch.index_select(u, 0, shared, out=buf)
+    dist.all_reduce(buf, group=group)
+    u.index_copy_(0, shared, buf)
+    return u

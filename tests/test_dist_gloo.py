@@ -37,9 +37,8 @@ def _worker(rank, world, port, out_dir):
     # the same graph / Phi on every rank (CSR graph replicated), rows sharded
     rng = np.random.default_rng(0)
     n = 101
-    a = sp.random(n, n, density=0.05, random_state=1, format="csr")
-    a = (a + a.T).tocsr()
-    a.data[:] = 1.0
+    i = np.arange(n)
+    a = sp.csr_matrix((np.ones(2 * n), (np.r_[i, i], np.r_[(i + 1) % n, (i - 1) % n])), shape=(n, n))   # ring: banded Phi
     lap = orc.normalized_laplacian_sparse(a)
     lo, hi = sharding.my_rows(n, world, rank)
     mats = c_oracle.step_matrices(lap, 12, 0.1, 3, seed=5, start_lo=lo, start_hi=hi)   # this rank's rows only
@@ -51,6 +50,18 @@ def _worker(rank, world, port, out_dir):
     out_g = sharding.sharded_kernel_matvec(
         lambda v: torch.tensor(phi_g.T @ v.numpy()), lambda u: torch.tensor(phi_g @ u.numpy()), v_g)
     dots = sharding.sharded_dot(out_g, v_g)
+    # shared-column exchange: only columns touched by both shards travel; every shard ends up with the
+    # full sum on the columns IT touches (the only ones its second half reads)
+    touched = torch.tensor(np.asarray((phi_g != 0).sum(axis=0)).ravel() > 0)
+    shared = sharding.shared_columns(touched, max_fraction=1.0)
+    u_g = torch.tensor(phi_g.T @ v_g.numpy())
+    u_full = u_g.clone()
+    dist.all_reduce(u_full)
+    u_sh = sharding.reduce_shared(u_g.clone(), shared)
+    assert shared is not None and 0 < shared.numel() < n
+    assert torch.allclose(u_sh[touched], u_full[touched], rtol=1e-13, atol=1e-13)
+    assert sharding.shared_columns(touched, max_fraction=0.0) is None          # falls back to the full all-reduce
+    assert torch.allclose(sharding.reduce_shared(u_g.clone(), None), u_full)
     np.save(os.path.join(out_dir, f"out{rank}.npy"), out_g.numpy())
     np.save(os.path.join(out_dir, f"dots{rank}.npy"), dots.numpy())
     dist.destroy_process_group()
@@ -79,9 +90,8 @@ def test_two_rank_sharded_matvec_equals_unsharded(tmp_path):
 
     rng = np.random.default_rng(0)
     n = 101
-    a = sp.random(n, n, density=0.05, random_state=1, format="csr")
-    a = (a + a.T).tocsr()
-    a.data[:] = 1.0
+    i = np.arange(n)
+    a = sp.csr_matrix((np.ones(2 * n), (np.r_[i, i], np.r_[(i + 1) % n, (i - 1) % n])), shape=(n, n))
     lap = orc.normalized_laplacian_sparse(a)
     mats = c_oracle.step_matrices(lap, 12, 0.1, 3, seed=5)
     v = rng.standard_normal((n, 4))
