@@ -25,7 +25,6 @@ int check_cuda(cudaError_t err, const char *what);
         if (!(cond)) return ::grf::fail(GRF_ERR_INVALID, __VA_ARGS__); \
     } while (0)
 
-constexpr int kWarp = 32;
 // Phi / Phi^T entries carry their walk length in the top bits of `col`
 // (GRF_ENTRY_STEP_SHIFT in grf_b200.h): the matvec then needs one pointer pair
 // per row instead of one per (row, length).

@@ -148,6 +148,44 @@ def _rmat(scale, m, seed=0, a=0.57, b=0.19, c=0.19):
     return sp.csr_matrix((np.ones(2 * key.size), (np.r_[lo, hi], np.r_[hi, lo])), shape=(n, n))
 
 
+def test_config1_cora_shape_both_kernels(env):
+    """BASELINE configs[0]: G(n = 2708, m = 5429) (networkx seed 0), W = 50, p = 0.1, f = [1, .5, .25] -- the
+    reference's own CPU case.  Dense and sparse drop-in kernels against the oracle fed the same Philox draws
+    (K to 1e-10: only the dgemm order differs), and the relative Frobenius error against the exact truncated
+    series lands where the reference's does (0.333 dense / 0.341 sparse)."""
+    import time
+
+    import networkx as nx
+
+    from efficient_graph_gp.graph_kernels.fast_grf_kernel_general import fast_general_grf_kernel as k_dense
+    from efficient_graph_gp.graph_kernels.utils import get_normalized_laplacian as lap_dense
+    from efficient_graph_gp_sparse.graph_kernels_sparse.fast_grf_kernel_general import fast_general_grf_kernel as k_sp
+
+    o, c = env["o"], env["c"]
+    adj = nx.to_numpy_array(nx.gnm_random_graph(2708, 5429, seed=0))
+    f = np.array([1.0, 0.5, 0.25])
+    t0 = time.perf_counter()
+    kd = k_dense(adj, f, walks_per_node=50, p_halt=0.1, max_walk_length=3)
+    t1 = time.perf_counter()
+    ks = k_sp(sp.csr_matrix(adj), f, walks_per_node=50, p_halt=0.1, max_walk_length=3)
+    t2 = time.perf_counter()
+    print(f"config 1: dense API {t1 - t0:.3f} s, sparse API {t2 - t1:.3f} s")
+    assert kd.shape == (2708, 2708) and ks.shape == (2708, 2708)
+    lap = lap_dense(adj)
+    exact = o.exact_series(lap, f)
+    # dense API: walk graph = dense Laplacian (isolated nodes keep a self-loop), value / W
+    mats = c.step_matrices(sp.csr_matrix(lap), 50, 0.1, 3, seed=42, scale_mode=1)
+    phi = sum(fl * m for fl, m in zip(f, mats)).toarray()
+    assert np.abs(kd - phi @ phi.T).max() <= 1e-10 * np.abs(kd).max()
+    # sparse API: walk graph = sparse Laplacian (isolated nodes are dead ends), value * (1/W)
+    mats = c.step_matrices(o.normalized_laplacian_sparse(sp.csr_matrix(adj)), 50, 0.1, 3, seed=42, scale_mode=0)
+    phi = sum(fl * m for fl, m in zip(f, mats))
+    assert abs(ks - phi @ phi.T).max() <= 1e-10 * abs(ks).max()
+    err_d, err_s = o.compute_fro(exact, kd), o.compute_fro(exact, ks.toarray())
+    assert 0.25 < err_d < 0.42 and 0.25 < err_s < 0.42, (err_d, err_s)
+    assert np.allclose(kd, kd.T, atol=1e-8) and np.linalg.eigvalsh(kd).min() >= -1e-8
+
+
 def test_config4_shape_rmat_bit_exact(env):
     """BASELINE config 4 in miniature: R-MAT power-law graph (65 k nodes, ~1 M edges, hubs, isolated nodes),
     W = 100, L = 5 -- every M_l bit-identical to the oracle, walk-step counts equal."""
