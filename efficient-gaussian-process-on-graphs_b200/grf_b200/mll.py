@@ -23,12 +23,54 @@ from typing import Optional
 import torch
 
 
+def lanczos_logdet(matmul, probes: torch.Tensor, iterations: int = 1) -> float:
+    """log|A| by stochastic Lanczos quadrature: mean_j ||z_j||^2 e_1^T log(T_j) e_1 with T_j the
+    ``iterations`` x ``iterations`` Lanczos tridiagonal of A started at z_j / ||z_j||.
+
+    The reference sets ``max_lanczos_quadrature_iterations = 1`` (run_scaling_experiment.py:133,
+    graph_bo/utils/gpytorch_config.py:8), for which T_j is the Rayleigh quotient z^T A z / z^T z --
+    one batched matvec.  More iterations run the three-term recurrence with full
+    re-orthogonalisation (small k)."""
+    z = probes.to(torch.float32)
+    norms2 = (z * z).sum(dim=0)
+    q = z / norms2.sqrt()
+    qs = [q]
+    alphas, betas = [], []
+    beta_prev, q_prev = None, None
+    for k in range(iterations):
+        w = matmul(q)
+        if q_prev is not None:
+            w = w - beta_prev * q_prev
+        alpha = (w * q).sum(dim=0)
+        w = w - alpha * q
+        for qq in qs:                                   # re-orthogonalise (k is small)
+            w = w - (w * qq).sum(dim=0) * qq
+        alphas.append(alpha)
+        beta = w.norm(dim=0)
+        if k + 1 < iterations:
+            betas.append(beta)
+            q_prev, beta_prev = q, beta
+            q = w / beta.clamp_min(1e-20)
+            qs.append(q)
+    a = torch.stack(alphas, dim=1).double().cpu()                      # [p, k]
+    p, k = a.shape
+    T = torch.diag_embed(a)
+    if k > 1:
+        b = torch.stack(betas, dim=1).double().cpu()                   # [p, k-1]
+        T = T + torch.diag_embed(b, offset=1) + torch.diag_embed(b, offset=-1)
+    evals, evecs = torch.linalg.eigh(T)
+    quad = (evecs[:, 0, :] ** 2 * torch.log(evals.clamp_min(1e-30))).sum(dim=1)   # e_1^T log(T) e_1
+    return float((norms2.double().cpu() * quad).mean())
+
+
 def neg_mll_backward(kernel, likelihood, x_train: torch.Tensor, y_train: torch.Tensor, num_probes: int = 16,
                      cg_tolerance: float = 1e-2, max_cg_iterations: int = 1000, probes: Optional[torch.Tensor] = None,
-                     generator: Optional[torch.Generator] = None, cg_eps: float = 1e-10):
+                     generator: Optional[torch.Generator] = None, cg_eps: float = 1e-10,
+                     lanczos_iterations: int = 1):
     """Accumulate d(-mll/n)/dtheta into ``.grad`` of the kernel's and the likelihood's parameters.
 
-    Returns a dict with the data-fit term, the CG iteration count and the modulator gradient.
+    Returns a dict with the loss estimate (-mll/n, log-determinant by ``lanczos_iterations`` steps of
+    stochastic Lanczos quadrature on the same probes; 0 skips it), the CG iteration count and the gradients.
     ``probes`` ([n, p]) overrides the Gaussian probe vectors (used by the exactness test)."""
     blocks = kernel.phi_blocks
     dev = blocks.device
@@ -56,8 +98,13 @@ def neg_mll_backward(kernel, likelihood, x_train: torch.Tensor, y_train: torch.T
         dL_df = 0.5 * g_fit - 0.5 * g_tr / p
         dL_ds2 = 0.5 * float((alpha * alpha).sum()) - 0.5 * float((w * probes).sum()) / p
         datafit = 0.5 * float((y * alpha[:, 0]).sum())
+        loss = None
+        if lanczos_iterations > 0:
+            plan = K.plan(p)
+            logdet = lanczos_logdet(lambda v: plan(v.contiguous()) + s2 * v, probes, lanczos_iterations)
+            loss = (datafit + 0.5 * logdet + 0.5 * n * 1.8378770664093453) / n
     # loss = -mll / n  (gpytorch's ExactMarginalLogLikelihood divides by the number of data points)
     f.backward((-dL_df / n).to(f.dtype).to(f.device), retain_graph=True)
     noise.backward(torch.as_tensor([-dL_ds2 / n], dtype=noise.dtype, device=noise.device).reshape(noise.shape))
-    return {"datafit": datafit, "cg_iterations": info["iterations"], "grad_modulator": (-dL_df / n).cpu(),
-            "grad_noise": -dL_ds2 / n}
+    return {"loss": loss, "datafit": datafit, "cg_iterations": info["iterations"],
+            "grad_modulator": (-dL_df / n).cpu(), "grad_noise": -dL_ds2 / n}

@@ -45,7 +45,7 @@ for ep in range(epochs):
     opt.step()
     torch.cuda.synchronize(); times.append(time.perf_counter() - ta)
     if ep % 10 == 0 or ep == epochs - 1:
-        print(f"  epoch {ep:3d}: {1e3*times[-1]:.1f} ms, CG iterations {info['cg_iterations']}, noise {float(lik.noise):.4f}, "
+        print(f"  epoch {ep:3d}: loss {info['loss']:.4f}, {1e3*times[-1]:.1f} ms, CG iterations {info['cg_iterations']}, noise {float(lik.noise):.4f}, "
               f"modulator {model.covar_module.modulator_vector.detach().cpu().numpy().round(3)}")
 print(f"training: {epochs} epochs, median {1e3*np.median(times):.1f} ms/epoch, total {sum(times):.2f} s")
 with torch.no_grad():

@@ -207,6 +207,17 @@ def test_mll_gradient_matches_dense_float64(setup):
     dnoise_draw = 1.0 / (1.0 + np.exp(-raw))
     assert abs(float(lik.raw_noise.grad) - want_s2 * dnoise_draw) <= 2e-3 * abs(want_s2 * dnoise_draw) + 1e-6
     assert abs(out["datafit"] - 0.5 * y.astype(np.float32) @ a) <= 1e-3 * abs(0.5 * y @ a)
+    # loss value: with probes sqrt(n) e_j and enough Lanczos steps the quadrature is exact
+    from grf_b200.mll import lanczos_logdet
+    Kop = kern(torch.tensor(idx).cuda(), torch.tensor(idx).cuda())
+    plan = Kop.plan(n)
+    ld = lanczos_logdet(lambda v: plan(v.contiguous()) + s2 * v, probes.cuda(), iterations=40)
+    sign, want_ld = np.linalg.slogdet(Kh)
+    assert abs(ld - want_ld) <= 2e-3 * abs(want_ld), (ld, want_ld)
+    want_loss = (0.5 * y.astype(np.float32) @ a + 0.5 * want_ld + 0.5 * n * np.log(2 * np.pi)) / n
+    ld1 = lanczos_logdet(lambda v: plan(v.contiguous()) + s2 * v, probes.cuda(), iterations=1)   # the reference's setting
+    assert abs(ld1 - np.sum(np.log(np.diag(Kh)))) <= 1e-3 * abs(want_ld)
+    assert out["loss"] is not None and np.isfinite(out["loss"])
     # with random probes the estimate is unbiased: average of a few draws lands near the exact value
     kern.raw_modulator_vector.grad = None
     lik.raw_noise.grad = None
