@@ -100,8 +100,12 @@ __host__ __device__ constexpr int epl(int tpr) { return tpr >= 16 ? 1 : (tpr >= 
 template <int TPR, int VEC, bool kShared>
 __device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int32_t b, int32_t e,
                                              int2 (&nxt)[epl(TPR)], int32_t next_b, int32_t next_e,
-                                             const float *__restrict__ fs, const float *X, int64_t ldx,
+                                             const float *__restrict__ fs, const float *X, uint32_t ldx,
                                              int32_t col_off, int c0, bool live, int sub) {
+    // X offsets are 32-bit element counts, multiplied by the leading dimension once per entry when it is
+    // staged (not once per lane and gather): the 64-bit col * ldx + c0 arithmetic was 8 of the ~20
+    // instructions per gathered entry (ncu instruction mix: IMAD 19 %, LEA 10 %, SHF 6 %).  The host
+    // falls back to the plain kernel when rows(X) * ldx does not fit in 32 bits.
     // `nxt` holds the row's first round of entries on entry; on exit it holds the first round
     // of the NEXT row of this group ([next_b, next_e)), fetched while the last gathers of this
     // row are in flight -- a two-deep software pipeline across rows (ncu on the one-row-at-a-
@@ -113,13 +117,13 @@ __device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int3
     acc.zero();
     int32_t base = b;
     do {
-        int cl[kEPL];
+        uint32_t cl[kEPL];
         float sv[kEPL];
 #pragma unroll
         for (int q = 0; q < kEPL; ++q) {
             // a padding slot is the all-zero pair: gather row col_off (always valid) with weight 0
             const bool pad = (nxt[q].x | nxt[q].y) == 0;
-            cl[q] = pad ? 0 : (int)((uint32_t)nxt[q].x & kColMask) - col_off;
+            cl[q] = pad ? 0u : (((uint32_t)nxt[q].x & kColMask) - (uint32_t)col_off) * ldx;
             sv[q] = __int_as_float(nxt[q].y) * fs[(uint32_t)nxt[q].x >> kStepShift];
         }
         const int32_t nb = base + TPR * kEPL;
@@ -149,12 +153,12 @@ __device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int3
 #pragma unroll
             for (int m = 0; m < kBatch; ++m) {
                 const int q = (m0 + m) / TPR, j = (m0 + m) % TPR;
-                const int c = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
+                const uint32_t off = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
                 a[m] = TPR == 1 ? sv[q] : __shfl_sync(gmask, sv[q], j, TPR);
                 if (kShared)
-                    x[m].load_shared(X + (int64_t)c * ldx + c0);
+                    x[m].load_shared(X + (off + (uint32_t)c0));
                 else
-                    x[m].load(X + (int64_t)c * ldx + c0);
+                    x[m].load(X + (off + (uint32_t)c0));
             }
 #pragma unroll
             for (int m = 0; m < kBatch; ++m) acc.fma(a[m], x[m]);
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
             const bool live = mine && c0 < t;
             const bool last_tile = tile + 1 == n_tiles;
             const Vec<VEC> acc = spmm_row<TPR, VEC, false>(ent2, b, e, nxt, last_tile ? nb : b, last_tile ? ne : e,
-                                                           fs, X, ldx, 0, c0 < t ? c0 : 0, live, sub);
+                                                           fs, X, (uint32_t)ldx, 0, c0 < t ? c0 : 0, live, sub);
             if (live && c0 < t_store) acc.store_cols(Y + orow * ldy + c0, t_store - c0, vec_store != 0);
         }
         b = nb;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__re
 // L1 wavefronts per entry of a global gather, no tag lookups, no L2 round trips.  A
 // chunk whose window does not fit (long-range edges) takes the global-gather path.
 template <int TPR>
-__global__ void __launch_bounds__(1024, 1) spmm_tiled_kernel(const int32_t *__restrict__ ptr,
+__global__ void __launch_bounds__(512, 1) spmm_tiled_kernel(const int32_t *__restrict__ ptr,
                                                              const GrfEntry *__restrict__ ent,
                                                              const float *__restrict__ f, int32_t L,
                                                              int64_t n_rows, int32_t chunk_rows,
@@ -344,9 +348,9 @@ __global__ void __launch_bounds__(1024, 1) spmm_tiled_kernel(const int32_t *__re
                 const bool live = row < r1 && col_live;
                 Vec<4> acc;
                 if (tiled)
-                    acc = spmm_row<TPR, 4, true>(ent2, b, e, nxt, nb, ne, fs, tile, ldt, cmin, c0, live, sub);
+                    acc = spmm_row<TPR, 4, true>(ent2, b, e, nxt, nb, ne, fs, tile, (uint32_t)ldt, cmin, c0, live, sub);
                 else
-                    acc = spmm_row<TPR, 4, false>(ent2, b, e, nxt, nb, ne, fs, X, ldx, 0, c0, live, sub);
+                    acc = spmm_row<TPR, 4, false>(ent2, b, e, nxt, nb, ne, fs, X, (uint32_t)ldx, 0, c0, live, sub);
                 if (live) acc.store(Y + row * ldy + c0);
                 b = nb;
                 e = ne;
@@ -653,7 +657,7 @@ static int try_launch_tiled(const int32_t *ptr, const GrfEntry *ent, const float
     case T: {                                                                                                 \
         auto kern = spmm_tiled_kernel<T>;                                                                     \
         GRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kern<<<grid, 1024, smem, st>>>(ptr, ent, f, L, n_rows, (int32_t)chunk, (const int2 *)win,             \
+        kern<<<grid, 512, smem, st>>>(ptr, ent, f, L, n_rows, (int32_t)chunk, (const int2 *)win,             \
                                        (int32_t)cap_rows, X, ldx, Y, ldy, t);                                 \
     } break
     switch (tpr) {
@@ -713,7 +717,7 @@ using namespace grf;
 static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float *f, int32_t L,
                             const int32_t *row_ids, int64_t n_tasks, int64_t row_lo, int64_t n_rows,
                             const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t_valid,
-                            bool vec_ok, bool out_by_row, int64_t avg_row_len, cudaStream_t st) {
+                            bool vec_ok, bool out_by_row, int64_t avg_row_len, int64_t x_rows, cudaStream_t st) {
     // vec_ok: X rows are 16-byte aligned and padded to a multiple of 4 columns -> compute the padded
     // column count with float4 gathers; only the t_valid real columns are stored to Y
     const bool split = lr && lr->n_long > 0 && (!row_ids || out_by_row);
@@ -721,6 +725,9 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
         GRF_REQUIRE(lr->rows && lr->chunk_ptr && lr->chunk_bounds && lr->partial && lr->ld >= t_valid,
                     "grf_phi_matvec: incomplete long-row metadata");
     }
+    if (x_rows * ldx + 4 >= (1ll << 32))
+        return fail(GRF_ERR_UNSUPPORTED, "grf_phi_matvec: right-hand side of %lld x %lld floats exceeds the 32-bit "
+                    "element offsets of the gather kernels; split the columns", (long long)x_rows, (long long)ldx);
     if (t_valid <= 4 && avg_row_len > 64) {
         // CSR-vector path for long rows (a row subset of a W = 1000 Phi): 32 lanes per row.  Short rows
         // (config 2: 28..64 entries) are faster with one row per lane group in the kernel below.
@@ -875,10 +882,10 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                     rc = phi->n_tcols == 0
                              ? GRF_OK
                              : launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, phi->tcols, phi->n_tcols, 0,
-                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, avg_len, st);
+                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, avg_len, phi->n_rows, st);
                 } else {
                     rc = launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0, phi->n_cols,
-                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, avg_len, st);
+                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, avg_len, phi->n_rows, st);
                 }
                 if (rc != GRF_OK) return rc;
             }
@@ -897,7 +904,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         }
         if (!tiled) {
             const int rc = launch_spmm_pass(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
-                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, avg_len, st);
+                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, avg_len, phi->n_cols, st);
             if (rc != GRF_OK) return rc;
         }
     }

@@ -15,6 +15,7 @@ torch.manual_seed(42)
 f = torch.randn(5).cuda()
 v = torch.randn(phi.n_rows, t, device="cuda")
 out = torch.empty_like(v)
+phi.use_tiles = bool(int(os.environ.get('GRF_TILES', '0')))
 plan = phi.plan(f, t)          # merged Phi_f on the union pattern (default)
 print('nnz per-length', phi.nnz, 'nnz union', phi.nnz_union)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
