@@ -20,7 +20,21 @@
 
 #include "grf_common.cuh"
 
+// Tuned on config 2 (t = 16, merged Phi_f; CUDA events, L2 flushed): (min CTAs/SM, gathers in flight per lane)
+//   (5,4) 74.5 us   (4,8) 62.5   (4,4) 56.0   (3,4) 55.8   (3,8) 56.1   (2,16) 51.9  <- fewer, fatter warps win
+#ifndef GRF_SPMM_MINBLOCKS
+#define GRF_SPMM_MINBLOCKS 2  // resident CTAs of 256 threads per SM the register budget allows (<= 128 registers)
+#endif
+#ifndef GRF_SPMM_BATCH
+#define GRF_SPMM_BATCH 16     // independent gathers in flight per lane
+#endif
+
 namespace grf {
+
+// one or two lanes per row (t <= 8) keep little state per row: there more resident warps win
+// (t = 1: 33.8 us at 3 CTAs/SM and 8 gathers in flight against 66 us at 2 CTAs/SM)
+__host__ __device__ constexpr int spmm_min_blocks(int tpr) { return tpr >= 4 ? GRF_SPMM_MINBLOCKS : 3; }
+__host__ __device__ constexpr int spmm_batch(int tpr) { return tpr >= 4 ? GRF_SPMM_BATCH : 8; }
 
 template <int VEC>
 struct Vec;
@@ -145,7 +159,7 @@ __device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int3
         // entry nvcc re-used one register quad and serialised load -> FMA -> load (ncu: one
         // long-scoreboard stall per entry, 16 dependent L2 round trips per round).
         constexpr int kSlots = TPR * kEPL;
-        constexpr int kBatch = kSlots < 8 ? kSlots : 8;
+        constexpr int kBatch = kSlots < spmm_batch(TPR) ? kSlots : spmm_batch(TPR);
 #pragma unroll
         for (int m0 = 0; m0 < kSlots; m0 += kBatch) {
             Vec<VEC> x[kBatch];
@@ -180,7 +194,7 @@ __device__ __forceinline__ void load_first_round(const int2 *__restrict__ ent2, 
 }
 
 template <int TPR, int VEC>
-__global__ void __launch_bounds__(256, 3) spmm_blocks_kernel(const int32_t *__restrict__ ptr,
+__global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(const int32_t *__restrict__ ptr,
                                                           const GrfEntry *__restrict__ ent,
                                                           const float *__restrict__ f, int32_t L,
                                                           const int32_t *__restrict__ row_ids, int64_t n_tasks,
@@ -492,6 +506,20 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
     }
 }
 
+// vfull[r, 0:t] = v[r, 0:t] for all rows (staging a V whose rows are not 16-byte friendly; a 2-D
+// DMA copy with 4*t-byte rows is far slower than this)
+__global__ void __launch_bounds__(256) pad_copy_kernel(const float *__restrict__ v, int64_t ldv,
+                                                       float *__restrict__ vfull, int64_t ldu, int64_t n_rows,
+                                                       int32_t t) {
+    const int64_t total = n_rows * t;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = g / t;
+        const int c = (int)(g - r * t);
+        vfull[r * ldu + c] = __ldg(v + r * ldv + c);
+    }
+}
+
 // same without atomics, for index sets without repeated ids (rows outside x2 keep their zeros)
 __global__ void __launch_bounds__(256) scatter_rows_unique_kernel(const int32_t *__restrict__ x2, int64_t n2,
                                                                   int64_t row_lo, int64_t n_rows,
@@ -677,7 +705,7 @@ static int try_launch_tiled(const int32_t *ptr, const GrfEntry *ent, const float
 static int spmm_grid(int64_t n_tasks, int tpr) {
     const int64_t threads = n_tasks * tpr;
     int64_t g = (threads + 255) / 256;
-    const int64_t cap = (int64_t)kSmCount * 3;  // 3 resident CTAs of 256 threads per SM at 80 registers
+    const int64_t cap = (int64_t)kSmCount * spmm_min_blocks(tpr);  // the resident CTAs of 256 threads per SM
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -850,11 +878,12 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             }
             src = vfull;
             lds = ldu;
-        } else if (vfull && phi->n_rows > 0 && (ldv % 4 != 0 || !aligned16(v)) && ldu % 4 == 0) {
+        } else if (vfull && phi->n_rows > 0 && t > 2 && (ldv % 4 != 0 || !aligned16(v)) && ldu % 4 == 0) {
             // V is not laid out for 16-byte gathers (e.g. t = 17): stage it in the padded buffer
-            GRF_CUDA_OK(cudaMemcpy2DAsync(vfull, (size_t)ldu * sizeof(float), v, (size_t)ldv * sizeof(float),
-                                          (size_t)t * sizeof(float), (size_t)phi->n_rows,
-                                          cudaMemcpyDeviceToDevice, st));
+            int64_t g = (phi->n_rows * t + 255) / 256;
+            if (g > (int64_t)kSmCount * 16) g = (int64_t)kSmCount * 16;
+            pad_copy_kernel<<<(int)g, 256, 0, st>>>(v, ldv, vfull, ldu, phi->n_rows, t);
+            GRF_CUDA_OK(cudaGetLastError());
             src = vfull;
             lds = ldu;
         }
@@ -866,7 +895,8 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                                           (size_t)phi->n_cols, st));
         } else if (phi->n_cols > 0) {
             const int32_t t4 = (t + 3) & ~3;
-            const bool vec_ok = (lds % 4 == 0) && (ldu % 4 == 0) && lds >= t4 && ldu >= t4 && aligned16(src) &&
+            // one or two columns: scalar lanes beat float4 gathers that are 3/4 padding
+            const bool vec_ok = t > 2 && (lds % 4 == 0) && (ldu % 4 == 0) && lds >= t4 && ldu >= t4 && aligned16(src) &&
                                 aligned16(u);
             int tiled = 0;
             if (vec_ok && t % 4 == 0 && !(tile_mode & 1)) {
@@ -895,7 +925,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         GRF_REQUIRE(out && ldo >= t, "grf_phi_matvec: out missing or ldo < t");
         GRF_REQUIRE(phi->blk_ptr, "grf_phi_matvec: Phi blocks missing");
         const int32_t t4 = (t + 3) & ~3;
-        const bool vec_ok = (ldu % 4 == 0) && ldu >= t4 && aligned16(u);   // gathers come from U
+        const bool vec_ok = t > 2 && (ldu % 4 == 0) && ldu >= t4 && aligned16(u);   // gathers come from U
         int tiled = 0;
         if (vec_ok && t % 4 == 0 && (ldo % 4 == 0) && aligned16(out) && !x1 && !(tile_mode & 1)) {
             tiled = try_launch_tiled(phi->blk_ptr, phi->entries, f, L, phi->n_rows, phi->win, phi->win_max_width, u,

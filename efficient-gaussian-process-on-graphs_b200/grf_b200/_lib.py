@@ -13,7 +13,7 @@ PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 INCLUDE = os.path.join(REPO_ROOT, "include")
-SO_PATH = os.path.join(_HERE, "libgrf_b200.so")
+SO_PATH = os.environ.get("GRF_B200_SO") or os.path.join(_HERE, "libgrf_b200.so")   # override: tuning experiments
 
 GRF_OK, GRF_ERR_INVALID, GRF_ERR_CUDA, GRF_ERR_UNSUPPORTED = 0, -1, -2, -3
 DRAW_PHILOX, DRAW_REPLAY = 0, 1
