@@ -28,6 +28,10 @@
 #ifndef GRF_SPMM_BATCH
 #define GRF_SPMM_BATCH 16     // independent gathers in flight per lane
 #endif
+#ifndef GRF_SPMM_STATIC_PCT
+#define GRF_SPMM_STATIC_PCT 50  // share of a pass's row groups assigned by fixed stride; the rest goes by ticket
+// (R-MAT 2^20 nodes, per-length matvec: fixed stride 2.92 ms, 90 % 2.73, 75 % 2.60, 50 % 2.48, 0 % 2.49; config 2: 52.3 us for all)
+#endif
 
 namespace grf {
 
@@ -203,7 +207,11 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
                                                           float *__restrict__ Y, int64_t ldy, int32_t t,
                                                           int32_t t_store, int32_t vec_store, int32_t long_thresh,
                                                           const int2 *__restrict__ chunk_bounds,
-                                                          int32_t out_by_row) {
+                                                          int32_t out_by_row, int32_t *__restrict__ sched) {
+    // sched != NULL: {ticket, finished warps}, both zero at launch and zero again at exit.  Every warp
+    // runs ~11 gather rounds of ~1.6 us at config 2, so with a fixed stride the SMs finish several
+    // rounds apart (ncu: L1 busy 77 % of its active cycles but 58 % of the elapsed ones); the last
+    // rows are therefore handed out by an atomic ticket, fetched one iteration ahead.
     // out_by_row: row_ids lists the non-empty rows and task k writes Y[row_ids[k]] (Phi^T of a row
     // shard touches only a fraction of the N columns); otherwise task k writes Y[k].
     // t = columns computed (a multiple of VEC; the operands are padded to it), t_store <= t = columns
@@ -232,7 +240,6 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
     const int n_tiles = (t + TPR * VEC - 1) / (TPR * VEC);
     // warp-uniform loop: the warp takes 32/TPR consecutive tasks per iteration; the row bounds of
     // the next iteration are fetched one iteration ahead, its first entries by spmm_row
-    const int64_t kstride = warp_stride * kGroupsPerWarp;
     auto bounds = [&](int64_t k, int32_t &b, int32_t &e, bool &mine, int64_t &orow) {
         b = e = 0;
         orow = k;
@@ -258,17 +265,52 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
             }
         }
     };
-    int64_t kb = warp0 * kGroupsPerWarp;
-    if (kb >= n_tasks) return;
+    // iteration `it` = the 32/TPR consecutive tasks [it * G, (it + 1) * G) of one warp
+    const int lane = threadIdx.x & 31;
+    const int32_t n_warps = (int32_t)warp_stride;
+    const int32_t n_iters = (int32_t)((n_tasks + kGroupsPerWarp - 1) / kGroupsPerWarp);
+    // iterations [0, n_static) go by stride (neighbouring rows stay on one SM), the rest by ticket
+    int32_t n_static = 0x7fffffff - n_warps;
+    int32_t ticket_base = 0;
+    if (sched) {
+        n_static = (int32_t)((int64_t)n_iters * GRF_SPMM_STATIC_PCT / 100) / n_warps * n_warps;
+        ticket_base = n_static > n_warps ? n_static : n_warps;
+    }
+    auto finish = [&]() {
+        if (sched && lane == 0) {
+            if (atomicAdd(sched + 1, 1) == n_warps - 1) {  // every other warp has drawn its last ticket
+                sched[0] = 0;
+                sched[1] = 0;
+            }
+        }
+    };
+    int32_t it = (int32_t)warp0;
+    if (it >= n_iters) {
+        finish();
+        return;
+    }
+    int32_t itn;
+    if (it + n_warps < n_static) {
+        itn = it + n_warps;
+    } else if (!sched) {
+        itn = n_iters;
+    } else {
+        int32_t tk = 0;
+        if (lane == 0) tk = ticket_base + atomicAdd(sched, 1);
+        itn = __shfl_sync(0xffffffffu, tk, 0);
+    }
     int32_t b, e, nb, ne;
     bool mine, nmine;
     int64_t orow, norow;
-    bounds(kb + g_in_warp, b, e, mine, orow);
+    bounds((int64_t)it * kGroupsPerWarp + g_in_warp, b, e, mine, orow);
     int2 nxt[epl(TPR)];
     load_first_round<TPR>(ent2, b, e, sub, nxt);
-    for (; kb < n_tasks; kb += kstride) {
-        const int64_t k = kb + g_in_warp;
-        bounds(k + kstride, nb, ne, nmine, norow);
+    while (it < n_iters) {
+        // the iteration after next: known by stride, or a ticket whose latency this iteration hides
+        const bool draw = sched && itn + n_warps >= n_static;
+        int32_t tk = 0;
+        if (draw && lane == 0) tk = ticket_base + atomicAdd(sched, 1);
+        bounds((int64_t)itn * kGroupsPerWarp + g_in_warp, nb, ne, nmine, norow);
         for (int tile = 0; tile < n_tiles; ++tile) {
             // lanes whose columns fall outside t (t not a multiple of TPR*VEC) still help with the
             // entry loads and shuffles; they just do not gather or store
@@ -283,7 +325,10 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
         e = ne;
         mine = nmine;
         orow = norow;
+        it = itn;
+        itn = draw ? __shfl_sync(0xffffffffu, tk, 0) : (sched || itn + n_warps < n_iters ? itn + n_warps : n_iters);
     }
+    finish();
 }
 
 // Tiled variant for banded Phi (lattices, rings, any ordering with locality): a CTA owns
@@ -745,7 +790,8 @@ using namespace grf;
 static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float *f, int32_t L,
                             const int32_t *row_ids, int64_t n_tasks, int64_t row_lo, int64_t n_rows,
                             const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t_valid,
-                            bool vec_ok, bool out_by_row, int64_t avg_row_len, int64_t x_rows, cudaStream_t st) {
+                            bool vec_ok, bool out_by_row, int64_t avg_row_len, int64_t x_rows, int32_t *sched,
+                            cudaStream_t st) {
     // vec_ok: X rows are 16-byte aligned and padded to a multiple of 4 columns -> compute the padded
     // column count with float4 gathers; only the t_valid real columns are stored to Y
     const bool split = lr && lr->n_long > 0 && (!row_ids || out_by_row);
@@ -805,7 +851,7 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
     GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
                        <<<grid, 256, 0, st>>>(ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy, t,
                                               ldy >= t ? t : t_valid, vec_store, split ? lr->threshold : 0, nullptr,
-                                              out_by_row ? 1 : 0));
+                                              out_by_row ? 1 : 0, sched));
     GRF_CUDA_OK(cudaGetLastError());
     if (split) {
         GRF_REQUIRE(lr->ld >= t, "grf_phi_matvec: long-row partial buffer narrower than the padded column count");
@@ -814,7 +860,7 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
         GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
                            <<<gridc, 256, 0, st>>>(ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
                                                    lr->partial, lr->ld, t, t, pvec, 0,
-                                                   (const int2 *)lr->chunk_bounds, 0));
+                                                   (const int2 *)lr->chunk_bounds, 0, sched));
         GRF_CUDA_OK(cudaGetLastError());
         int64_t g = ((int64_t)lr->n_long * t + 255) / 256;
         if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
@@ -912,10 +958,10 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                     rc = phi->n_tcols == 0
                              ? GRF_OK
                              : launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, phi->tcols, phi->n_tcols, 0,
-                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, avg_len, phi->n_rows, st);
+                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, avg_len, phi->n_rows, phi->sched, st);
                 } else {
                     rc = launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0, phi->n_cols,
-                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, avg_len, phi->n_rows, st);
+                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, avg_len, phi->n_rows, phi->sched, st);
                 }
                 if (rc != GRF_OK) return rc;
             }
@@ -934,7 +980,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         }
         if (!tiled) {
             const int rc = launch_spmm_pass(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
-                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, avg_len, phi->n_cols, st);
+                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, avg_len, phi->n_cols, phi->sched, st);
             if (rc != GRF_OK) return rc;
         }
     }

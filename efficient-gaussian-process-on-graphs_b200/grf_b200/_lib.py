@@ -51,7 +51,7 @@ class GrfPhi(Structure):
                 ("blk_ptr", c_void_p), ("entries", c_void_p), ("tblk_ptr", c_void_p), ("tentries", c_void_p),
                 ("win", c_void_p), ("twin", c_void_p), ("win_max_width", c_int32), ("twin_max_width", c_int32),
                 ("long_fwd", POINTER(GrfLongRows)), ("long_t", POINTER(GrfLongRows)),
-                ("tcols", c_void_p), ("n_tcols", c_int64), ("nnz", c_int64)]
+                ("tcols", c_void_p), ("n_tcols", c_int64), ("nnz", c_int64), ("sched", c_void_p)]
 
 
 def nvcc_command(out_path: str = SO_PATH):
@@ -136,7 +136,7 @@ def lib():
     L.grf_block_windows.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.grf_phi_fgrad.restype = i32
     L.grf_phi_fgrad.argtypes = [POINTER(GrfPhi), vp, i64, vp, i64, vp, i64, i32, vp, vp]
-    if L.grf_abi_version() != 1:
+    if L.grf_abi_version() != 2:
         raise RuntimeError("grf_b200: ABI version mismatch between _lib.py and libgrf_b200.so")
     _lib = L
     return _lib

@@ -15,6 +15,7 @@ Reference call stack this replaces:
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -363,6 +364,10 @@ class PhiBlocks:
         # shared-memory-tiled matvec for banded Phi: correct and tested, but measured equal to the
         # global-gather kernel at config 2 (both are bound by L1 wavefronts per entry), so opt-in
         self.use_tiles = False
+        # hand the last rows of every matvec pass out by ticket (GrfPhi.sched); env GRF_B200_DYNAMIC=0
+        # keeps the fixed stride (for A/B timing)
+        self.dynamic_rows = os.environ.get("GRF_B200_DYNAMIC", "1") != "0"
+        self._sched = None
         self.visits = visits
         self._union = None
         self._tcols = None      # non-empty columns of this shard (int32) when that is a small fraction of N
@@ -526,7 +531,15 @@ class PhiBlocks:
                       ctypes.pointer(fwd) if fwd is not None else None,
                       ctypes.pointer(tr) if tr is not None else None,
                       None if self._tcols is None else self._tcols.data_ptr(),
-                      0 if self._tcols is None else self._tcols.numel(), self.nnz)
+                      0 if self._tcols is None else self._tcols.numel(), self.nnz, self._sched_ptr())
+
+    def _sched_ptr(self):
+        # ticket scratch of the matvec kernels (GrfPhi.sched): zero between launches
+        if not self.dynamic_rows:
+            return None
+        if getattr(self, "_sched", None) is None:
+            self._sched = torch.zeros(4, dtype=torch.int32, device=self.device)
+        return self._sched.data_ptr()
 
     @staticmethod
     def _ids(x, dev):
@@ -810,6 +823,7 @@ class MatvecPlan:
             self.phi = phi
             self.f = phi._f(f).clone()
         self.phi.use_tiles = phi.use_tiles
+        self.phi.dynamic_rows = phi.dynamic_rows
         self.phi.build_windows()
         self.phi.build_long_rows()
         self.x1, self.x2 = phi._ids(x1, dev), phi._ids(x2, dev)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GRF_B200_ABI_VERSION 1
+#define GRF_B200_ABI_VERSION 2
 
 enum {
     GRF_OK = 0,
@@ -130,6 +130,11 @@ typedef struct {
     const int32_t *tcols;
     int64_t n_tcols;
     int64_t nnz; /* stored entries (0 = unknown); picks the lanes-per-row of the few-column kernels */
+    /* optional: two device ints, zero when handed over and private to this GrfPhi (the kernels leave
+     * them zero again): the second half of a pass's rows is then handed out warp by warp through a
+     * ticket counter instead of by a fixed stride, which evens out the finish times of the SMs.
+     * Two products of the SAME GrfPhi must then not run concurrently (same rule as long_*->partial). */
+    int32_t *sched;
 } GrfPhi;
 
 int grf_abi_version(void);
