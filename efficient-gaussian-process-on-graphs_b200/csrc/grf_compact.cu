@@ -393,6 +393,31 @@ __global__ void __launch_bounds__(512) transpose_sort_long_kernel(const int32_t 
     }
 }
 
+// Row statistics of one side of the Phi blocks in one pass over the row pointers:
+// census[0] = rows longer than `threshold`, census[1] = chunks of `threshold` entries those rows
+// split into, census[2] = non-empty rows.  Decides (without a host round trip per quantity)
+// whether the matvec needs the long-row split and whether a non-empty-column list pays off.
+__global__ void __launch_bounds__(256) row_census_kernel(const int32_t *__restrict__ ptr, int64_t n_rows, int32_t L,
+                                                         int32_t threshold, int32_t *__restrict__ census) {
+    int32_t n_long = 0, n_chunks = 0, n_full = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t len = __ldg(ptr + (r + 1) * L) - __ldg(ptr + r * L);
+        n_full += len > 0;
+        if (len > threshold) {
+            n_long += 1;
+            n_chunks += (len + threshold - 1) / threshold;
+        }
+    }
+    n_long = __reduce_add_sync(0xffffffffu, n_long);
+    n_chunks = __reduce_add_sync(0xffffffffu, n_chunks);
+    n_full = __reduce_add_sync(0xffffffffu, n_full);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_long) atomicAdd(census + 0, n_long);
+        if (n_chunks) atomicAdd(census + 1, n_chunks);
+        if (n_full) atomicAdd(census + 2, n_full);
+    }
+}
+
 }  // namespace grf
 
 // ---------------------------------------------------------------------------
@@ -479,6 +504,20 @@ extern "C" int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n
     if (g > (int64_t)kSmCount * 32) g = (int64_t)kSmCount * 32;
     count_from_steps_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(offsets_step_major, n_rows, n_steps, row_cnt);
     return check_cuda(cudaGetLastError(), "count_from_steps_kernel launch");
+}
+
+extern "C" int grf_row_census(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t threshold,
+                              int32_t *census, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && threshold >= 1, "grf_row_census: bad shape");
+    GRF_REQUIRE(census, "grf_row_census: null census");
+    cudaStream_t st = (cudaStream_t)stream;
+    GRF_CUDA_OK(cudaMemsetAsync(census, 0, 3 * sizeof(int32_t), st));
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(blk_ptr, "grf_row_census: null blk_ptr");
+    int64_t g = (n_rows + 255) / 256;
+    if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
+    row_census_kernel<<<(int)g, 256, 0, st>>>(blk_ptr, n_rows, n_steps, threshold, census);
+    return check_cuda(cudaGetLastError(), "row_census_kernel launch");
 }
 
 extern "C" int grf_blocks_from_steps(const int64_t *offsets_step_major, const int32_t *col, const double *val,

@@ -488,17 +488,29 @@ class PhiBlocks:
                     bounds=bounds, n_long=int(rows.numel()), n_chunks=n_chunks)
 
     def build_long_rows(self) -> "PhiBlocks":
+        """One-off matvec preparation: which rows / columns need the long-row split, and the list of
+        non-empty columns when this shard touches few of them.  One census kernel per side and a
+        single host read; the chunk tables are only built when a long row exists."""
         if self._long is None:
             self.build_transpose()
-            self._long = [self._long_rows_of(self.blk_ptr, self.n_rows),
-                          self._long_rows_of(self.tblk_ptr, self.n_cols)]
+            self._long = [None, None]
+            if self.nnz == 0:
+                return self
+            lib, L = _lib.lib(), self.n_steps
+            census = torch.empty(6, dtype=torch.int32, device=self.device)
+            check(lib.grf_row_census(_ptr(self.blk_ptr), self.n_rows, L, LONG_ROW_THRESHOLD, _ptr(census[0:3]),
+                                     _stream(self.device)))
+            check(lib.grf_row_census(_ptr(self.tblk_ptr), self.n_cols, L, LONG_ROW_THRESHOLD, _ptr(census[3:6]),
+                                     _stream(self.device)))
+            long_f, _, _, long_t, _, cols_used = census.tolist()
+            if long_f:
+                self._long[0] = self._long_rows_of(self.blk_ptr, self.n_rows)
+            if long_t:
+                self._long[1] = self._long_rows_of(self.tblk_ptr, self.n_cols)
             # columns this (row) shard touches: worth a list when most of the N columns are empty
-            if self.n_cols > 0 and self.nnz > 0:
-                L = self.n_steps
+            if cols_used < 0.75 * self.n_cols:
                 lens = self.tblk_ptr[L:self.n_cols * L + 1:L] - self.tblk_ptr[0:self.n_cols * L:L]
-                cols = torch.nonzero(lens > 0).flatten()
-                if cols.numel() < 0.75 * self.n_cols:
-                    self._tcols = cols.to(torch.int32).contiguous()
+                self._tcols = torch.nonzero(lens > 0).flatten().to(torch.int32).contiguous()
         return self
 
     def _long_structs(self, ld: int):

@@ -191,6 +191,13 @@ int grf_blocks_from_steps(const int64_t *offsets_step_major, const int32_t *col,
 int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps, int32_t *row_cnt,
                          void *stream);
 
+/* Row statistics of Phi or Phi^T blocks in one pass over the row pointers (device int32 census[3]):
+ * {rows with more than `threshold` entries, chunks of `threshold` entries they split into,
+ * non-empty rows}.  Sizes GrfLongRows and decides whether GrfPhi.tcols pays off; part of the
+ * one-off preparation that replaces sparse_lo.py:23-25. */
+int grf_row_census(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t threshold, int32_t *census,
+                   void *stream);
+
 /* Replaces sparse_lo.py:23-25 (.t().to_sparse_csr(), redone on every forward in
  * the reference): build Phi^T blocks once.  count -> grf_scan_counts -> fill. */
 int grf_transpose_count(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
