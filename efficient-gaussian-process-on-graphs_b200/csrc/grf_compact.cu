@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *cn
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) scan_of_tile_sums(int64_t *tile_sums, int64_t n_tiles) {
+// also leaves the grand total in *total (the caller sizes its output from it with one 8-byte read)
+__global__ void __launch_bounds__(1024) scan_of_tile_sums(int64_t *tile_sums, int64_t n_tiles, int64_t *total) {
     __shared__ int64_t sh[32];
     __shared__ int64_t carry_sh;
     if (threadIdx.x == 0) carry_sh = 0;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(1024) scan_of_tile_sums(int64_t *tile_sums, in
         if (threadIdx.x == 0) carry_sh = carry + all;
         __syncthreads();
     }
+    if (threadIdx.x == 0) *total = carry_sh;
 }
 
 template <typename OutT>
@@ -436,7 +438,7 @@ static inline int grid_for_warps(int64_t n_rows, int threads) {
 
 extern "C" int64_t grf_scan_workspace_bytes(int64_t n_items) {
     const int64_t tiles = (n_items + kScanTile - 1) / kScanTile;
-    return (tiles + 1) * (int64_t)sizeof(int64_t);
+    return (tiles + 2) * (int64_t)sizeof(int64_t);  // [grand total][tile sums]
 }
 
 extern "C" int grf_scan_counts(const int32_t *row_cnt, int64_t n_rows, int32_t n_steps, int32_t order, void *offsets,
@@ -448,14 +450,16 @@ extern "C" int grf_scan_counts(const int32_t *row_cnt, int64_t n_rows, int32_t n
     const int64_t n = n_rows * n_steps;
     if (n == 0) {
         GRF_CUDA_OK(cudaMemsetAsync(offsets, 0, out_is_i64 ? 8 : 4, st));
+        GRF_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int64_t), st));
         return GRF_OK;
     }
     GRF_REQUIRE(row_cnt, "grf_scan_counts: null counts");
     const int64_t tiles = (n + kScanTile - 1) / kScanTile;
     GRF_REQUIRE(tiles < (1ll << 31), "grf_scan_counts: too many items");
-    int64_t *tile_sums = (int64_t *)workspace;
+    int64_t *total = (int64_t *)workspace;
+    int64_t *tile_sums = total + 1;
     scan_tile_sums<<<(int)tiles, kScanThreads, 0, st>>>(row_cnt, n, n_rows, n_steps, order, tile_sums);
-    scan_of_tile_sums<<<1, 1024, 0, st>>>(tile_sums, tiles);
+    scan_of_tile_sums<<<1, 1024, 0, st>>>(tile_sums, tiles, total);
     if (out_is_i64)
         scan_apply<int64_t><<<(int)tiles, kScanThreads, 0, st>>>(row_cnt, n, n_rows, n_steps, order, tile_sums,
                                                                  (int64_t *)offsets);
@@ -531,17 +535,46 @@ extern "C" int grf_blocks_from_steps(const int64_t *offsets_step_major, const in
     return check_cuda(cudaGetLastError(), "blocks_from_steps_kernel launch");
 }
 
-extern "C" int grf_transpose_count(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                                   int32_t n_steps, int32_t *tcnt, void *stream) {
-    GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_count: bad shape");
-    if (n_cols == 0) return GRF_OK;
-    GRF_REQUIRE(tcnt, "grf_transpose_count: null buffer");
+static int64_t transpose_cursor_bytes(int64_t n_cols, int32_t n_steps) {
+    return ((n_cols * n_steps + 2) * (int64_t)sizeof(int32_t) + 15) / 16 * 16;
+}
+
+extern "C" int64_t grf_transpose_workspace_bytes(int64_t n_cols, int32_t n_steps) {
+    // [segment counts, later the fill cursor / sort work lists: n_cols*L + 2 ints][scan workspace][census: 8 ints]
+    return transpose_cursor_bytes(n_cols, n_steps) + grf_scan_workspace_bytes(n_cols * n_steps) + 32;
+}
+
+extern "C" int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
+                                     int32_t n_steps, int32_t *tblk_ptr, void *workspace, int32_t census_threshold,
+                                     int32_t *census_host, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_offsets: bad shape");
+    GRF_REQUIRE(tblk_ptr && workspace, "grf_transpose_offsets: null buffer");
+    GRF_REQUIRE(!census_host || census_threshold >= 1, "grf_transpose_offsets: bad census threshold");
     cudaStream_t st = (cudaStream_t)stream;
-    GRF_CUDA_OK(cudaMemsetAsync(tcnt, 0, (size_t)n_cols * n_steps * sizeof(int32_t), st));
-    if (n_rows == 0) return GRF_OK;
-    GRF_REQUIRE(blk_ptr, "grf_transpose_count: null blk_ptr");
-    transpose_count_kernel<<<grid_for_warps(n_rows, 256), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps, tcnt);
-    return check_cuda(cudaGetLastError(), "transpose_count_kernel launch");
+    int32_t *tcnt = (int32_t *)workspace;
+    char *scan_ws = (char *)workspace + transpose_cursor_bytes(n_cols, n_steps);
+    int32_t *census = (int32_t *)(scan_ws + grf_scan_workspace_bytes(n_cols * n_steps));
+    if (n_cols > 0) {
+        GRF_CUDA_OK(cudaMemsetAsync(tcnt, 0, (size_t)n_cols * n_steps * sizeof(int32_t), st));
+        if (n_rows > 0) {
+            GRF_REQUIRE(blk_ptr, "grf_transpose_offsets: null blk_ptr");
+            transpose_count_kernel<<<grid_for_warps(n_rows, 256), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps,
+                                                                                 tcnt);
+            GRF_CUDA_OK(cudaGetLastError());
+        }
+    }
+    int rc = grf_scan_counts(tcnt, n_cols, n_steps, GRF_ORDER_ROW_MAJOR, tblk_ptr, 0, scan_ws, stream);
+    if (rc != GRF_OK) return rc;
+    if (census_host) {
+        // row statistics of both sides while the fill / sort kernels that follow keep the GPU busy: the
+        // host reads them from pinned memory after an event recorded behind this call
+        rc = grf_row_census(blk_ptr, n_rows, n_steps, census_threshold, census, stream);
+        if (rc != GRF_OK) return rc;
+        rc = grf_row_census(tblk_ptr, n_cols, n_steps, census_threshold, census + 3, stream);
+        if (rc != GRF_OK) return rc;
+        GRF_CUDA_OK(cudaMemcpyAsync(census_host, census, 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    return GRF_OK;
 }
 
 extern "C" int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,

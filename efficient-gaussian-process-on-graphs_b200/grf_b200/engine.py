@@ -46,7 +46,13 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(device: torch.device):
+    """cudaStream_t of torch's current stream on ``device`` (every C call is asynchronous on it)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(device.index))   # same handle, without building a Stream object
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -168,14 +174,17 @@ class Staging:
     visits: torch.Tensor      # int64 [1] walk-steps executed
 
 
-def scan_counts(row_cnt: torch.Tensor, n_rows: int, n_steps: int, order: int, i64: bool) -> torch.Tensor:
+def scan_counts(row_cnt: torch.Tensor, n_rows: int, n_steps: int, order: int, i64: bool,
+                with_total: bool = False):
+    """Exclusive prefix sum of the counts ([n + 1], last = total).  ``with_total``: also return the
+    device int64[1] grand total (exact even when an int32 output wrapped)."""
     dev = row_cnt.device
     n = n_rows * n_steps
     out = torch.empty(n + 1, dtype=torch.int64 if i64 else torch.int32, device=dev)
-    ws = torch.empty(max(1, _lib.lib().grf_scan_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    ws = torch.empty(_lib.lib().grf_scan_workspace_bytes(n) // 8, dtype=torch.int64, device=dev)
     check(_lib.lib().grf_scan_counts(_ptr(row_cnt), n_rows, n_steps, order, _ptr(out), int(i64), _ptr(ws),
                                      _stream(dev)))
-    return out
+    return (out, ws[:1]) if with_total else out
 
 
 def run_walker(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
@@ -368,6 +377,7 @@ class PhiBlocks:
         # keeps the fixed stride (for A/B timing)
         self.dynamic_rows = os.environ.get("GRF_B200_DYNAMIC", "1") != "0"
         self._sched = None
+        self._census = None     # (pinned int32[6], event): row statistics of both sides, see _start_census
         self.visits = visits
         self._union = None
         self._tcols = None      # non-empty columns of this shard (int32) when that is a small fraction of N
@@ -384,20 +394,43 @@ class PhiBlocks:
         return int(self.entries.shape[0])
 
     def build_transpose(self) -> "PhiBlocks":
+        """Phi^T blocks (once per Phi).  Two C calls on one workspace; the row census of both sides is
+        copied to pinned host memory behind the offsets, so build_long_rows() reads it while the
+        fill / sort kernels still run instead of draining the GPU."""
         if self.tblk_ptr is not None:
             return self
         L = _lib.lib()
-        dev = self.device
+        dev, st = self.device, _stream(self.device)
         n_seg = self.n_cols * self.n_steps
-        tcnt = torch.empty(max(1, n_seg), dtype=torch.int32, device=dev)
-        check(L.grf_transpose_count(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
-                                    _ptr(tcnt), _stream(dev)))
-        self.tblk_ptr = scan_counts(tcnt, self.n_cols, self.n_steps, _lib.ORDER_ROW_MAJOR, i64=False)
-        cursor = torch.empty(n_seg + 2, dtype=torch.int32, device=dev)
+        ws = torch.empty(L.grf_transpose_workspace_bytes(self.n_cols, self.n_steps), dtype=torch.uint8, device=dev)
+        self.tblk_ptr = torch.empty(n_seg + 1, dtype=torch.int32, device=dev)
         self.tentries = torch.empty((max(1, self.nnz), 2), dtype=torch.int32, device=dev)[: self.nnz]
+        host = torch.empty(6, dtype=torch.int32, pin_memory=True) if self.nnz else None
+        check(L.grf_transpose_offsets(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
+                                      _ptr(self.tblk_ptr), _ptr(ws), LONG_ROW_THRESHOLD, _ptr(host), st))
+        if host is not None:
+            arrived = torch.cuda.Event()
+            arrived.record(torch.cuda.current_stream(dev))
+            self._census = (host, arrived)
         check(L.grf_transpose_fill(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
-                                   _ptr(self.tblk_ptr), _ptr(cursor), _ptr(self.tentries), _stream(dev)))
+                                   _ptr(self.tblk_ptr), _ptr(ws), _ptr(self.tentries), st))
         return self
+
+    def _start_census(self) -> None:
+        """Row statistics of both sides for Phi blocks that did not come through build_transpose()."""
+        if self.nnz == 0 or self._census is not None:
+            return
+        lib, dev, L = _lib.lib(), self.device, self.n_steps
+        census = torch.empty(6, dtype=torch.int32, device=dev)
+        check(lib.grf_row_census(_ptr(self.blk_ptr), self.n_rows, L, LONG_ROW_THRESHOLD, _ptr(census[0:3]),
+                                 _stream(dev)))
+        check(lib.grf_row_census(_ptr(self.tblk_ptr), self.n_cols, L, LONG_ROW_THRESHOLD, _ptr(census[3:6]),
+                                 _stream(dev)))
+        host = torch.empty(6, dtype=torch.int32, pin_memory=True)
+        host.copy_(census, non_blocking=True)
+        arrived = torch.cuda.Event()
+        arrived.record(torch.cuda.current_stream(dev))
+        self._census = (host, arrived)
 
     def build_windows(self) -> "PhiBlocks":
         """Column windows per 32 rows of Phi and Phi^T (lets a banded Phi use the tiled matvec)."""
@@ -489,20 +522,18 @@ class PhiBlocks:
 
     def build_long_rows(self) -> "PhiBlocks":
         """One-off matvec preparation: which rows / columns need the long-row split, and the list of
-        non-empty columns when this shard touches few of them.  One census kernel per side and a
-        single host read; the chunk tables are only built when a long row exists."""
+        non-empty columns when this shard touches few of them.  Reads the census that
+        build_transpose() started; the chunk tables are only built when a long row exists."""
         if self._long is None:
             self.build_transpose()
             self._long = [None, None]
             if self.nnz == 0:
                 return self
-            lib, L = _lib.lib(), self.n_steps
-            census = torch.empty(6, dtype=torch.int32, device=self.device)
-            check(lib.grf_row_census(_ptr(self.blk_ptr), self.n_rows, L, LONG_ROW_THRESHOLD, _ptr(census[0:3]),
-                                     _stream(self.device)))
-            check(lib.grf_row_census(_ptr(self.tblk_ptr), self.n_cols, L, LONG_ROW_THRESHOLD, _ptr(census[3:6]),
-                                     _stream(self.device)))
-            long_f, _, _, long_t, _, cols_used = census.tolist()
+            L = self.n_steps
+            self._start_census()
+            host, done = self._census
+            done.synchronize()
+            long_f, _, _, long_t, _, cols_used = host.tolist()
             if long_f:
                 self._long[0] = self._long_rows_of(self.blk_ptr, self.n_rows)
             if long_t:
@@ -735,11 +766,10 @@ class PhiBlocks:
 def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: int) -> PhiBlocks:
     L = cfg.max_walk_length
     dev = st.stage_col.device
-    blk_ptr = scan_counts(st.row_cnt, st.n_rows, L, _lib.ORDER_ROW_MAJOR, i64=True)
-    total = int(blk_ptr[-1].item())
+    blk_ptr, total = scan_counts(st.row_cnt, st.n_rows, L, _lib.ORDER_ROW_MAJOR, i64=False, with_total=True)
+    total = int(total.item())
     if total >= 2 ** 31:
         raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
-    blk_ptr = blk_ptr.to(torch.int32)
     entries = torch.empty((max(1, total), 2), dtype=torch.int32, device=dev)[:total]
     check(_lib.lib().grf_compact_blocks(_ptr(st.stage_col), _ptr(st.stage_sum), _ptr(st.row_cnt), _ptr(blk_ptr),
                                         st.n_rows, L, st.stride, cfg.walks_per_node, scale_mode, _ptr(entries),

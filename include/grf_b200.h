@@ -167,7 +167,8 @@ int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t stage_stride,
 
 /* Exclusive prefix sum of row_cnt[n_rows][L] in row-major or step-major order;
  * offsets has n_rows*L + 1 elements (last = total).  out_is_i64 selects
- * int64_t / int32_t output.  workspace: grf_scan_workspace_bytes(n_rows*L). */
+ * int64_t / int32_t output.  workspace: grf_scan_workspace_bytes(n_rows*L) bytes; after the
+ * call its first 8 bytes hold the grand total as int64_t (also when the int32 output wrapped). */
 int64_t grf_scan_workspace_bytes(int64_t n_items);
 int grf_scan_counts(const int32_t *row_cnt, int64_t n_rows, int32_t n_steps, int32_t order, void *offsets,
                     int32_t out_is_i64, void *workspace, void *stream);
@@ -199,9 +200,18 @@ int grf_row_census(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int3
                    void *stream);
 
 /* Replaces sparse_lo.py:23-25 (.t().to_sparse_csr(), redone on every forward in
- * the reference): build Phi^T blocks once.  count -> grf_scan_counts -> fill. */
-int grf_transpose_count(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                        int32_t n_steps, int32_t *tcnt /* [n_cols*L], zeroed by the call */, void *stream);
+ * the reference): build Phi^T blocks once, in two calls that share one workspace of
+ * grf_transpose_workspace_bytes(n_cols, L) bytes:
+ *   grf_transpose_offsets  segment sizes per (column, length) and their prefix sum tblk_ptr
+ *                          [n_cols*L + 1]; with census_host != NULL (pinned host int32[6]) also the
+ *                          grf_row_census of Phi ([0..3)) and Phi^T ([3..6)), copied to the host
+ *                          behind the scan so that it arrives while grf_transpose_fill still runs
+ *   grf_transpose_fill     scatters the entries (col = local row) and sorts every segment by row;
+ *                          `cursor` = the same workspace (its first n_cols*L + 2 ints) */
+int64_t grf_transpose_workspace_bytes(int64_t n_cols, int32_t n_steps);
+int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
+                          int32_t n_steps, int32_t *tblk_ptr, void *workspace, int32_t census_threshold,
+                          int32_t *census_host, void *stream);
 int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
                        int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor /* [n_cols*L + 2] scratch */,
                        GrfEntry *tentries, void *stream);
