@@ -92,8 +92,11 @@ __device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) 
 
 // KPL = keys per lane of the warp-per-node variant (sort width 32*KPL >= W); 0 for the
 // CTA-per-node variant, which sorts in shared memory.
+#ifndef GRF_WALK_MINBLOCKS
+#define GRF_WALK_MINBLOCKS 7  // 66 registers, no spills; 1 (80 registers, 6 CTAs/SM): 804 us, 7: 590, 8: 591, 9: 602 at config 2
+#endif
 template <bool kBlock, typename KeyT, int KPL>
-__global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const WalkParams p) {
+__global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINBLOCKS) walk_merge_kernel(const WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int GS = kBlock ? (int)blockDim.x : 32;
     const int tg = kBlock ? (int)threadIdx.x : (int)(threadIdx.x & 31);
@@ -118,35 +121,33 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
         const int64_t start = p.start_lo + row;
 
         // ---------------- phase 1: the walks -------------------------------
+        // a walk that stops at length s leaves no visit at lengths > s: mark every slot empty first
+        // (16-byte stores; per-walk tail loops cost 6 % of the kernel's instructions under ncu)
+        {
+            int4 *n4 = reinterpret_cast<int4 *>(nodes);
+            const int n_vec = (int)(p.nodes_bytes >> 4);
+            for (int i = tg; i < n_vec; i += GS) n4[i] = make_int4(-1, -1, -1, -1);
+        }
+        group_sync<kBlock>();
         for (int w = tg; w < W; w += GS) {
             const unsigned long long walk_id = (unsigned long long)start * (unsigned long long)W + (unsigned)w;
             int32_t cur = (int32_t)start;
             double load = 1.0;
             ++my_visits;  // the length-0 visit (start, 1.0)
             int step = 0;
-            uint32_t x[4] = {0u, 0u, 0u, 0u};  // one Philox block serves two consecutive steps
-            for (; step < L - 1; ++step) {
+            // one transition: false = the walk ends before a visit at length step + 1
+            auto advance = [&](const uint32_t xh, const uint32_t xk) -> bool {
                 const int32_t rs = __ldg(p.row_ptr + cur);
                 const int32_t re = __ldg(p.row_ptr + cur + 1);
                 const int32_t deg = re - rs;
-                if (deg == 0) break;  // dead end: stop without drawing (sparse_sampler.py:47)
+                if (deg == 0) return false;  // dead end: stop without drawing (sparse_sampler.py:47)
                 int32_t k;
                 if (p.draw_mode == GRF_DRAW_REPLAY) {
                     const unsigned long long ti = walk_id * (unsigned)L + (unsigned)step;
-                    if (__ldg(p.trace_u + ti) < p.p_halt) break;
+                    if (__ldg(p.trace_u + ti) < p.p_halt) return false;
                     k = __ldg(p.trace_k + ti);
                 } else {
-                    uint32_t xh, xk;
-                    if ((step & 1) == 0) {
-                        philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)(step >> 1), 0u, p.k0,
-                                      p.k1, x);
-                        xh = x[0];
-                        xk = x[1];
-                    } else {
-                        xh = x[2];
-                        xk = x[3];
-                    }
-                    if ((unsigned long long)xh < p.halt_thr) break;
+                    if ((unsigned long long)xh < p.halt_thr) return false;
                     k = (int32_t)__umulhi(xk, (uint32_t)deg);
                 }
                 const int64_t e = (int64_t)rs + k;
@@ -166,8 +167,22 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128) walk_merge_kernel(const Wa
                 nodes[step * W + w] = cur;  // the visit at length step+1
                 loads[step * W + w] = load;
                 ++my_visits;
+                ++step;
+                return true;
+            };
+            if (p.draw_mode == GRF_DRAW_REPLAY) {
+                while (step < L - 1 && advance(0u, 0u)) {
+                }
+            } else {
+                // one Philox block serves two consecutive steps: words (0,1) the even one, (2,3) the odd one
+                while (step < L - 1) {
+                    uint32_t x[4];
+                    philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)(step >> 1), 0u, p.k0, p.k1,
+                                  x);
+                    if (!advance(x[0], x[1])) break;
+                    if (step >= L - 1 || !advance(x[2], x[3])) break;
+                }
             }
-            for (int s2 = step; s2 < L - 1; ++s2) nodes[s2 * W + w] = -1;
         }
 
         int32_t *out_col = p.stage_col + row * p.stride;
@@ -395,8 +410,8 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     const bool key32 = node_bits + p.wbits <= 31;
     const size_t key_size = key32 ? 4 : 8;
     const size_t steps = (size_t)(p.L - 1);
-    p.loads_bytes = (uint32_t)(steps * p.W * 8);
-    p.nodes_bytes = (uint32_t)((steps * p.W * 4 + 7) & ~(size_t)7);
+    p.loads_bytes = (uint32_t)((steps * p.W * 8 + 15) & ~(size_t)15);  // keeps `nodes` 16-byte aligned
+    p.nodes_bytes = (uint32_t)((steps * p.W * 4 + 15) & ~(size_t)15);  // whole int4s: the kernel clears it with 16-byte stores
     const bool warp_variant = p.W <= 256;
     const int kpl = p.Wp <= 32 ? 1 : p.Wp / 32;  // warp variant sorts 32*kpl keys
     const size_t n_keys = warp_variant ? (size_t)32 * kpl : (size_t)p.Wp;
