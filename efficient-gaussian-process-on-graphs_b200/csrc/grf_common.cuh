@@ -83,34 +83,56 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // distance < KPL stay in registers, larger ones are one shuffle per key.  ~4x fewer issue
 // slots than the shared-memory network it replaces (ncu: the sort was 45 % of all
 // instructions of the kernel).
+// All-ascending form: the first stage of every merge pairs e with its mirror e ^ (k - 1), the
+// remaining ones e with e ^ j, and every comparator puts the smaller key at the lower index, so
+// the in-register exchanges are a plain min/max pair (no per-lane direction select).
 template <typename KeyT, int KPL>
 __device__ __forceinline__ void warp_bitonic_sort(KeyT (&key)[KPL], const int lane) {
 #pragma unroll
     for (int k = 2; k <= 32 * KPL; k <<= 1) {
+        if (k <= KPL) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int r = 0; r < KPL; ++r) {
+                const int pr = r ^ (k - 1);
+                if (r < pr) {
+                    const KeyT a = key[r], b = key[pr];
+                    key[r] = a < b ? a : b;
+                    key[pr] = a < b ? b : a;
+                }
+            }
+        } else {
+            const bool lower = (lane & (k / 2 / KPL)) == 0;
+            KeyT other[KPL];
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) other[r] = __shfl_xor_sync(0xffffffffu, key[KPL - 1 - r], k / KPL - 1);
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) {
+                const KeyT mine = key[r];
+                const KeyT mn = mine < other[r] ? mine : other[r];
+                const KeyT mx = mine < other[r] ? other[r] : mine;
+                key[r] = lower ? mn : mx;
+            }
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
             if (j >= KPL) {
                 const int lj = j / KPL;
+                const bool lower = (lane & lj) == 0;
 #pragma unroll
                 for (int r = 0; r < KPL; ++r) {
                     const KeyT mine = key[r];
                     const KeyT other = __shfl_xor_sync(0xffffffffu, mine, lj);
-                    const bool up = ((lane * KPL + r) & k) == 0;
-                    const bool lower = (lane & lj) == 0;
                     const KeyT mn = mine < other ? mine : other;
                     const KeyT mx = mine < other ? other : mine;
-                    key[r] = (lower == up) ? mn : mx;
+                    key[r] = lower ? mn : mx;
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < KPL; ++r) {
                     if ((r & j) == 0) {
-                        const bool up = ((lane * KPL + r) & k) == 0;
                         const KeyT a = key[r], b = key[r | j];
-                        const KeyT mn = a < b ? a : b;
-                        const KeyT mx = a < b ? b : a;
-                        key[r] = up ? mn : mx;
-                        key[r | j] = up ? mx : mn;
+                        key[r] = a < b ? a : b;
+                        key[r | j] = a < b ? b : a;
                     }
                 }
             }
