@@ -95,7 +95,9 @@ __device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) 
 #ifndef GRF_WALK_MINBLOCKS
 #define GRF_WALK_MINBLOCKS 7  // 66 registers, no spills; 1 (80 registers, 6 CTAs/SM): 804 us, 7: 590, 8: 591, 9: 602 at config 2
 #endif
-template <bool kBlock, typename KeyT, int KPL>
+// kFast: Philox draws, cumulative load, per-edge factors precomputed (the production setting) --
+// strips the per-step mode tests; the generic instantiation serves replay / ablation / sequential.
+template <bool kBlock, typename KeyT, int KPL, bool kFast>
 __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINBLOCKS) walk_merge_kernel(const WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int GS = kBlock ? (int)blockDim.x : 32;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 const int32_t deg = re - rs;
                 if (deg == 0) return false;  // dead end: stop without drawing (sparse_sampler.py:47)
                 int32_t k;
-                if (p.draw_mode == GRF_DRAW_REPLAY) {
+                if (!kFast && p.draw_mode == GRF_DRAW_REPLAY) {
                     const unsigned long long ti = walk_id * (unsigned)L + (unsigned)step;
                     if (__ldg(p.trace_u + ti) < p.p_halt) return false;
                     k = __ldg(p.trace_k + ti);
@@ -155,13 +157,13 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 // load *= degree * weight / (1 - p_halt), evaluated left to right in float64 with
                 // no contraction (sparse_sampler.py:54).  (deg * w) / (1 - p) depends on the edge
                 // only, so grf_edge_scale may have computed it once per edge (same roundings).
-                if (p.load_mode == GRF_LOAD_ABLATION) {
+                if (!kFast && p.load_mode == GRF_LOAD_ABLATION) {
                     load = __ldg(p.val + e);
                 } else {
-                    const double scaled = p.scaled_val
+                    const double scaled = (kFast || p.scaled_val)
                                               ? __ldg(p.scaled_val + e)
                                               : __ddiv_rn(__dmul_rn((double)deg, __ldg(p.val + e)), p.one_minus_p);
-                    load = p.load_mode == GRF_LOAD_CUMULATIVE ? __dmul_rn(load, scaled) : scaled;
+                    load = (kFast || p.load_mode == GRF_LOAD_CUMULATIVE) ? __dmul_rn(load, scaled) : scaled;
                 }
                 cur = nxt;
                 nodes[step * W + w] = cur;  // the visit at length step+1
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 ++step;
                 return true;
             };
-            if (p.draw_mode == GRF_DRAW_REPLAY) {
+            if (!kFast && p.draw_mode == GRF_DRAW_REPLAY) {
                 while (step < L - 1 && advance(0u, 0u)) {
                 }
             } else {
@@ -337,9 +339,9 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
     }
 }
 
-template <bool kBlock, typename KeyT, int KPL>
+template <bool kBlock, typename KeyT, int KPL, bool kFast = false>
 static int launch_walk(const WalkParams &p, size_t smem, int threads, int grid, cudaStream_t stream) {
-    auto kern = walk_merge_kernel<kBlock, KeyT, KPL>;
+    auto kern = walk_merge_kernel<kBlock, KeyT, KPL, kFast>;
     GRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(p);
     return check_cuda(cudaGetLastError(), "walk_merge_kernel launch");
@@ -428,8 +430,12 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
         const int grid = (int)(want < (int64_t)kSmCount * 64 ? want : (int64_t)kSmCount * 64);
         const size_t smem = warps * gb;
         const int threads = warps * 32;
+        const bool fast = p.draw_mode == GRF_DRAW_PHILOX && p.load_mode == GRF_LOAD_CUMULATIVE && p.scaled_val;
 #define GRF_WALK_CASE(K)                                                                              \
     case K:                                                                                           \
+        if (fast)                                                                                     \
+            return key32 ? launch_walk<false, uint32_t, K, true>(p, smem, threads, grid, st)         \
+                         : launch_walk<false, unsigned long long, K, true>(p, smem, threads, grid, st); \
         return key32 ? launch_walk<false, uint32_t, K>(p, smem, threads, grid, st)                   \
                      : launch_walk<false, unsigned long long, K>(p, smem, threads, grid, st)
         switch (kpl) {
