@@ -215,59 +215,44 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                     key[r] = kk;
                 }
                 warp_bitonic_sort<KeyT, KPL>(key, lane);
-                // park the sorted keys and, in the same order, their loads: the run walk below
-                // is then two sequential shared-memory streams
-                constexpr int kSortN = 32 * KPL;
+                // park the loads in sorted order; a run (= one output entry) is then a contiguous
+                // stretch of that stream.  Heads write their node and where their run starts; one lane
+                // per run then adds the run's loads in walk order (the reference's summation order).
 #pragma unroll
                 for (int r = 0; r < KPL; ++r) {
                     const KeyT kk = key[r];
-                    keys[lane * KPL + r] = kk;
                     if (kk != KEY_MAX) sorted_loads[lane * KPL + r] = loads[si * W + (int)(kk & wmask)];
                 }
-                __syncwarp();
                 const KeyT prev_last = __shfl_up_sync(0xffffffffu, key[KPL - 1], 1);
-                int heads = 0, first_head = -1;
+                bool head[KPL];
+                int counts = 0;  // heads in the low half, valid elements in the high half: one scan for both
 #pragma unroll
                 for (int r = 0; r < KPL; ++r) {
                     const KeyT kk = key[r];
                     const KeyT pv = r == 0 ? prev_last : key[r > 0 ? r - 1 : 0];
                     const bool first = (lane == 0 && r == 0);
-                    const bool h = (kk != KEY_MAX) && (first || (pv >> wbits) != (kk >> wbits));
-                    heads += h;
-                    if (h && first_head < 0) first_head = r;
+                    head[r] = (kk != KEY_MAX) && (first || (pv >> wbits) != (kk >> wbits));
+                    counts += (int)head[r] + ((int)(kk != KEY_MAX) << 16);
                 }
-                int total;
-                int rank = group_excl_scan<false>(heads, scan_scratch, total);
-                if (first_head >= 0) {
-                    // this lane emits every run that STARTS in its chunk: walk the elements from its
-                    // first head until a run starts in a later chunk; loads are added in walk order
-                    const int chunk_end = (lane + 1) * KPL;
-                    int q = lane * KPL + first_head;
-                    KeyT node = key[0] >> wbits;
+                int totals;
+                int rank = group_excl_scan<false>(counts, scan_scratch, totals) & 0xffff;
+                const int total = totals & 0xffff, n_valid = totals >> 16;
+                int32_t *run_start = reinterpret_cast<int32_t *>(keys);  // [total + 1]
 #pragma unroll
-                    for (int r = 1; r < KPL; ++r)
-                        if (r == first_head) node = key[r] >> wbits;
+                for (int r = 0; r < KPL; ++r) {
+                    if (head[r]) {
+                        run_start[rank] = lane * KPL + r;
+                        out_col[off + rank] = (int32_t)(key[r] >> wbits);
+                        ++rank;
+                    }
+                }
+                if (lane == 0) run_start[total] = n_valid;
+                __syncwarp();
+                for (int j = lane; j < total; j += 32) {
+                    const int qb = run_start[j], qe = run_start[j + 1];
                     double sum = 0.0;
-                    for (; q < kSortN; ++q) {
-                        const KeyT kq = keys[q];
-                        const KeyT nd = kq >> wbits;
-                        if (nd != node) {
-                            out_col[off + rank] = (int32_t)node;
-                            out_sum[off + rank] = sum;
-                            ++rank;
-                            if (kq == KEY_MAX || q >= chunk_end) {
-                                node = KEY_MAX;  // nothing pending
-                                break;
-                            }
-                            node = nd;
-                            sum = 0.0;
-                        }
-                        sum = __dadd_rn(sum, sorted_loads[q]);
-                    }
-                    if (node != KEY_MAX) {  // ran off the end of the array with a run pending
-                        out_col[off + rank] = (int32_t)node;
-                        out_sum[off + rank] = sum;
-                    }
+                    for (int q = qb; q < qe; ++q) sum = __dadd_rn(sum, sorted_loads[q]);
+                    out_sum[off + j] = sum;
                 }
                 if (lane == 0) p.row_cnt[row * L + si + 1] = total;
                 off += total;
@@ -418,7 +403,8 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     const int kpl = p.Wp <= 32 ? 1 : p.Wp / 32;  // warp variant sorts 32*kpl keys
     const size_t n_keys = warp_variant ? (size_t)32 * kpl : (size_t)p.Wp;
     p.sorted_bytes = warp_variant ? (uint32_t)(n_keys * 8) : 0u;
-    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + p.sorted_bytes + n_keys * key_size + 15) & ~(size_t)15;
+    // + 4: the warp variant reuses the key area as run_start[runs + 1] (runs <= n_keys)
+    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + p.sorted_bytes + n_keys * key_size + 4 + 15) & ~(size_t)15;
     p.group_bytes = (uint32_t)gb;
     const size_t kMaxSmem = 227 * 1024 - 256;
     GRF_REQUIRE((uint64_t)p.W * (uint64_t)p.L < (1ull << 31), "grf_walk: W*L too large");
