@@ -26,6 +26,7 @@ same workload.  oracle/ is used here only as the timed CPU baseline.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -175,6 +176,7 @@ def workload_config(n_gpus, n_nodes):
         "n_nodes": int(n_nodes), "walks_per_node": W, "max_walk_length": L, "p_halt": P_HALT, "rhs_columns": T_RHS,
         "sharding": f"start nodes row-sharded over {n_gpus} GPU(s), CSR graph replicated",
         "l2": "flushed (256 MB write) before every timed phase; staging (480 MB) exceeds L2 as well",
+        "host": "Python gc disabled inside the timed region",
     }
 
 
@@ -201,6 +203,10 @@ def run_gpu(args):
     lo, hi = rank * rows_per, (rank + 1) * rows_per if rank < world - 1 else n
     graph = engine.DeviceGraph.from_scipy(lap, dev)
     cfg = engine.WalkConfig(W, P_HALT, L, seed=SEED)
+    # rows of Phi^T V the ranks must sum: nodes within L - 1 hops of two or more row shards.  A property of
+    # the graph and the sharding (like the Laplacian itself), so computed once here, not per step.
+    bounds = [r * rows_per for r in range(world)] + [n]
+    shared_hint = graph.shared_columns(bounds, L) if world > 1 else None
     torch.manual_seed(42)
     f = torch.randn(L).to(dev)                         # learnable modulator init, sparse_grf_kernel.py:14-17
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -255,15 +261,23 @@ def run_gpu(args):
         del r
     if rank == 0:
         sampler.wait_first_sample()
+    # no Python garbage-collector pause inside the timed region (a gen-2 collection on one rank stalls the
+    # other ranks in the matvec's all-reduce for about a millisecond)
+    gc.collect()
+    gc.disable()
     barrier()
     t_wall0 = time.perf_counter()
     results = [one_step() for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    gc.enable()
 
     phase_ms = {k: sum(r["events"][k][0].elapsed_time(r["events"][k][1]) for r in results)
                 for k in ("walk", "compact", "transpose", "matvec")}
     step_ms_total = sum(phase_ms.values())
+    if os.environ.get("GRF_BENCH_DEBUG"):
+        print(f"[rank {rank}] per-phase ms over {args.steps} steps: "
+              + ", ".join(f"{k} {v:.3f}" for k, v in phase_ms.items()), file=sys.stderr, flush=True)
     visits_total = sum(int(r["visits"].item()) for r in results)
     nnz = results[-1]["nnz"]
     n_rows = results[-1]["n_rows"]
@@ -274,6 +288,7 @@ def run_gpu(args):
     phi_cg = engine._blocks_from_staging(st, cfg, graph.n_nodes, _lib.SCALE_MUL_RECIP)
     del st
     phi_cg.row_lo = lo
+    phi_cg.shared_hint = shared_hint
     phi_cg.build_transpose()
     _, e_union = timed(lambda: phi_cg.build_union())
     cg_plan, e_mat = timed(lambda: phi_cg.plan(f, T_RHS, group=True if world > 1 else None, merged=True))
@@ -304,6 +319,7 @@ def run_gpu(args):
         mats = steps.to_scipy()                          # D2H of every M_l (float64 + int32 + offsets)
         phi_e = engine.PhiBlocks.from_step_matrices(steps)
         phi_e.row_lo = lo
+        phi_e.shared_hint = shared_hint
         vd = v_host.to(dev, non_blocking=True)
         out_host = phi_e.plan(f, T_RHS, group=True if world > 1 else None, merged=False)(vd).cpu()   # one product
         torch.cuda.synchronize(dev)

@@ -420,6 +420,20 @@ __global__ void __launch_bounds__(256) row_census_kernel(const int32_t *__restri
     }
 }
 
+// ids of the non-empty rows, ascending, without a host round trip: flags -> scan -> scatter
+__global__ void __launch_bounds__(256) row_flags_kernel(const int32_t *__restrict__ ptr, int64_t n_rows, int32_t L,
+                                                        int32_t *__restrict__ flags) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+        flags[r] = __ldg(ptr + (r + 1) * L) > __ldg(ptr + r * L);
+}
+
+__global__ void __launch_bounds__(256) scatter_ids_kernel(const int32_t *__restrict__ flags,
+                                                          const int32_t *__restrict__ pos, int64_t n_rows,
+                                                          int32_t *__restrict__ ids) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+        if (flags[r]) ids[pos[r]] = (int32_t)r;
+}
+
 }  // namespace grf
 
 // ---------------------------------------------------------------------------
@@ -533,6 +547,22 @@ extern "C" int grf_blocks_from_steps(const int64_t *offsets_step_major, const in
     blocks_from_steps_kernel<<<grid_for_warps(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(
         offsets_step_major, col, val, blk_ptr, n_rows, n_steps, entries);
     return check_cuda(cudaGetLastError(), "blocks_from_steps_kernel launch");
+}
+
+extern "C" int grf_nonempty_rows(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t *flags,
+                                 int32_t *pos, void *scan_workspace, int32_t *ids, void *stream) {
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_nonempty_rows: bad shape");
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(blk_ptr && flags && pos && scan_workspace && ids, "grf_nonempty_rows: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t g = (n_rows + 255) / 256;
+    if (g > (int64_t)kSmCount * 16) g = (int64_t)kSmCount * 16;
+    row_flags_kernel<<<(int)g, 256, 0, st>>>(blk_ptr, n_rows, n_steps, flags);
+    GRF_CUDA_OK(cudaGetLastError());
+    const int rc = grf_scan_counts(flags, n_rows, 1, GRF_ORDER_ROW_MAJOR, pos, 0, scan_workspace, stream);
+    if (rc != GRF_OK) return rc;
+    scatter_ids_kernel<<<(int)g, 256, 0, st>>>(flags, pos, n_rows, ids);
+    return check_cuda(cudaGetLastError(), "nonempty_rows kernels launch");
 }
 
 static int64_t transpose_cursor_bytes(int64_t n_cols, int32_t n_steps) {

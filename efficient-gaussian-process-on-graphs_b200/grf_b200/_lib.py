@@ -26,10 +26,10 @@ ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
 EXPORTS = (
     "grf_abi_version", "grf_last_error", "grf_walk_stage_stride", "grf_walk", "grf_scan_workspace_bytes",
     "grf_scan_counts", "grf_compact_steps", "grf_compact_blocks", "grf_blocks_from_steps", "grf_count_from_steps",
-    "grf_row_census", "grf_transpose_workspace_bytes", "grf_transpose_offsets", "grf_transpose_fill",
+    "grf_row_census", "grf_nonempty_rows", "grf_transpose_workspace_bytes", "grf_transpose_offsets", "grf_transpose_fill",
     "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_scale", "grf_union_rank", "grf_union_fill",
     "grf_union_materialize", "grf_cg_num_partials", "grf_cg_dot", "grf_cg_update", "grf_cg_direction",
-    "grf_laplacian_count", "grf_laplacian_fill",
+    "grf_laplacian_count", "grf_laplacian_fill", "grf_shard_reach",
 )
 
 
@@ -111,6 +111,10 @@ def lib():
     L.grf_count_from_steps.argtypes = [vp, i64, i32, vp, vp]
     L.grf_row_census.restype = i32
     L.grf_row_census.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.grf_shard_reach.restype = i32
+    L.grf_shard_reach.argtypes = [POINTER(GrfGraph), vp, i32, i32, vp, vp, vp]
+    L.grf_nonempty_rows.restype = i32
+    L.grf_nonempty_rows.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp]
     L.grf_transpose_workspace_bytes.restype = i64
     L.grf_transpose_workspace_bytes.argtypes = [i64, i32]
     L.grf_transpose_offsets.restype = i32

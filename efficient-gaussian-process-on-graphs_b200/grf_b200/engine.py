@@ -94,6 +94,7 @@ class DeviceGraph:
         self.n_nodes = int(n_nodes)
         self.nnz = nnz
         self._scaled = {}
+        self._shared = {}
         self.row_ptr = torch.from_numpy(indptr.astype(np.int32, copy=False)).to(self.device, non_blocking=True)
         self.col_idx = torch.from_numpy(np.ascontiguousarray(indices[:nnz]).astype(np.int32, copy=False)).to(
             self.device, non_blocking=True)
@@ -117,6 +118,7 @@ class DeviceGraph:
         g.device = row_ptr.device
         g.n_nodes, g.nnz = int(n_nodes), int(col_idx.numel())
         g._scaled = {}
+        g._shared = {}
         g.row_ptr, g.col_idx, g.val = row_ptr, col_idx, val
         return g
 
@@ -151,6 +153,29 @@ class DeviceGraph:
 
         return sp.csr_matrix((self.val.cpu().numpy(), self.col_idx.cpu().numpy(), self.row_ptr.cpu().numpy()),
                              shape=(self.n_nodes, self.n_nodes))
+
+    def shared_columns(self, bounds: Sequence[int], max_walk_length: int, max_fraction: float = 0.5):
+        """Columns that the Phi blocks of two or more row shards can touch: nodes reachable within
+        ``max_walk_length - 1`` hops from start nodes of >= 2 of the shards ``bounds[g] .. bounds[g+1]``.
+        Depends on the graph and the sharding only (cached), needs no collective, and is a superset
+        of what any draw touches -- assign it to ``PhiBlocks.shared_hint`` and the sharded matvec
+        exchanges just these rows of Phi^T V.  Returns "all" when they exceed ``max_fraction`` of the
+        nodes (then a plain all-reduce is cheaper)."""
+        key = (tuple(int(b) for b in bounds), int(max_walk_length))
+        if key not in self._shared:
+            world = len(key[0]) - 1
+            if world > 64:
+                return None             # no bound: the plan falls back to exchanging the touched columns
+            b = torch.tensor(key[0], dtype=torch.int64, device=self.device)
+            mask = torch.empty(max(1, self.n_nodes), dtype=torch.int64, device=self.device)
+            scratch = torch.empty_like(mask)
+            g = self.c_struct()
+            check(_lib.lib().grf_shard_reach(ctypes.byref(g), _ptr(b), world, max(0, key[1] - 1), _ptr(mask),
+                                             _ptr(scratch), _stream(self.device)))
+            mask = mask[: self.n_nodes]
+            shared = torch.nonzero((mask & (mask - 1)) != 0).flatten()
+            self._shared = {key: "all" if shared.numel() > max_fraction * self.n_nodes else shared}
+        return self._shared[key]
 
     def scaled_val(self, p_halt: float) -> torch.Tensor:
         """(deg * w) / (1 - p_halt) per edge (cached per p_halt): the load-update factor."""
@@ -381,6 +406,10 @@ class PhiBlocks:
         self.visits = visits
         self._union = None
         self._tcols = None      # non-empty columns of this shard (int32) when that is a small fraction of N
+        self._touched = None    # int32 0/1 per column, set together with _tcols
+        # sharded matvec: columns to exchange between the ranks, if known up front (tensor of ids or
+        # "all"; DeviceGraph.shared_columns); None = the plan finds them with one all-reduce
+        self.shared_hint = None
         self._long = None       # [fwd, transposed] long-row metadata (dicts) or None per side
         self._long_c = {}       # ld -> (ctypes structs, partial buffers) kept alive for the calls
         self._ws = {}
@@ -540,8 +569,13 @@ class PhiBlocks:
                 self._long[1] = self._long_rows_of(self.tblk_ptr, self.n_cols)
             # columns this (row) shard touches: worth a list when most of the N columns are empty
             if cols_used < 0.75 * self.n_cols:
-                lens = self.tblk_ptr[L:self.n_cols * L + 1:L] - self.tblk_ptr[0:self.n_cols * L:L]
-                self._tcols = torch.nonzero(lens > 0).flatten().to(torch.int32).contiguous()
+                lib, dev = _lib.lib(), self.device
+                self._touched = torch.empty(self.n_cols, dtype=torch.int32, device=dev)
+                pos = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
+                ws = torch.empty(lib.grf_scan_workspace_bytes(self.n_cols), dtype=torch.uint8, device=dev)
+                self._tcols = torch.empty(cols_used, dtype=torch.int32, device=dev)
+                check(lib.grf_nonempty_rows(_ptr(self.tblk_ptr), self.n_cols, L, _ptr(self._touched), _ptr(pos),
+                                            _ptr(ws), _ptr(self._tcols), _stream(dev)))
         return self
 
     def _long_structs(self, ld: int):
@@ -886,11 +920,13 @@ class MatvecPlan:
             # exchange only the columns that more than one row shard touches (sharding.shared_columns)
             from . import sharding
 
-            touched = torch.ones(phi.n_cols, dtype=torch.bool, device=dev)
-            if self.phi._tcols is not None:
-                touched.zero_()
-                touched[self.phi._tcols.long()] = True
-            self._shared = sharding.shared_columns(touched, None if group is True else group)
+            if phi.shared_hint is not None:
+                self._shared = None if isinstance(phi.shared_hint, str) else phi.shared_hint
+            else:
+                touched = self.phi._touched
+                if touched is None:     # most columns touched: a plain all-reduce follows
+                    touched = torch.ones(phi.n_cols, dtype=torch.int32, device=dev)
+                self._shared = sharding.shared_columns(touched, None if group is True else group)
             if self._shared is not None and self._shared.numel():
                 self._shared_buf = torch.empty((self._shared.numel(), self.ldu), dtype=torch.float32, device=dev)
 

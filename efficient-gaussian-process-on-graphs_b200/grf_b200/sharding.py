@@ -70,7 +70,7 @@ def shared_columns(touched: torch.Tensor, group=None, max_fraction: float = 0.5)
     shard boundaries, so the exchange shrinks from N x t to O(bandwidth x t)."""
     import torch.distributed as dist
 
-    count = touched.to(torch.int32).contiguous()
+    count = touched.to(torch.int32).clone()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(count, group=group)
     else:

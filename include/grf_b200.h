@@ -199,6 +199,23 @@ int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int3
 int grf_row_census(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t threshold, int32_t *census,
                    void *stream);
 
+/* Multi-GPU row of the path (no reference counterpart: its fork pool merges dictionaries on the host,
+ * sparse_sampler.py:90-114).  Start nodes are sharded in contiguous blocks, bounds[g] .. bounds[g+1]
+ * (device int64 [world + 1], world <= 64).  mask[v] receives bit g iff a start node of shard g reaches
+ * node v within `hops` steps of the walk graph, i.e. a superset of the columns shard g's Phi can
+ * touch with max_walk_length = hops + 1.  Columns with >= 2 bits are the only rows of Phi^T V the
+ * ranks must sum.  scratch: n_nodes words. */
+int grf_shard_reach(const GrfGraph *graph, const int64_t *bounds, int32_t world, int32_t hops,
+                    unsigned long long *mask, unsigned long long *scratch, void *stream);
+
+/* Ascending ids of the non-empty rows of Phi or Phi^T blocks (GrfPhi.tcols for a row shard that
+ * touches few of the N columns), with no host round trip: the caller sizes `ids` from
+ * grf_row_census()[2].  flags [n_rows] receives 0/1 per row (also the "touched" vector the ranks
+ * sum to find the columns they share), pos [n_rows + 1] and scan_workspace
+ * (grf_scan_workspace_bytes(n_rows)) are scratch. */
+int grf_nonempty_rows(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t *flags, int32_t *pos,
+                      void *scan_workspace, int32_t *ids, void *stream);
+
 /* Replaces sparse_lo.py:23-25 (.t().to_sparse_csr(), redone on every forward in
  * the reference): build Phi^T blocks once, in two calls that share one workspace of
  * grf_transpose_workspace_bytes(n_cols, L) bytes:

@@ -386,6 +386,43 @@ def test_sharded_rows_sum_to_the_full_product(env, case):
     assert torch.allclose(parts, want[x], rtol=1e-4, atol=1e-5 * float(want.abs().max()))
 
 
+def test_shard_reach_bounds_the_columns_row_shards_share(env, case):
+    """grf_shard_reach == (L-1)-hop reachability from every row shard (scipy), and the columns it
+    marks as shared contain every column that two shards' Phi blocks actually touch."""
+    eng, torch = env["eng"], env["torch"]
+    g, cfg, lap = case["g"], case["cfg"], case["lap"]
+    n = g.n_nodes
+    bounds = [0, 150, 151, 420, n]
+    pattern = (abs(lap) > 0).astype(np.int64).tocsr()          # u -> v: v is a neighbour in the walk graph
+    L = cfg.max_walk_length
+    reach = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        ind = np.zeros(n, dtype=np.int64)
+        ind[lo:hi] = 1
+        cur = ind.copy()
+        for _ in range(L - 1):
+            cur = ((pattern.T @ cur) + cur > 0).astype(np.int64)
+        reach.append(cur > 0)
+    want_shared = np.flatnonzero(np.sum(reach, axis=0) >= 2)
+    got = g.shared_columns(bounds, L, max_fraction=2.0)
+    assert np.array_equal(got.cpu().numpy(), want_shared)
+    assert g.shared_columns(bounds, L, max_fraction=2.0) is got       # cached per (sharding, L)
+    # zero hops: every node belongs to exactly one shard
+    assert eng.DeviceGraph.from_scipy(lap).shared_columns(bounds, 1, max_fraction=2.0).numel() == 0
+    touched = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        mats = eng.build_phi_blocks(g, cfg, lo, hi).to_scipy_steps()
+        cols = np.zeros(n, dtype=bool)
+        for m in mats:
+            cols[m.indices] = True
+        touched.append(cols)
+        assert not np.any(cols & ~reach[len(touched) - 1])
+    actually_shared = np.flatnonzero(np.sum(touched, axis=0) >= 2)
+    assert np.isin(actually_shared, want_shared).all()
+    # "all" once the shared columns pass the fraction
+    assert eng.DeviceGraph.from_scipy(lap).shared_columns(bounds, L, max_fraction=0.0) == "all" or want_shared.size == 0
+
+
 @pytest.mark.parametrize("kind", ["grid", "powerlaw", "isolated", "ring_bigW", "no_edges"])
 def test_every_path_on_small_and_degenerate_graphs(env, kind):
     """Device Laplacian -> walker (chunked staging) -> step matrices / Phi blocks -> every matvec variant
