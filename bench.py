@@ -232,7 +232,7 @@ def run_gpu(args):
         """walker -> Phi blocks -> Phi^T blocks -> one Phi(Phi^T V).  Returns events + the visit counter only,
         so every step reuses the previous step's device memory (no cudaMalloc in the timed region)."""
         visits = torch.zeros(1, dtype=torch.int64, device=dev)
-        st, e_walk = timed(lambda: engine.run_walker(graph, cfg, lo, hi, visits=visits))
+        st, e_walk = timed(lambda: engine.run_walker(graph, cfg, lo, hi, visits=visits, count_columns=True))
         phi, e_comp = timed(lambda: engine._blocks_from_staging(st, cfg, graph.n_nodes, _lib.SCALE_MUL_RECIP))
         del st
         phi.row_lo = lo

@@ -575,8 +575,8 @@ extern "C" int64_t grf_transpose_workspace_bytes(int64_t n_cols, int32_t n_steps
 }
 
 extern "C" int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                                     int32_t n_steps, int32_t *tblk_ptr, void *workspace, int32_t census_threshold,
-                                     int32_t *census_host, void *stream) {
+                                     int32_t n_steps, const int32_t *col_counts, int32_t *tblk_ptr, void *workspace,
+                                     int32_t census_threshold, int32_t *census_host, void *stream) {
     GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_offsets: bad shape");
     GRF_REQUIRE(tblk_ptr && workspace, "grf_transpose_offsets: null buffer");
     GRF_REQUIRE(!census_host || census_threshold >= 1, "grf_transpose_offsets: bad census threshold");
@@ -584,7 +584,9 @@ extern "C" int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *ent
     int32_t *tcnt = (int32_t *)workspace;
     char *scan_ws = (char *)workspace + transpose_cursor_bytes(n_cols, n_steps);
     int32_t *census = (int32_t *)(scan_ws + grf_scan_workspace_bytes(n_cols * n_steps));
-    if (n_cols > 0) {
+    if (col_counts) {
+        tcnt = const_cast<int32_t *>(col_counts);  // the walker counted while it emitted the entries
+    } else if (n_cols > 0) {
         GRF_CUDA_OK(cudaMemsetAsync(tcnt, 0, (size_t)n_cols * n_steps * sizeof(int32_t), st));
         if (n_rows > 0) {
             GRF_REQUIRE(blk_ptr, "grf_transpose_offsets: null blk_ptr");

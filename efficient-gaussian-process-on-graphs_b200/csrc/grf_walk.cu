@@ -51,6 +51,7 @@ struct WalkParams {
     int32_t *row_cnt;
     unsigned long long *visits;
     uint32_t group_bytes, loads_bytes, nodes_bytes, sorted_bytes;
+    int32_t *col_counts;  // optional [n_nodes][L]: entries per (column, length), for the Phi^T offsets
 };
 
 template <bool kBlock>
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
             out_col[0] = (int32_t)start;  // M_0 = I: W visits of load 1.0, summed exactly
             out_sum[0] = (double)W;
             p.row_cnt[row * L] = 1;
+            if (p.col_counts) atomicAdd(p.col_counts + start * L, 1);
         }
         int off = 1;
         group_sync<kBlock>();
@@ -242,7 +244,9 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 for (int r = 0; r < KPL; ++r) {
                     if (head[r]) {
                         run_start[rank] = lane * KPL + r;
-                        out_col[off + rank] = (int32_t)(key[r] >> wbits);
+                        const int32_t node = (int32_t)(key[r] >> wbits);
+                        out_col[off + rank] = node;
+                        if (p.col_counts) atomicAdd(p.col_counts + (int64_t)node * L + si + 1, 1);
                         ++rank;
                     }
                 }
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                         }
                         out_col[off + rank] = (int32_t)node;
                         out_sum[off + rank] = sum;
+                        if (p.col_counts) atomicAdd(p.col_counts + (int64_t)node * L + si + 1, 1);
                         ++rank;
                     }
                 }
@@ -392,6 +397,7 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     p.stage_sum = stage_sum;
     p.row_cnt = row_cnt;
     p.visits = visits_out;
+    p.col_counts = cfg->col_counts;
 
     const int node_bits = bit_width((uint64_t)(graph->n_nodes > 0 ? graph->n_nodes - 1 : 0));
     const bool key32 = node_bits + p.wbits <= 31;

@@ -41,7 +41,7 @@ class GrfGraph(Structure):
 class GrfWalkCfg(Structure):
     _fields_ = [("start_lo", c_int64), ("start_hi", c_int64), ("walks_per_node", c_int32),
                 ("max_walk_length", c_int32), ("p_halt", c_double), ("draw_mode", c_int32), ("load_mode", c_int32),
-                ("seed", c_uint64), ("trace_u", c_void_p), ("trace_k", c_void_p), ("scaled_val", c_void_p)]
+                ("seed", c_uint64), ("trace_u", c_void_p), ("trace_k", c_void_p), ("scaled_val", c_void_p), ("col_counts", c_void_p)]
 
 
 class GrfLongRows(Structure):
@@ -118,7 +118,7 @@ def lib():
     L.grf_transpose_workspace_bytes.restype = i64
     L.grf_transpose_workspace_bytes.argtypes = [i64, i32]
     L.grf_transpose_offsets.restype = i32
-    L.grf_transpose_offsets.argtypes = [vp, vp, i64, i64, i32, vp, vp, i32, vp, vp]
+    L.grf_transpose_offsets.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, i32, vp, vp]
     L.grf_transpose_fill.restype = i32
     L.grf_transpose_fill.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, vp]
     L.grf_phi_matvec.restype = i32

@@ -197,6 +197,7 @@ class Staging:
     n_rows: int
     row_lo: int
     visits: torch.Tensor      # int64 [1] walk-steps executed
+    col_counts: Optional[torch.Tensor] = None   # int32 [n_nodes * L] entries per (column, length), if counted
 
 
 def scan_counts(row_cnt: torch.Tensor, n_rows: int, n_steps: int, order: int, i64: bool,
@@ -213,8 +214,11 @@ def scan_counts(row_cnt: torch.Tensor, n_rows: int, n_steps: int, order: int, i6
 
 
 def run_walker(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
-               visits: Optional[torch.Tensor] = None) -> Staging:
-    """One grf_walk launch over start nodes [start_lo, start_hi)."""
+               visits: Optional[torch.Tensor] = None, col_counts: Optional[torch.Tensor] = None,
+               count_columns: bool = False) -> Staging:
+    """One grf_walk launch over start nodes [start_lo, start_hi).  ``count_columns`` (or a zeroed /
+    partially accumulated ``col_counts`` int32 [n_nodes * L]) also counts the entries per (column,
+    length) while they are emitted: the segment sizes of the Phi^T blocks, for free."""
     cfg.validate()
     L = _lib.lib()
     dev = graph.device
@@ -226,6 +230,8 @@ def run_walker(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi:
     row_cnt = torch.empty(max(1, n_rows * cfg.max_walk_length), dtype=torch.int32, device=dev)
     if visits is None:
         visits = torch.zeros(1, dtype=torch.int64, device=dev)
+    if col_counts is None and count_columns:
+        col_counts = torch.zeros(max(1, graph.n_nodes * cfg.max_walk_length), dtype=torch.int32, device=dev)
     tu = tk = None
     if cfg.draw_mode == _lib.DRAW_REPLAY:
         tu = torch.as_tensor(cfg.trace[0], dtype=torch.float64).to(dev).contiguous()
@@ -240,10 +246,11 @@ def run_walker(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi:
     c = GrfWalkCfg(start_lo, start_hi, cfg.walks_per_node, cfg.max_walk_length, float(cfg.p_halt), cfg.draw_mode,
                    cfg.load_mode, int(cfg.seed) & 0xFFFFFFFFFFFFFFFF,
                    None if tu is None else tu.data_ptr(), None if tk is None else tk.data_ptr(),
-                   None if scaled is None else scaled.data_ptr())
+                   None if scaled is None else scaled.data_ptr(),
+                   None if col_counts is None else col_counts.data_ptr())
     check(L.grf_walk(ctypes.byref(g), ctypes.byref(c), stride, _ptr(stage_col), _ptr(stage_sum), _ptr(row_cnt),
                      _ptr(visits), _stream(dev)))
-    return Staging(stage_col, stage_sum, row_cnt, stride, n_rows, start_lo, visits)
+    return Staging(stage_col, stage_sum, row_cnt, stride, n_rows, start_lo, visits, col_counts)
 
 
 def _row_chunks(start_lo: int, start_hi: int, stride: int, max_stage_bytes: int):
@@ -403,6 +410,7 @@ class PhiBlocks:
         self.dynamic_rows = os.environ.get("GRF_B200_DYNAMIC", "1") != "0"
         self._sched = None
         self._census = None     # (pinned int32[6], event): row statistics of both sides, see _start_census
+        self._col_counts = None  # int32 [n_cols * L] from the walker (GrfWalkCfg.col_counts), used once by build_transpose
         self.visits = visits
         self._union = None
         self._tcols = None      # non-empty columns of this shard (int32) when that is a small fraction of N
@@ -436,7 +444,9 @@ class PhiBlocks:
         self.tentries = torch.empty((max(1, self.nnz), 2), dtype=torch.int32, device=dev)[: self.nnz]
         host = torch.empty(6, dtype=torch.int32, pin_memory=True) if self.nnz else None
         check(L.grf_transpose_offsets(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
-                                      _ptr(self.tblk_ptr), _ptr(ws), LONG_ROW_THRESHOLD, _ptr(host), st))
+                                      _ptr(self._col_counts), _ptr(self.tblk_ptr), _ptr(ws), LONG_ROW_THRESHOLD,
+                                      _ptr(host), st))
+        self._col_counts = None
         if host is not None:
             arrived = torch.cuda.Event()
             arrived.record(torch.cuda.current_stream(dev))
@@ -808,7 +818,9 @@ def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: 
     check(_lib.lib().grf_compact_blocks(_ptr(st.stage_col), _ptr(st.stage_sum), _ptr(st.row_cnt), _ptr(blk_ptr),
                                         st.n_rows, L, st.stride, cfg.walks_per_node, scale_mode, _ptr(entries),
                                         _stream(dev)))
-    return PhiBlocks(blk_ptr, entries, st.n_rows, n_cols, L, st.row_lo)
+    phi = PhiBlocks(blk_ptr, entries, st.n_rows, n_cols, L, st.row_lo)
+    phi._col_counts = st.col_counts
+    return phi
 
 
 def build_phi_blocks(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
@@ -819,12 +831,16 @@ def build_phi_blocks(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, sta
     start_hi = graph.n_nodes if start_hi is None else start_hi
     stride = _lib.lib().grf_walk_stage_stride(cfg.walks_per_node, cfg.max_walk_length)
     visits = torch.zeros(1, dtype=torch.int64, device=graph.device)
+    col_counts = None
+    if transpose:   # the walker counts the Phi^T segment sizes while it emits the entries
+        col_counts = torch.zeros(max(1, graph.n_nodes * cfg.max_walk_length), dtype=torch.int32, device=graph.device)
     parts = []
     for lo, hi in _row_chunks(start_lo, start_hi, stride, max_stage_bytes):
-        st = run_walker(graph, cfg, lo, hi, visits=visits)
+        st = run_walker(graph, cfg, lo, hi, visits=visits, col_counts=col_counts)
         parts.append(_blocks_from_staging(st, cfg, graph.n_nodes, scale_mode))
         del st
     phi = PhiBlocks.concat_rows(parts)
+    phi._col_counts = col_counts
     phi.row_lo = start_lo
     phi.visits = visits  # device counter; int(phi.visits) syncs
     return phi.build_transpose() if transpose else phi

@@ -92,6 +92,10 @@ typedef struct {
     const int32_t *trace_k;
     /* optional: (deg(row) * val) / (1 - p_halt) per edge from grf_edge_scale (NULL: computed per step) */
     const double *scaled_val;
+    /* optional (device int32 [n_nodes][L], zeroed by the caller before the first launch of a shard):
+     * += 1 per emitted entry at (column, length) -- the segment sizes of the Phi^T blocks, so that
+     * grf_transpose_offsets need not re-read the entries to count them */
+    int32_t *col_counts;
 } GrfWalkCfg;
 
 /* Optional split of long rows (hub columns of a power-law Phi^T hold 10^5..10^6 entries): rows
@@ -227,8 +231,9 @@ int grf_nonempty_rows(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, i
  *                          `cursor` = the same workspace (its first n_cols*L + 2 ints) */
 int64_t grf_transpose_workspace_bytes(int64_t n_cols, int32_t n_steps);
 int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                          int32_t n_steps, int32_t *tblk_ptr, void *workspace, int32_t census_threshold,
-                          int32_t *census_host, void *stream);
+                          int32_t n_steps, const int32_t *col_counts /* from GrfWalkCfg, or NULL: counted here */,
+                          int32_t *tblk_ptr, void *workspace, int32_t census_threshold, int32_t *census_host,
+                          void *stream);
 int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
                        int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor /* [n_cols*L + 2] scratch */,
                        GrfEntry *tentries, void *stream);
