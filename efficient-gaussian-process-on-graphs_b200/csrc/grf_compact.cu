@@ -281,22 +281,58 @@ __device__ __forceinline__ void sort_segment_regs(GrfEntry *seg, int len) {
 }
 
 // lists: [0] = number of mid segments, [1] = number of long segments, then the two lists
+//
+// A warp takes 32 consecutive segments (one per lane).  Their entries are one contiguous stretch of
+// tentries: it is copied to shared memory with coalesced 8-byte loads, every lane sorts its own
+// segment there, and the stretch is written back coalesced.  (One thread per segment straight on
+// global memory -- 32 lanes striding through 32 different segments -- took 66 us at config 2.)
+constexpr int kSortStage = 1024;  // entries a warp stages (32 segments of <= 32 entries always fit)
+
 __global__ void __launch_bounds__(128) transpose_sort_short_kernel(const int32_t *tblk_ptr, int64_t n_segs,
                                                                    GrfEntry *tentries, int32_t *counts,
                                                                    int32_t *mid_list, int32_t *long_list) {
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_segs;
-         g += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t b = tblk_ptr[g];
-        const int32_t len = tblk_ptr[g + 1] - b;
-        if (len <= 1) continue;
-        if (len <= kTinySeg) {
-            sort_segment_regs<kTinySeg>(tentries + b, len);
-        } else if (len <= kShortSeg) {
-            sort_segment_regs<kShortSeg>(tentries + b, len);
-        } else if (len <= kMidSeg) {
-            mid_list[atomicAdd(&counts[0], 1)] = (int32_t)g;   // grows upwards
-        } else {
+    __shared__ int2 stage_all[4][kSortStage];
+    const int lane = threadIdx.x & 31;
+    int2 *stage = stage_all[threadIdx.x >> 5];
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int2 *ent2 = reinterpret_cast<int2 *>(tentries);
+    for (int64_t g0 = warp0 * 32; g0 < n_segs; g0 += nwarps * 32) {
+        const int64_t g = g0 + lane;
+        int32_t b = 0, len = 0;
+        if (g < n_segs) {
+            b = tblk_ptr[g];
+            len = tblk_ptr[g + 1] - b;
+        }
+        // longer segments go to the warp / CTA tiers; their entries are staged and written back untouched
+        if (len > kMidSeg)
             long_list[-atomicAdd(&counts[1], 1)] = (int32_t)g;  // grows downwards from the end
+        else if (len > kShortSeg)
+            mid_list[atomicAdd(&counts[0], 1)] = (int32_t)g;   // grows upwards
+        const bool mine = len > 1 && len <= kShortSeg;
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        const int32_t base = __shfl_sync(0xffffffffu, b, 0);
+        const int last = (int)min((int64_t)31, n_segs - 1 - g0);
+        const int32_t total = __shfl_sync(0xffffffffu, b + len, last) - base;
+        const bool staged = total <= kSortStage;
+        GrfEntry *seg = tentries + b;
+        if (staged) {
+            for (int32_t i = lane; i < total; i += 32) stage[i] = ent2[base + i];
+            __syncwarp();
+            seg = reinterpret_cast<GrfEntry *>(stage) + (b - base);
+        }
+        if (mine) {
+            if (len <= kTinySeg)
+                sort_segment_regs<kTinySeg>(seg, len);
+            else if (len <= 16)
+                sort_segment_regs<16>(seg, len);
+            else
+                sort_segment_regs<kShortSeg>(seg, len);
+        }
+        if (staged) {
+            __syncwarp();
+            for (int32_t i = lane; i < total; i += 32) ent2[base + i] = stage[i];
+            __syncwarp();
         }
     }
 }
