@@ -415,6 +415,7 @@ class PhiBlocks:
         self._union = None
         self._tcols = None      # non-empty columns of this shard (int32) when that is a small fraction of N
         self._touched = None    # int32 0/1 per column, set together with _tcols
+        self._tcols_cap = None  # id list with spare capacity, written before the census says how many there are
         # sharded matvec: columns to exchange between the ranks, if known up front (tensor of ids or
         # "all"; DeviceGraph.shared_columns); None = the plan finds them with one all-reduce
         self.shared_hint = None
@@ -453,7 +454,20 @@ class PhiBlocks:
             self._census = (host, arrived)
         check(L.grf_transpose_fill(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
                                    _ptr(self.tblk_ptr), _ptr(ws), _ptr(self.tentries), st))
+        if self.nnz and self.n_rows < self.n_cols:
+            # a row shard: list its non-empty columns now (capacity n_cols, the census gives the length
+            # later), while the host would otherwise wait for the fill / sort kernels
+            self._list_nonempty_columns(self.n_cols)
         return self
+
+    def _list_nonempty_columns(self, capacity: int) -> None:
+        lib, dev = _lib.lib(), self.device
+        self._touched = torch.empty(self.n_cols, dtype=torch.int32, device=dev)
+        pos = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
+        ws = torch.empty(lib.grf_scan_workspace_bytes(self.n_cols), dtype=torch.uint8, device=dev)
+        self._tcols_cap = torch.empty(max(1, capacity), dtype=torch.int32, device=dev)
+        check(lib.grf_nonempty_rows(_ptr(self.tblk_ptr), self.n_cols, self.n_steps, _ptr(self._touched), _ptr(pos),
+                                    _ptr(ws), _ptr(self._tcols_cap), _stream(dev)))
 
     def _start_census(self) -> None:
         """Row statistics of both sides for Phi blocks that did not come through build_transpose()."""
@@ -579,13 +593,12 @@ class PhiBlocks:
                 self._long[1] = self._long_rows_of(self.tblk_ptr, self.n_cols)
             # columns this (row) shard touches: worth a list when most of the N columns are empty
             if cols_used < 0.75 * self.n_cols:
-                lib, dev = _lib.lib(), self.device
-                self._touched = torch.empty(self.n_cols, dtype=torch.int32, device=dev)
-                pos = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
-                ws = torch.empty(lib.grf_scan_workspace_bytes(self.n_cols), dtype=torch.uint8, device=dev)
-                self._tcols = torch.empty(cols_used, dtype=torch.int32, device=dev)
-                check(lib.grf_nonempty_rows(_ptr(self.tblk_ptr), self.n_cols, L, _ptr(self._touched), _ptr(pos),
-                                            _ptr(ws), _ptr(self._tcols), _stream(dev)))
+                if self._tcols_cap is None:
+                    self._list_nonempty_columns(cols_used)
+                self._tcols = self._tcols_cap[:cols_used]
+            else:
+                self._touched = None
+            self._tcols_cap = None
         return self
 
     def _long_structs(self, ld: int):
