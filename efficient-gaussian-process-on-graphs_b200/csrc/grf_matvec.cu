@@ -208,10 +208,11 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
                                                           int32_t t_store, int32_t vec_store, int32_t long_thresh,
                                                           const int2 *__restrict__ chunk_bounds,
                                                           int32_t out_by_row, int32_t *__restrict__ sched) {
-    // sched != NULL: {ticket, finished warps}, both zero at launch and zero again at exit.  Every warp
-    // runs ~11 gather rounds of ~1.6 us at config 2, so with a fixed stride the SMs finish several
-    // rounds apart (ncu: L1 busy 77 % of its active cycles but 58 % of the elapsed ones); the last
-    // rows are therefore handed out by an atomic ticket, fetched one iteration ahead.
+    // sched != NULL: {ticket, finished warps}, both zero at launch and zero again at exit.  The first
+    // GRF_SPMM_STATIC_PCT % of the row groups go to the warps by fixed stride (neighbouring rows stay
+    // on one SM), the rest by an atomic ticket fetched one iteration ahead: with skewed row lengths
+    // (power-law graphs) a fixed stride leaves SMs idle at the end (R-MAT 2^20: 2.92 -> 2.48 ms per
+    // product); on the uniform rows of config 2 it changes nothing.
     // out_by_row: row_ids lists the non-empty rows and task k writes Y[row_ids[k]] (Phi^T of a row
     // shard touches only a fraction of the N columns); otherwise task k writes Y[k].
     // t = columns computed (a multiple of VEC; the operands are padded to it), t_store <= t = columns
@@ -952,9 +953,10 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             }
             if (!tiled) {
                 int rc;
-                if (phi->tcols && phi->n_tcols < phi->n_cols) {
-                    // only the columns this shard touches; the others are zero
-                    GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
+                if (phi->tcols) {
+                    // only the listed columns (those this shard touches, in any order); the others are zero
+                    if (phi->n_tcols < phi->n_cols)
+                        GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
                     rc = phi->n_tcols == 0
                              ? GRF_OK
                              : launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, phi->tcols, phi->n_tcols, 0,
