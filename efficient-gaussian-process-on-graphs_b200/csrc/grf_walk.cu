@@ -94,7 +94,8 @@ __device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) 
 // KPL = keys per lane of the warp-per-node variant (sort width 32*KPL >= W); 0 for the
 // CTA-per-node variant, which sorts in shared memory.
 #ifndef GRF_WALK_MINBLOCKS
-#define GRF_WALK_MINBLOCKS 7  // 66 registers, no spills; 1 (80 registers, 6 CTAs/SM): 804 us, 7: 590, 8: 591, 9: 602 at config 2
+#define GRF_WALK_MINBLOCKS 5  // register cap for the warp-per-node variant (walk-steps/s: grid config 2 | R-MAT 2^20 nodes)
+// 1 or 4: 85 registers 97 G | 37 G;  5: 74 registers 102 G | 45 G;  6 or 7: 58-60 registers 102 G | 30 G
 #endif
 // kFast: Philox draws, cumulative load, per-edge factors precomputed (the production setting) --
 // strips the per-step mode tests; the generic instantiation serves replay / ablation / sequential.

@@ -46,7 +46,7 @@ g = engine.DeviceGraph.from_scipy(lap)
 torch.cuda.synchronize()
 print(f"H2D graph {time.perf_counter()-t3:.2f}s", flush=True)
 cfg = engine.WalkConfig(W, 0.1, L, seed=42)
-for rep in range(2):
+for rep in range(int(os.environ.get("GRF_REPS", "2"))):
     torch.cuda.synchronize(); t4 = time.perf_counter()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
