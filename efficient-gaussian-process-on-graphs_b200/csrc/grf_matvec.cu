@@ -270,12 +270,25 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
     const int lane = threadIdx.x & 31;
     const int32_t n_warps = (int32_t)warp_stride;
     const int32_t n_iters = (int32_t)((n_tasks + kGroupsPerWarp - 1) / kGroupsPerWarp);
-    // iterations [0, n_static) go by stride (neighbouring rows stay on one SM), the rest by ticket
-    int32_t n_static = 0x7fffffff - n_warps;
-    int32_t ticket_base = 0;
-    if (sched) {
-        n_static = (int32_t)((int64_t)n_iters * GRF_SPMM_STATIC_PCT / 100) / n_warps * n_warps;
-        ticket_base = n_static > n_warps ? n_static : n_warps;
+    // Iterations [0, n_static) are assigned up front, the rest by ticket.  The static part gives
+    // every SM ONE contiguous range of rows, which its resident warps walk interleaved (warp j of
+    // the SM takes range_begin + j, + warps_per_sm, ...): at any moment an SM works on ~128
+    // consecutive rows and its window of X slides, so a banded Phi re-reads X from L1, not L2
+    // (with a grid-wide stride every iteration of a warp landed in a fresh window).
+    const int32_t n_static = sched ? (int32_t)((int64_t)n_iters * GRF_SPMM_STATIC_PCT / 100) : n_iters;
+    int32_t it, it_step, it_end;
+    if (gridDim.x % kSmCount == 0) {
+        const int warps_per_block = blockDim.x >> 5;
+        const int per_sm = gridDim.x / kSmCount;
+        const int sm = blockIdx.x % kSmCount;  // CTAs s, s + 148, ... share an SM (round-robin placement)
+        const int32_t q = (n_static + kSmCount - 1) / kSmCount;
+        it = sm * q + (blockIdx.x / kSmCount) * warps_per_block + (threadIdx.x >> 5);
+        it_step = per_sm * warps_per_block;
+        it_end = min((sm + 1) * q, n_static);
+    } else {
+        it = (int32_t)warp0;
+        it_step = n_warps;
+        it_end = n_static;
     }
     auto finish = [&]() {
         if (sched && lane == 0) {
@@ -285,20 +298,26 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
             }
         }
     };
-    int32_t it = (int32_t)warp0;
+    auto ticket = [&]() {
+        int32_t tk = 0;
+        if (lane == 0) tk = n_static + atomicAdd(sched, 1);
+        return __shfl_sync(0xffffffffu, tk, 0);
+    };
+    bool static_next = true;  // `itn` still belongs to this warp's static sequence
+    if (it >= it_end) {
+        it = sched ? ticket() : n_iters;
+        static_next = false;
+    }
     if (it >= n_iters) {
         finish();
         return;
     }
     int32_t itn;
-    if (it + n_warps < n_static) {
-        itn = it + n_warps;
-    } else if (!sched) {
-        itn = n_iters;
+    if (static_next && it + it_step < it_end) {
+        itn = it + it_step;
     } else {
-        int32_t tk = 0;
-        if (lane == 0) tk = ticket_base + atomicAdd(sched, 1);
-        itn = __shfl_sync(0xffffffffu, tk, 0);
+        itn = sched ? ticket() : n_iters;
+        static_next = false;
     }
     int32_t b, e, nb, ne;
     bool mine, nmine;
@@ -307,10 +326,12 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
     int2 nxt[epl(TPR)];
     load_first_round<TPR>(ent2, b, e, sub, nxt);
     while (it < n_iters) {
-        // the iteration after next: known by stride, or a ticket whose latency this iteration hides
-        const bool draw = sched && itn + n_warps >= n_static;
+        // the iteration after next: the next one of the static sequence, or a ticket whose latency
+        // this iteration hides
+        const int32_t after = static_next && itn + it_step < it_end ? itn + it_step : -1;
+        const bool draw = sched && after < 0;
         int32_t tk = 0;
-        if (draw && lane == 0) tk = ticket_base + atomicAdd(sched, 1);
+        if (draw && lane == 0) tk = n_static + atomicAdd(sched, 1);
         bounds((int64_t)itn * kGroupsPerWarp + g_in_warp, nb, ne, nmine, norow);
         for (int tile = 0; tile < n_tiles; ++tile) {
             // lanes whose columns fall outside t (t not a multiple of TPR*VEC) still help with the
@@ -327,7 +348,12 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
         mine = nmine;
         orow = norow;
         it = itn;
-        itn = draw ? __shfl_sync(0xffffffffu, tk, 0) : (sched || itn + n_warps < n_iters ? itn + n_warps : n_iters);
+        if (after >= 0) {
+            itn = after;
+        } else {
+            itn = draw ? __shfl_sync(0xffffffffu, tk, 0) : n_iters;
+            static_next = false;
+        }
     }
     finish();
 }
