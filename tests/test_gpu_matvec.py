@@ -104,6 +104,30 @@ def test_transpose_with_hub_columns_uses_the_long_segment_sort(env):
     assert sum(m.nnz for m in back) == len(rows)
 
 
+def test_transpose_sorts_segments_longer_than_the_shared_memory_stage(env):
+    """A star: every row reaches the hub, so the hub's (column, length) segments hold ~n entries --
+    more than the 16384 the long-segment sort stages in shared memory (tiled path), and sizes
+    (1024, 4096] / (4096, 16384] appear on the way there."""
+    eng = env["eng"]
+    for n in (3000, 12000, 40000):
+        leaves = np.arange(1, n)
+        adj = sp.csr_matrix((np.ones(2 * (n - 1)), (np.r_[np.zeros(n - 1, dtype=np.int64), leaves],
+                                                    np.r_[leaves, np.zeros(n - 1, dtype=np.int64)])), shape=(n, n))
+        lap = env["o"].normalized_laplacian_sparse(adj)
+        g = eng.DeviceGraph.from_scipy(lap)
+        phi = eng.build_phi_blocks(g, eng.WalkConfig(8, 0.1, 3, seed=5))
+        tptr = phi.tblk_ptr.cpu().numpy().astype(np.int64)
+        seg = np.diff(tptr)
+        assert seg.max() > 0.5 * n
+        rows = phi.tentries.cpu().numpy()[:, 0] & ((1 << 27) - 1)
+        for g0 in np.flatnonzero(seg > 1):
+            r = rows[tptr[g0]:tptr[g0 + 1]]
+            assert np.all(r[1:] > r[:-1]), (n, g0, seg[g0])
+        want = sp.vstack([m for m in phi.to_scipy_steps()]).tocsc()      # same multiset, column by column
+        got_cols = np.repeat(np.arange(n), np.add.reduceat(seg, np.arange(0, seg.size, 3)))
+        assert np.array_equal(np.bincount(got_cols, minlength=n), np.diff(want.indptr))
+
+
 @pytest.mark.parametrize("t", [1, 2, 3, 4, 8, 12, 16, 17, 32, 64, 65, 130])
 def test_matvec_matches_float64(env, case, t):
     torch, o = env["torch"], env["o"]
