@@ -395,9 +395,9 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * red[5] / e2e_steps,
                     "what": "SparseRandomWalk(host scipy CSR) -> list of host scipy CSR step matrices, plus one "
                             "host-V -> Phi(Phi^T V) -> host matvec"},
-            "gpu_launches": K * 17,
+            "gpu_launches": K * 18,
             "gpu_launches_per_step": {"walk_merge": 1, "scan": 3 + 3, "compact_blocks": 1,
-                                      "transpose_count_fill_sort": 5, "row_census": 2, "spmm_blocks": 2},
+                                      "transpose_fill": 1, "transpose_sort": 5, "row_census": 2, "spmm_blocks": 2},
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:

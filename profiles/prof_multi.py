@@ -23,6 +23,8 @@ cfg = engine.WalkConfig(bench.W, bench.P_HALT, bench.L, seed=bench.SEED)
 f = torch.randn(bench.L, device=dev)
 v = torch.randn(hi - lo, 16, device=dev)
 out = torch.empty_like(v)
+bounds = [r * per for r in range(world)] + [n]
+hint = g.shared_columns(bounds, bench.L)
 acc = {}
 
 
@@ -34,7 +36,11 @@ def timed(name, fn):
 
 
 for it in range(8):
-    phi = engine.build_phi_blocks(g, cfg, lo, hi, transpose=False)
+    st = engine.run_walker(g, cfg, lo, hi, count_columns=True)
+    phi = engine._blocks_from_staging(st, cfg, g.n_nodes, 0)
+    del st
+    phi.row_lo = lo
+    phi.shared_hint = hint
     dist.barrier(); torch.cuda.synchronize()
     timed("transpose", lambda: phi.build_transpose())
     timed("long_rows+tcols", lambda: phi.build_long_rows())
