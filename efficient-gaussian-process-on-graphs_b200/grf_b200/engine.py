@@ -27,6 +27,7 @@ from ._lib import GrfGraph, GrfLongRows, GrfPhi, GrfWalkCfg, check
 
 LONG_ROW_THRESHOLD = 256   # rows of Phi / Phi^T with more entries are split into chunks of this size
 _MAX_STAGE_BYTES = 6 << 30  # staging budget per walker launch; larger shards are walked in row chunks
+_LAZY_ENTRY_BYTES = 1 << 30  # up to this bound the Phi entries are allocated by capacity (no host wait for the count)
 
 
 def _device(device=None) -> torch.device:
@@ -40,6 +41,16 @@ def _device(device=None) -> torch.device:
     if device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
     return device
+
+
+_pending_host = []
+
+
+def _keep_until_done(buf: torch.Tensor, event: torch.cuda.Event) -> None:
+    """The C library copies into ``buf`` (pinned) asynchronously, which torch's host allocator does
+    not see: hold a reference until the copy's event has completed, whoever drops the owner first."""
+    _pending_host[:] = [(b, e) for b, e in _pending_host if not e.query()]
+    _pending_host.append((buf, event))
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -396,7 +407,8 @@ class PhiBlocks:
     def __init__(self, blk_ptr, entries, n_rows, n_cols, n_steps, row_lo=0, visits=0):
         if max(n_rows, n_cols) > (1 << _lib.ENTRY_STEP_SHIFT) or n_steps > (1 << (32 - _lib.ENTRY_STEP_SHIFT)):
             raise ValueError("Phi blocks hold at most 2^27 rows/columns per GPU and 32 walk lengths")
-        self.blk_ptr, self.entries = blk_ptr, entries
+        self.blk_ptr, self._entries = blk_ptr, entries
+        self._nnz_pending = None   # (pinned int64[1], event): `_entries` has spare capacity until this resolves
         self.n_rows, self.n_cols, self.n_steps, self.row_lo = n_rows, n_cols, n_steps, row_lo
         self.tblk_ptr = None
         self.tentries = None
@@ -428,6 +440,23 @@ class PhiBlocks:
         return self.blk_ptr.device
 
     @property
+    def entries(self) -> torch.Tensor:
+        """[nnz, 2] int32 view of the {length << 27 | col, value bits} pairs.  A Phi built straight from
+        staging holds a capacity-sized buffer until the entry count -- copied to pinned host memory behind
+        the offset scan -- is first needed; by then the compaction kernel is already queued, so reading
+        it does not idle the GPU."""
+        if self._nnz_pending is not None:
+            host, arrived = self._nnz_pending
+            arrived.synchronize()
+            self._nnz_pending = None
+            self._entries = self._entries[: int(host[0])]
+        return self._entries
+
+    @entries.setter
+    def entries(self, value: torch.Tensor) -> None:
+        self._entries, self._nnz_pending = value, None
+
+    @property
     def nnz(self) -> int:
         return int(self.entries.shape[0])
 
@@ -452,6 +481,7 @@ class PhiBlocks:
             arrived = torch.cuda.Event()
             arrived.record(torch.cuda.current_stream(dev))
             self._census = (host, arrived)
+            _keep_until_done(host, arrived)
         check(L.grf_transpose_fill(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
                                    _ptr(self.tblk_ptr), _ptr(ws), _ptr(self.tentries), st))
         if self.nnz and self.n_rows < self.n_cols:
@@ -824,14 +854,27 @@ def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: 
     L = cfg.max_walk_length
     dev = st.stage_col.device
     blk_ptr, total = scan_counts(st.row_cnt, st.n_rows, L, _lib.ORDER_ROW_MAJOR, i64=False, with_total=True)
-    total = int(total.item())
-    if total >= 2 ** 31:
-        raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
-    entries = torch.empty((max(1, total), 2), dtype=torch.int32, device=dev)[:total]
+    capacity = st.n_rows * st.stride            # one entry per staging slot at most
+    pending = None
+    if 0 < capacity * 8 <= _LAZY_ENTRY_BYTES:
+        # small shard: allocate the bound, launch the compaction, and let the count arrive on the side
+        host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+        host.copy_(total, non_blocking=True)
+        arrived = torch.cuda.Event()
+        arrived.record(torch.cuda.current_stream(dev))
+        _keep_until_done(host, arrived)
+        pending = (host, arrived)
+        entries = torch.empty((capacity, 2), dtype=torch.int32, device=dev)
+    else:
+        total = int(total.item())
+        if total >= 2 ** 31:
+            raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
+        entries = torch.empty((max(1, total), 2), dtype=torch.int32, device=dev)[:total]
     check(_lib.lib().grf_compact_blocks(_ptr(st.stage_col), _ptr(st.stage_sum), _ptr(st.row_cnt), _ptr(blk_ptr),
                                         st.n_rows, L, st.stride, cfg.walks_per_node, scale_mode, _ptr(entries),
                                         _stream(dev)))
     phi = PhiBlocks(blk_ptr, entries, st.n_rows, n_cols, L, st.row_lo)
+    phi._nnz_pending = pending
     phi._col_counts = st.col_counts
     return phi
 

@@ -67,3 +67,43 @@ def test_no_cpu_fallback():
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         DeviceGraph(np.zeros(2, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0), 1)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct in include/grf_b200.h, as a C compiler sees them, equal the
+    ctypes mirrors in grf_b200/_lib.py (the header is plain C: it must compile with gcc)."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from grf_b200 import _lib
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"GrfEntry": None, "GrfGraph": _lib.GrfGraph, "GrfWalkCfg": _lib.GrfWalkCfg,
+               "GrfLongRows": _lib.GrfLongRows, "GrfPhi": _lib.GrfPhi}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grf_b200.h"', 'int main(void) {']
+    for name, mirror in structs.items():
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        if mirror is not None:
+            for field, _ in mirror._fields_:
+                lines.append(f'  printf("{name} {field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", _lib.INCLUDE, "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True)
+    seen = 0
+    for line in out.splitlines():
+        name, what, value = line.split()
+        mirror = structs[name]
+        if mirror is None:
+            assert what == "size" and int(value) == 8
+            continue
+        if what == "size":
+            assert ctypes.sizeof(mirror) == int(value), name
+        else:
+            assert getattr(mirror, what).offset == int(value), (name, what)
+        seen += 1
+    assert seen == sum(1 + len(m._fields_) for m in structs.values() if m is not None)

@@ -407,3 +407,32 @@ def test_frobenius_error_matches_reference_level(env):
     err_ref = np.mean([o.compute_fro(exact, o.grf_kernel_sparse(adj, f, 50, 0.1, 3, n_processes=2).toarray())])
     err_gpu = o.compute_fro(exact, fast_general_grf_kernel(adj, f, 50, 0.1, 3).toarray())
     assert abs(err_gpu - err_ref) <= 0.25 * err_ref, (err_gpu, err_ref)
+
+
+def test_integration_md_binding_runs_and_matches_the_oracle():
+    """The ctypes stub INTEGRATION.md tells a reference maintainer to add is executed as written
+    (only the library path is substituted) and must give the oracle's native-mode step matrices."""
+    import os
+    import re
+
+    import torch
+
+    assert torch.cuda.is_available()
+    from grf_b200 import _lib
+    from oracle import c_oracle, grf_oracle
+
+    _lib.lib()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# efficient_graph_gp_sparse/random_walk_samplers_sparse/_grf_b200\.py.*?)```", text, re.S).group(1)
+    code = code.replace('ctypes.CDLL("libgrf_b200.so")', f'ctypes.CDLL({_lib.SO_PATH!r})')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    lap = grf_oracle.normalized_laplacian_sparse(random_graph(300, 900, 3, weighted=True)).tocsr()
+    W, p, L, seed = 20, 0.1, 4, 7
+    got = ns["step_matrices"](lap.indptr, lap.indices, lap.data, lap.shape[0], W, p, L, seed)
+    want = c_oracle.step_matrices(lap, W, p, L, seed=seed)
+    assert len(got) == L
+    for a, b in zip(got, want):
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+        assert np.array_equal(a.data.view(np.int64), b.data.view(np.int64))
