@@ -227,15 +227,7 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
     const int sub = threadIdx.x % TPR;
     constexpr int kGroupsPerWarp = 32 / TPR;
     const int g_in_warp = (threadIdx.x & 31) / TPR;
-    // CTAs are handed to the SMs round-robin, so blockIdx = s, s + 148, s + 296 ... share an SM (and
-    // its L1).  Give those CTAs NEIGHBOURING rows: for a banded Phi their gathers then hit the same
-    // lines of X.  (Only a locality hint: correctness does not depend on the placement.)
-    int logical_block = blockIdx.x;
-    if (gridDim.x % kSmCount == 0) {
-        const int per_sm = gridDim.x / kSmCount;
-        logical_block = (blockIdx.x % kSmCount) * per_sm + blockIdx.x / kSmCount;
-    }
-    const int64_t warp0 = ((int64_t)logical_block * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
     const int n_tiles = (t + TPR * VEC - 1) / (TPR * VEC);
@@ -280,7 +272,9 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
     if (gridDim.x % kSmCount == 0) {
         const int warps_per_block = blockDim.x >> 5;
         const int per_sm = gridDim.x / kSmCount;
-        const int sm = blockIdx.x % kSmCount;  // CTAs s, s + 148, ... share an SM (round-robin placement)
+        // CTAs are handed to the SMs round-robin, so blockIdx = s, s + 148, ... share an SM and its L1
+        // (only a locality hint: correctness does not depend on the placement)
+        const int sm = blockIdx.x % kSmCount;
         const int32_t q = (n_static + kSmCount - 1) / kSmCount;
         it = sm * q + (blockIdx.x / kSmCount) * warps_per_block + (threadIdx.x >> 5);
         it_step = per_sm * warps_per_block;
