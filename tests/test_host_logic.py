@@ -119,3 +119,31 @@ def test_cg_restatement_solves_spd_systems():
     assert np.allclose(xt.numpy(), np.linalg.solve(a, b), rtol=1e-3, atol=1e-4) and info["iterations"] >= 10
     x1 = linear_cg(lambda v: at @ v, torch.tensor(b[:, 0], dtype=torch.float32), tolerance=1e-6)
     assert x1.shape == (40,)
+
+
+def test_walk_config_validation_and_row_chunks():
+    """Host-side argument checks of the engine (no GPU needed) and the row chunking that keeps the
+    staging of one walker launch under its byte budget."""
+    from grf_b200 import engine
+
+    for bad in (dict(walks_per_node=0, p_halt=0.1, max_walk_length=3),
+                dict(walks_per_node=5, p_halt=0.1, max_walk_length=0),
+                dict(walks_per_node=5, p_halt=1.5, max_walk_length=3),
+                dict(walks_per_node=5, p_halt=-0.1, max_walk_length=3)):
+        with pytest.raises(ValueError):
+            engine.WalkConfig(**bad).validate()
+    with pytest.raises(ValueError):
+        engine.WalkConfig(5, 0.1, 3, draw_mode=engine._lib.DRAW_REPLAY).validate()   # replay without a trace
+    engine.WalkConfig(5, 0.0, 1).validate()
+    engine.WalkConfig(5, 1.0, 3).validate()
+
+    stride = 401                                   # W = 100, L = 5
+    chunks = list(engine._row_chunks(10, 1_000_010, stride, 6 << 30))
+    assert chunks[0][0] == 10 and chunks[-1][1] == 1_000_010
+    assert all(a[1] == b[0] for a, b in zip(chunks[:-1], chunks[1:]))
+    assert all((hi - lo) * stride * 12 <= 6 << 30 for lo, hi in chunks)
+    assert len(chunks) == 1
+    chunks = list(engine._row_chunks(0, 4_194_304, stride, 6 << 30))
+    assert len(chunks) > 1 and sum(hi - lo for lo, hi in chunks) == 4_194_304
+    assert all((hi - lo) * stride * 12 <= 6 << 30 for lo, hi in chunks)
+    assert list(engine._row_chunks(7, 7, stride, 6 << 30)) == [(7, 7)]       # empty shard: one empty chunk
