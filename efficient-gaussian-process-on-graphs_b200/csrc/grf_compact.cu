@@ -210,16 +210,20 @@ __global__ void __launch_bounds__(256) blocks_from_steps_kernel(const int64_t *o
 // ---------------------------------------------------------------------------
 // Phi^T blocks
 // ---------------------------------------------------------------------------
+// A row's L per-length segments are contiguous and every entry carries its length in the top bits
+// of `col`, so a warp takes the whole row as one flat run: ~2 rounds of 32 entries per row at
+// config 2 instead of one (mostly short) round per length -- the kernels are bound by the latency
+// of the atomic round trips, i.e. by the number of rounds.
 __global__ void __launch_bounds__(256) transpose_count_kernel(const int32_t *blk_ptr, const GrfEntry *entries,
                                                               int64_t n_rows, int32_t L, int32_t *tcnt) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        for (int s = 0; s < L; ++s) {
-            const int32_t b = blk_ptr[r * L + s], e = blk_ptr[r * L + s + 1];
-            for (int32_t i = b + lane; i < e; i += 32)
-                atomicAdd(&tcnt[(int64_t)entry_col(entries[i].col) * L + s], 1);
+        const int32_t b = blk_ptr[r * L], e = blk_ptr[(r + 1) * L];
+        for (int32_t i = b + lane; i < e; i += 32) {
+            const int32_t packed = entries[i].col;
+            atomicAdd(&tcnt[(int64_t)entry_col(packed) * L + entry_step(packed)], 1);
         }
     }
 }
@@ -231,16 +235,15 @@ __global__ void __launch_bounds__(256) transpose_fill_kernel(const int32_t *blk_
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        for (int s = 0; s < L; ++s) {
-            const int32_t b = blk_ptr[r * L + s], e = blk_ptr[r * L + s + 1];
-            for (int32_t i = b + lane; i < e; i += 32) {
-                const GrfEntry src = entries[i];
-                const int32_t slot = atomicAdd(&cursor[(int64_t)entry_col(src.col) * L + s], 1);
-                GrfEntry dst;
-                dst.col = pack_col((int32_t)r, s);
-                dst.val = src.val;
-                tentries[slot] = dst;
-            }
+        const int32_t b = blk_ptr[r * L], e = blk_ptr[(r + 1) * L];
+        for (int32_t i = b + lane; i < e; i += 32) {
+            const GrfEntry src = entries[i];
+            const int s = entry_step(src.col);
+            const int32_t slot = atomicAdd(&cursor[(int64_t)entry_col(src.col) * L + s], 1);
+            GrfEntry dst;
+            dst.col = pack_col((int32_t)r, s);
+            dst.val = src.val;
+            tentries[slot] = dst;
         }
     }
 }
