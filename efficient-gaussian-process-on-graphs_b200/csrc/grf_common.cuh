@@ -25,6 +25,47 @@ int check_cuda(cudaError_t err, const char *what);
         if (!(cond)) return ::grf::fail(GRF_ERR_INVALID, __VA_ARGS__); \
     } while (0)
 
+// Every entry point runs on the device that owns `stream`, whatever device is current in the calling
+// thread (a caller that holds cuda:1 tensors while cuda:0 is current would otherwise launch on the
+// wrong device: "invalid resource handle").  The previous device is restored on return.
+struct StreamDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    int rc = GRF_OK;
+    explicit StreamDeviceGuard(void *stream) {
+        int dev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();  // no usable device: argument checks still run, the first CUDA call reports it
+            return;
+        }
+        // the legacy / per-thread default stream handles belong to whatever device is current
+        if (stream == nullptr || stream == (void *)cudaStreamLegacy || stream == (void *)cudaStreamPerThread) return;
+        // a capturing stream is left alone: the capture was begun with its device current, and stream
+        // queries other than this one may invalidate the capture
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        if (cap != cudaStreamCaptureStatusNone) return;
+        if (cudaStreamGetDevice((cudaStream_t)stream, &dev) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        if (dev != prev) {
+            rc = check_cuda(cudaSetDevice(dev), "cudaSetDevice(stream's device)");
+            switched = rc == GRF_OK;
+        }
+    }
+    ~StreamDeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+#define GRF_ON_STREAM_DEVICE(stream)                 \
+    ::grf::StreamDeviceGuard _grf_guard(stream);     \
+    if (_grf_guard.rc != GRF_OK) return _grf_guard.rc
+
 // Phi / Phi^T entries carry their walk length in the top bits of `col`
 // (GRF_ENTRY_STEP_SHIFT in grf_b200.h): the matvec then needs one pointer pair
 // per row instead of one per (row, length).

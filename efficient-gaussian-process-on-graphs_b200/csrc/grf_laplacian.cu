@@ -18,30 +18,65 @@
 
 namespace grf {
 
-// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum), restated
-__device__ double numpy_pairwise_sum(const double *a, int64_t n) {
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum), restated.
+// Blocks of up to 128 elements are summed with 8 accumulators; longer runs are halved recursively
+// (left half rounded down to a multiple of 8) and the two halves added.  The recursion is unrolled
+// onto an explicit stack: a hub row of a power-law graph has 10^5 neighbours, and a recursive device
+// function of that depth overruns the default 1 KB call stack (illegal memory access at 4 M nodes).
+__device__ __forceinline__ double numpy_pairwise_leaf(const double *a, int64_t n) {
     if (n < 8) {
         double res = 0.0;
         for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int64_t i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int64_t i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
     }
-    int64_t n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(numpy_pairwise_sum(a, n2), numpy_pairwise_sum(a + n2, n - n2));
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__device__ double numpy_pairwise_sum(const double *a, int64_t n) {
+    // post-order walk of the halving tree; the current root-to-node path has one node per level, so
+    // the per-level arrays are the whole stack (depth <= log2(2^31 / 128) + 1 < 32)
+    constexpr int kDepth = 32;
+    int64_t right_off[kDepth], right_n[kDepth];
+    double left_sum[kDepth];
+    bool left_done[kDepth];
+    int level = 0;
+    int64_t off = 0, len = n;
+    for (;;) {
+        while (len > 128) {  // descend along left children, remembering the right ones
+            int64_t n2 = len / 2;
+            n2 -= n2 % 8;
+            right_off[level] = off + n2;
+            right_n[level] = len - n2;
+            left_done[level] = false;
+            len = n2;
+            ++level;
+        }
+        double ret = numpy_pairwise_leaf(a + off, len);
+        for (;;) {  // ascend
+            if (level == 0) return ret;
+            const int parent = level - 1;
+            if (!left_done[parent]) {  // that was the parent's left child: its right child is next
+                left_sum[parent] = ret;
+                left_done[parent] = true;
+                off = right_off[parent];
+                len = right_n[parent];
+                break;
+            }
+            ret = __dadd_rn(left_sum[parent], ret);  // right child done: parent = left + right
+            level = parent;
+        }
+    }
 }
 
 // thread per row; the summation order is scipy's (see the header comment)
@@ -145,6 +180,7 @@ static inline int lap_grid(int64_t n, int per_block) {
 using namespace grf;
 
 extern "C" int grf_laplacian_count(const GrfGraph *adj, double *deg, double *dis, int32_t *out_cnt, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream);
     GRF_REQUIRE(adj, "grf_laplacian_count: null graph");
     GRF_REQUIRE(adj->n_nodes >= 0 && adj->n_nodes < (1ll << 31) && adj->nnz < (1ll << 31) - adj->n_nodes,
                 "grf_laplacian_count: graph exceeds int32 index range");
@@ -161,6 +197,7 @@ extern "C" int grf_laplacian_count(const GrfGraph *adj, double *deg, double *dis
 
 extern "C" int grf_laplacian_fill(const GrfGraph *adj, const double *deg, const double *dis, const int32_t *out_ptr,
                                   int32_t *out_col, double *out_val, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream);
     GRF_REQUIRE(adj, "grf_laplacian_fill: null graph");
     if (adj->n_nodes == 0) return GRF_OK;
     GRF_REQUIRE(adj->row_ptr && deg && dis && out_ptr, "grf_laplacian_fill: null buffer");

@@ -347,6 +347,7 @@ extern "C" int64_t grf_walk_stage_stride(int32_t walks_per_node, int32_t max_wal
 
 extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t stage_stride, int32_t *stage_col,
                         double *stage_sum, int32_t *row_cnt, unsigned long long *visits_out, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream);
     using namespace grf;
     GRF_REQUIRE(graph && cfg, "grf_walk: null graph/cfg");
     GRF_REQUIRE(graph->n_nodes >= 0 && graph->n_nodes < (1ll << 31), "grf_walk: n_nodes %lld out of int32 range",
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(256) edge_scale_kernel(const int32_t *__restri
 }  // namespace grf
 
 extern "C" int grf_edge_scale(const GrfGraph *graph, double p_halt, double *scaled_val, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream);
     using namespace grf;
     GRF_REQUIRE(graph, "grf_edge_scale: null graph");
     GRF_REQUIRE(p_halt >= 0.0 && p_halt <= 1.0, "grf_edge_scale: p_halt must be in [0, 1]");

@@ -143,21 +143,26 @@ class DeviceGraph:
         if not a.has_canonical_format:
             a = a.copy()
             a.sum_duplicates()
-        A = cls(a.indptr, a.indices, a.data.astype(float, copy=False), a.shape[0], device)
+        return cls(a.indptr, a.indices, a.data.astype(float, copy=False), a.shape[0], device).laplacian()
+
+    def laplacian(self) -> "DeviceGraph":
+        """D^-1/2 (D - A) D^-1/2 of this graph read as a canonical CSR adjacency (sorted columns, no
+        duplicates), on the device -- no host round trip (graph_utils.py:5-30)."""
         L = _lib.lib()
-        dev, n = A.device, A.n_nodes
-        deg = torch.empty(max(1, n), dtype=torch.float64, device=dev)
-        dis = torch.empty(max(1, n), dtype=torch.float64, device=dev)
-        cnt = torch.empty(max(1, n), dtype=torch.int32, device=dev)
-        g = A.c_struct()
-        check(L.grf_laplacian_count(ctypes.byref(g), _ptr(deg), _ptr(dis), _ptr(cnt), _stream(dev)))
-        ptr = scan_counts(cnt, n, 1, _lib.ORDER_ROW_MAJOR, i64=False)
-        total = int(ptr[-1].item()) if n else 0
-        col = torch.empty(max(1, total), dtype=torch.int32, device=dev)[:total]
-        val = torch.empty(max(1, total), dtype=torch.float64, device=dev)[:total]
-        check(L.grf_laplacian_fill(ctypes.byref(g), _ptr(deg), _ptr(dis), _ptr(ptr), _ptr(col), _ptr(val),
-                                   _stream(dev)))
-        return cls._from_device(ptr, col, val, n)
+        dev, n = self.device, self.n_nodes
+        with torch.cuda.device(dev):
+            deg = torch.empty(max(1, n), dtype=torch.float64, device=dev)
+            dis = torch.empty(max(1, n), dtype=torch.float64, device=dev)
+            cnt = torch.empty(max(1, n), dtype=torch.int32, device=dev)
+            g = self.c_struct()
+            check(L.grf_laplacian_count(ctypes.byref(g), _ptr(deg), _ptr(dis), _ptr(cnt), _stream(dev)))
+            ptr = scan_counts(cnt, n, 1, _lib.ORDER_ROW_MAJOR, i64=False)
+            total = int(ptr[-1].item()) if n else 0
+            col = torch.empty(max(1, total), dtype=torch.int32, device=dev)[:total]
+            val = torch.empty(max(1, total), dtype=torch.float64, device=dev)[:total]
+            check(L.grf_laplacian_fill(ctypes.byref(g), _ptr(deg), _ptr(dis), _ptr(ptr), _ptr(col), _ptr(val),
+                                       _stream(dev)))
+        return DeviceGraph._from_device(ptr, col, val, n)
 
     def to_scipy(self):
         import scipy.sparse as sp

@@ -114,15 +114,16 @@ class GeneratorDraws:
     ``record=(trace_u, trace_k)`` stores every draw at ``[walk_id*L + step]``
     so that the CUDA walker can replay it."""
 
-    def __init__(self, rng: np.random.Generator, record=None, dense_choice: bool = False):
+    def __init__(self, rng: np.random.Generator, record=None, dense_choice: bool = False, walk_base: int = 0):
         self.rng = rng
         self.record = record
         self.dense_choice = dense_choice
+        self.walk_base = walk_base      # the record holds walks walk_base, walk_base + 1, ... (a row slice)
 
     def halt(self, walk_id: int, step: int, L: int, p_halt: float) -> bool:
         u = self.rng.random()
         if self.record is not None:
-            self.record[0][walk_id * L + step] = u
+            self.record[0][(walk_id - self.walk_base) * L + step] = u
         return u < p_halt
 
     def pick(self, walk_id: int, step: int, L: int, deg: int) -> int:
@@ -130,20 +131,21 @@ class GeneratorDraws:
         # like rng.integers(deg) (sparse_sampler.py:51); checked in the tests.
         k = int(self.rng.integers(deg))
         if self.record is not None:
-            self.record[1][walk_id * L + step] = k
+            self.record[1][(walk_id - self.walk_base) * L + step] = k
         return k
 
 
 class TraceDraws:
-    def __init__(self, trace_u: np.ndarray, trace_k: np.ndarray):
+    def __init__(self, trace_u: np.ndarray, trace_k: np.ndarray, walk_base: int = 0):
         self.u = trace_u
         self.k = trace_k
+        self.walk_base = walk_base
 
     def halt(self, walk_id, step, L, p_halt):
-        return self.u[walk_id * L + step] < p_halt
+        return self.u[(walk_id - self.walk_base) * L + step] < p_halt
 
     def pick(self, walk_id, step, L, deg):
-        return int(self.k[walk_id * L + step])
+        return int(self.k[(walk_id - self.walk_base) * L + step])
 
 
 class PhiloxDraws:
@@ -279,6 +281,47 @@ def sparse_step_matrices(
     return (mats, trace) if record else mats
 
 
+def worker_slice_rows(indptr, indices, data, n: int, lo: int, hi: int, num_walks: int, p_halt: float,
+                      max_walk_length: int, worker_seed: int, record: bool = False, draws=None):
+    """ONE reference worker (``_worker_walks``, sparse_sampler.py:26-56) on the contiguous chunk of start
+    nodes ``lo .. hi-1`` with ``default_rng(worker_seed)``, and the rows ``lo .. hi-1`` of the step matrices
+    it contributes (``csr_matrix(...) / num_walks``, :125-130) as ``(hi - lo) x n`` CSR.  The trace, if
+    recorded, is slice-local: element ``[(walk_id - lo * W) * L + step]``.  Works on graphs far too large
+    to walk as a whole (the 2^25-node ring of the 64-bit-key fixtures)."""
+    L = max_walk_length
+    trace = None
+    if record:
+        m = (hi - lo) * num_walks * L
+        trace = (np.full(m, np.nan), np.full(m, -1, dtype=np.int32))
+    if draws is None:
+        draws = GeneratorDraws(np.random.default_rng(worker_seed), record=trace, walk_base=lo * num_walks)
+    accs = walk_accumulate(indptr, indices, np.asarray(data, dtype=float), range(lo, hi), num_walks, p_halt, L, draws)
+    mats = []
+    for acc in accs:
+        if not acc:
+            mats.append(sp.csr_matrix((hi - lo, n)))
+            continue
+        keys = list(acc.keys())
+        rows = np.array([k[0] - lo for k in keys], dtype=np.int32)
+        cols = np.array([k[1] for k in keys], dtype=np.int32)
+        vals = np.array([acc[k] for k in keys], dtype=float)
+        mats.append(sp.csr_matrix((vals, (rows, cols)), shape=(hi - lo, n)) / num_walks)
+    return (mats, trace) if record else mats
+
+
+def ring_laplacian_csr(n: int, diag_v: float, off_v: float) -> sp.csr_matrix:
+    """Normalized Laplacian of the unit-weight n-ring built directly (three entries per row, sorted columns);
+    the two values come from the reference's get_normalized_laplacian (stored in the slice fixtures)."""
+    i = np.arange(n, dtype=np.int64)
+    cols = np.stack([(i - 1) % n, i, (i + 1) % n], axis=1)
+    vals = np.stack([np.full(n, off_v), np.full(n, diag_v), np.full(n, off_v)], axis=1)
+    order = np.argsort(cols, axis=1, kind="stable")
+    cols = np.take_along_axis(cols, order, axis=1)
+    vals = np.take_along_axis(vals, order, axis=1)
+    return sp.csr_matrix((vals.ravel(), cols.ravel().astype(np.int32), (np.arange(n + 1, dtype=np.int64) * 3).astype(np.int32)),
+                         shape=(n, n))
+
+
 def dense_step_tensor(
     adjacency: np.ndarray,
     num_walks: int,
@@ -398,6 +441,15 @@ def phi_matvec_f64(mats: Sequence[sp.csr_matrix], f: Sequence[float], v: np.ndar
     p1 = phi if x1 is None else phi[np.asarray(x1, dtype=np.int64)]
     p2 = phi if x2 is None else phi[np.asarray(x2, dtype=np.int64)]
     return p1 @ (p2.T @ np.asarray(v, dtype=np.float64))
+
+
+def torch_csr_f32(m: sp.csr_matrix):
+    """``GraphPreprocessor.from_scipy_csr`` (graph_preprocessor.py:117-139): int64 indices, float32 values."""
+    import torch
+
+    m = m.tocsr()
+    return torch.sparse_csr_tensor(torch.from_numpy(m.indptr).long(), torch.from_numpy(m.indices).long(),
+                                   torch.from_numpy(m.data).float(), (m.shape[0], m.shape[1]), dtype=torch.float32)
 
 
 def phi_matvec_reference_torch(mats: Sequence[sp.csr_matrix], f, v, x1=None, x2=None):

@@ -18,6 +18,7 @@ anything is written.
 Nothing in here is product code; the fixtures pin ``oracle/`` to the reference.
 """
 
+import hashlib
 import os
 import sys
 import tempfile
@@ -112,6 +113,24 @@ def _grid(nx, ny):
     return (sp.kron(sp.eye(ny), path(nx)) + sp.kron(path(ny), sp.eye(nx))).tocsr()
 
 
+def _ring_csr(n, diag_v, off_v, adjacency=False):
+    """CSR of the n-ring: adjacency (unit weights) or its normalized Laplacian with the given two values,
+    columns sorted -- built directly, no SpGEMM."""
+    i = np.arange(n, dtype=np.int64)
+    if adjacency:
+        cols = np.sort(np.stack([(i - 1) % n, (i + 1) % n], axis=1), axis=1)
+        vals = np.ones((n, 2))
+    else:
+        cols = np.stack([(i - 1) % n, i, (i + 1) % n], axis=1)
+        vals = np.stack([np.full(n, off_v), np.full(n, diag_v), np.full(n, off_v)], axis=1)
+        order = np.argsort(cols, axis=1, kind="stable")
+        cols = np.take_along_axis(cols, order, axis=1)
+        vals = np.take_along_axis(vals, order, axis=1)
+    k = cols.shape[1]
+    return sp.csr_matrix((vals.ravel(), cols.ravel().astype(np.int32), (np.arange(n + 1, dtype=np.int64) * k).astype(np.int32)),
+                         shape=(n, n))
+
+
 def _random_graph(n, m, seed, weighted):
     rng = np.random.default_rng(seed)
     rows, cols, vals = [], [], []
@@ -153,6 +172,13 @@ def main():
         ("ring32_lap_p8", lap_sparse(sp.csr_matrix(np.roll(np.eye(32), 1, 1) + np.roll(np.eye(32), -1, 1))), 7, 0.1, 5, 3, 8),
         ("gnm40_weighted_iso_lap_p4", lap_sparse(g_iso), 10, 0.1, 4, 11, 4),
         ("gnm40_weighted_raw_p2", g_iso, 6, 0.3, 6, 5, 2),
+        # production walk counts: every instantiation of the CUDA walker replays the reference
+        # (W <= 32: 1 key per lane, 40: 2, 100: 4 -- BASELINE's setting --, 130: 8, 300: CTA per start node)
+        ("ring60_lap_W100_p3", lap_sparse(sp.csr_matrix(np.roll(np.eye(60), 1, 1) + np.roll(np.eye(60), -1, 1))),
+         100, 0.1, 5, 42, 3),
+        ("gnm50_weighted_lap_W40_p2", lap_sparse(_random_graph(50, 120, 21, weighted=True)), 40, 0.1, 4, 7, 2),
+        ("grid6x6_lap_W130_p4", lap_sparse(_grid(6, 6)), 130, 0.15, 3, 13, 4),
+        ("gnm30_weighted_lap_W300_p2", lap_sparse(_random_graph(30, 70, 5, weighted=True)), 300, 0.1, 4, 1, 2),
     ]
     for name, graph, W, p, L, seed, nproc in sparse_cases:
         graph = graph.tocsr()
@@ -171,9 +197,67 @@ def main():
             assert np.array_equal(m.indices, pooled[s].indices) and np.array_equal(m.indptr, pooled[s].indptr)
             _csr_pack(f"step{s}", pooled[s], out)
         for i, log in enumerate(logs):
-            out[f"draws{i}"] = log
+            if log.shape[0] <= 4000:
+                out[f"draws{i}"] = log
+            else:   # 10^4..10^5 incompressible doubles: keep the head and a digest of the whole stream
+                out[f"draws{i}_head"] = log[:64]
+                out[f"draws{i}_count"] = np.array(log.shape[0])
+                out[f"draws{i}_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(log).tobytes()).digest(),
+                                                        dtype=np.uint8)
         np.savez_compressed(os.path.join(HERE, f"sparse_{name}.npz"), **out)
         print("sparse", name, [m.nnz for m in pooled])
+
+    # ---------------- row slices of huge graphs (64-bit sort keys; slice-local traces) -----
+    # One reference worker (sparse_sampler.py:26-56) run in-process on a contiguous chunk of start nodes
+    # of a ring with 2^23 / 2^25 nodes: node ids need 23 / 25 bits, so (node, walk) sort keys exceed 32
+    # bits -- the walker's 64-bit-key instantiations -- and the trace covers the slice only.  The ring's
+    # Laplacian is translation invariant (two distinct values), so the fixture stores those two values
+    # (checked against the reference's get_normalized_laplacian on a 2^12 ring and, for 2^23, on the
+    # full graph) and the test rebuilds the CSR procedurally.
+    small = lap_sparse(_ring_csr(1 << 12, 1.0, 1.0, adjacency=True)).tocsr()
+    diag_v, off_v = float(small[5, 5]), float(small[5, 6])
+    assert np.all(small.diagonal() == diag_v) and set(np.unique(small.data)) == {diag_v, off_v}
+    for name, log2n, lo_off, n_rows, W, p, L, seed in [
+        ("ring2p25_slice_W100", 25, -5, 5, 100, 0.1, 5, 77),     # warp variant, 4 keys per lane, 64-bit keys
+        ("ring2p23_slice_W300", 23, -3, 3, 300, 0.1, 4, 78),     # CTA-per-node variant, 64-bit keys
+        ("ring2p20_slice_W100", 20, 1000, 6, 100, 0.1, 5, 79),   # 32-bit keys, slice in the middle
+    ]:
+        n = 1 << log2n
+        lap = _ring_csr(n, diag_v, off_v)
+        if log2n <= 23:
+            ref_lap = lap_sparse(_ring_csr(n, 1.0, 1.0, adjacency=True)).tocsr()
+            ref_lap.sort_indices()
+            assert np.array_equal(ref_lap.indptr, lap.indptr) and np.array_equal(ref_lap.indices, lap.indices)
+            assert np.array_equal(ref_lap.data, lap.data), name
+        lo = (n + lo_off) if lo_off < 0 else lo_off
+        hi = lo + n_rows
+        chunk = list(range(lo, hi))
+        ss._init_worker(lap.indptr, lap.indices, lap.data.astype(float, copy=False), n)
+        log = []
+        real_rng = np.random.default_rng
+        np.random.default_rng = lambda sd, _log=log: _RecordingRNG(real_rng(sd), _log)
+        try:
+            res = ss._worker_walks((chunk, W, p, L, seed, False))
+        finally:
+            np.random.default_rng = real_rng
+        out = {"log2_n": log2n, "lo": lo, "hi": hi, "W": W, "p_halt": p, "L": L, "worker_seed": seed,
+               "lap_diag": diag_v, "lap_off": off_v}
+        for st in range(L):
+            keys = list(res[st].keys())
+            m = sp.csr_matrix((np.array([res[st][k] for k in keys], dtype=float),
+                               (np.array([k[0] for k in keys], dtype=np.int32),
+                                np.array([k[1] for k in keys], dtype=np.int32))), shape=(n, n)) / W   # :125-130
+            rows = m[lo:hi].tocsr()
+            out[f"step{st}_indptr"] = rows.indptr.astype(np.int64)
+            out[f"step{st}_indices"] = rows.indices.astype(np.int64)
+            out[f"step{st}_data"] = rows.data.astype(np.float64)
+        log = np.array(log, dtype=np.float64).reshape(-1, 2)
+        out["draws_head"] = log[:64]
+        out["draws_count"] = np.array(log.shape[0])
+        out["draws_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(log).tobytes()).digest(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(HERE, f"slice_{name}.npz"), **out)
+        print("slice", name, [int(out[f"step{st}_indptr"][-1]) for st in range(L)], "draws", log.shape[0])
+        del lap
 
     # ---------------- dense sampler cases --------------------------------
     real = np.random.default_rng
@@ -235,6 +319,67 @@ def main():
         kern[name + "_K_dense"] = kernel_dense(adj.toarray(), f, walks_per_node=10, p_halt=0.2, max_walk_length=3)
     np.savez_compressed(os.path.join(HERE, "kernels.npz"), **kern)
     print("kernels written (n_processes = os.cpu_count() =", nproc_here, ")")
+
+    # ---------------- matvec layer: SparseLinearOperator (M1) and GraphPreprocessor (P1) ----------
+    # The real utils_sparse/sparse_lo.py:4-25 and preprocessor/graph_preprocessor.py:85-139 on torch-CPU
+    # sparse CSR (the stub LinearOperator base only stores nothing): conversion to float32 / int64, the
+    # per-length products M_l @ X and M_l^T @ X (transposed through .t().to_sparse_csr() as the reference
+    # does), and the reference's op sequence for one kernel matvec  sum_l f_l M_l (sum_l' f_l' M_l'^T V)
+    # (sparse_grf_kernel.py:51-62: ConstantMul + Sum of the SparseLinearOperators) in float32.
+    import torch
+    from efficient_graph_gp_sparse.preprocessor.graph_preprocessor import GraphPreprocessor as RefPP
+    from efficient_graph_gp_sparse.utils_sparse.sparse_lo import SparseLinearOperator as RefLO
+
+    torch.manual_seed(0)
+    adj = (_grid(7, 5) + _random_graph(35, 20, 3, weighted=True)).tocsr()
+    adj.sum_duplicates()
+    adj.sort_indices()
+    W, p, L, seed, nproc = 25, 0.1, 4, 9, 3
+    pp = RefPP(adj, walks_per_node=W, p_halt=p, max_walk_length=L, random_walk_seed=seed, use_tqdm=False,
+               n_processes=nproc)
+    ops = pp.preprocess_graph(save_to_disk=False)
+    lap = lap_sparse(adj)
+    logs, _ = _record_sparse(ss, lap, W, p, L, seed, nproc)
+    n = adj.shape[0]
+    t = 6
+    X = torch.randn(n, t)
+    V = torch.randn(n, t)
+    f = torch.randn(L)
+    mv = {"W": W, "p_halt": p, "L": L, "seed": seed, "n_processes": nproc, "X": X.numpy(), "V": V.numpy(),
+          "f": f.numpy()}
+    _csr_pack("adj", adj, mv)
+    for i, log in enumerate(logs):
+        mv[f"draws{i}"] = log
+    u = torch.zeros(n, t)
+    for st, (m, op) in enumerate(zip(pp.step_matrices_scipy, ops)):
+        assert isinstance(op, RefLO) and tuple(op._size()) == (n, n)
+        _csr_pack(f"step{st}", m, mv)
+        csr = op.sparse_csr_tensor
+        mv[f"torch{st}_crow"] = csr.crow_indices().numpy()
+        mv[f"torch{st}_col"] = csr.col_indices().numpy()
+        mv[f"torch{st}_val"] = csr.values().numpy()                      # float32
+        mv[f"matmul{st}"] = op._matmul(X).numpy()
+        opt = op._transpose_nonbatch()
+        mv[f"tmatmul{st}"] = opt._matmul(X).numpy()
+        tc = opt.sparse_csr_tensor
+        mv[f"torchT{st}_crow"] = tc.crow_indices().numpy()
+        mv[f"torchT{st}_col"] = tc.col_indices().numpy()
+        mv[f"torchT{st}_val"] = tc.values().numpy()
+        u = u + f[st] * opt._matmul(V)                                   # Phi^T V, length by length
+    out = torch.zeros(n, t)
+    for st, op in enumerate(ops):
+        out = out + f[st] * op._matmul(u)                                # Phi (Phi^T V)
+    mv["phiT_V"] = u.numpy()
+    mv["K_V"] = out.numpy()
+    x1 = torch.tensor([3, 0, 17, 17, 30])
+    x2 = torch.tensor([1, 2, 3, 20, 34, 8])
+    V2 = torch.randn(x2.numel(), t)
+    full = torch.zeros(n, t).index_add_(0, x2, V2)                       # Phi[x2]^T V2 = Phi^T scatter(V2)
+    u2 = sum(f[st] * ops[st]._transpose_nonbatch()._matmul(full) for st in range(L))
+    mv["x1"], mv["x2"], mv["V2"] = x1.numpy(), x2.numpy(), V2.numpy()
+    mv["K_x1x2_V2"] = sum(f[st] * ops[st]._matmul(u2) for st in range(L))[x1].numpy()
+    np.savez_compressed(os.path.join(HERE, "matvec_layer.npz"), **mv)
+    print("matvec layer written:", [m.nnz for m in pp.step_matrices_scipy])
 
 
 if __name__ == "__main__":

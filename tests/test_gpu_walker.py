@@ -324,6 +324,14 @@ def test_device_laplacian_is_bit_exact(env):
         if trial >= 4:
             m.data[rng.integers(0, m.nnz, 20)] = 0.0                                            # explicit zeros
         cases.append(m)
+    # weighted hub rows far beyond numpy's 128-element pairwise-summation blocks (a recursive device
+    # function overran the call stack on the 167 k-neighbour hub of the 4 M-node R-MAT graph)
+    n = 6000
+    hub_cols = np.arange(1, n)
+    w = rng.uniform(0.5, 2.0, n - 1)
+    star = sp.coo_matrix((np.r_[w, w], (np.r_[np.zeros(n - 1, int), hub_cols], np.r_[hub_cols, np.zeros(n - 1, int)])),
+                         shape=(n, n)).tocsr()
+    cases.append((star + random_graph(n, 30000, 9, weighted=True)).tocsr())
     for a in cases:
         a = a.tocsr()
         a.sum_duplicates()
