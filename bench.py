@@ -1,26 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- the GRF hot path on B200, measured the way BASELINE.json asks.
 
-Workload (config.workload): BASELINE.json configs[1] -- sparse CSR GRF on a 2-D
-grid graph of 316 x 316 = 99 856 nodes, walks_per_node = 100, max_walk_length =
-5, p_halt = 0.1, learnable modulator f = randn(5) (torch.manual_seed(42)),
-t = 16 right-hand sides.  With N > 1 GPUs the grid grows to 316 x (316 N)
-nodes and every rank owns a contiguous block of 99 856 start nodes (weak
-scaling; CSR graph replicated; per matvec one all-reduce of the rows of Phi^T V
-that more than one rank touches).
+Headline workload (config.workload): BASELINE.json configs[3], the configuration the north star quotes
+its target on -- a SNAP-shaped power-law graph: R-MAT (0.57, 0.19, 0.19, 0.05), 2^22 = 4.19 M nodes,
+>= 70 M undirected edges after symmetrising / de-duplicating / dropping self-loops (drawn on the
+device, grf_b200/synth.py), walks_per_node = 100, max_walk_length = 5, p_halt = 0.1, learnable
+modulator f = randn(5), t = 16 right-hand sides.  STRONG scaling: the same graph on every GPU count,
+start nodes sharded in contiguous ranges of equal estimated work over the ranks, the normalised-
+Laplacian CSR replicated, one sum of the N x t partials Phi_g^T V_g per product (grf_exchange_sum over
+NVLink peer memory, or NCCL all-reduce when symmetric memory is not available).
 
-One "step" = one pass of the hot path: walker (+ merge) -> compaction into Phi
-blocks -> Phi^T blocks (+ the one-off matvec preparation: row census, workspaces)
--> one kernel matvec Phi(Phi^T V).  Every phase is timed
-on the device with CUDA events on the launching stream; L2 is flushed (a 256 MB
-write) before every timed phase.  `value` = walk-steps executed by all ranks /
-max-over-ranks step time.
+One "step" = one pass of the hot path over this rank's start nodes: walker (+ merge) -> compaction into
+Phi blocks -> Phi^T blocks (stable radix sort) + the one-off matvec preparation -> one kernel matvec
+Phi(Phi^T V) including the exchange.  The step is bracketed by CUDA events on the launching stream; the
+phases inside it are timed with their own events.  No L2 flush at this size: every phase streams 4 - 17 GB
+(edge records 2.3 GB, staging 13 GB, entries 4.2 GB), far beyond the 126 MB L2.  `value` = walk-steps
+executed by all ranks / max-over-ranks step time.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+A second section (`config2`) reports BASELINE.json configs[1] (316 x 316 grid, L2 flushed before
+every timed phase) on each rank's own copy, as round 1 did.
 
-`--impl reference` times the reference's CPU algorithm (oracle/cpu_baseline.py:
-the pure-Python fork-pool sampler, all host cores) on a bounded sample of the
-same workload.  oracle/ is used here only as the timed CPU baseline.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale 22] [--edges 70e6]
+
+`--impl reference` times the reference's CPU algorithm (oracle/cpu_baseline.py: the pure-Python
+fork-pool sampler, all host cores) on a bounded sample of the same workload's start nodes.  oracle/
+is used here only as the timed CPU baseline.
 """
 
 from __future__ import annotations
@@ -32,7 +36,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -41,12 +44,17 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "efficient-gaussian-process-on-graphs_b
 import numpy as np
 import scipy.sparse as sp
 
+# config 4 (headline)
+RMAT_SCALE, RMAT_EDGES, RMAT_SEED = 22, 70_000_000, 0
+# config 2 (second section)
 GRID_NX, GRID_NY = 316, 316
 W, P_HALT, L, T_RHS = 100, 0.1, 5, 16
 SEED = 42
 METRIC = "grf_walk_steps_per_sec"
 UNIT = "walk-steps/s"
-WALK_BYTES_PER_STEP = 32          # row_ptr pair 8 + col 4 + val 8 (fp64) + merged record 12 (SURVEY 8d, fp64 path)
+# algorithmic bytes per walk-step of the production walker (SURVEY 8d, fp64 loads): row_ptr pair 8 + neighbour 4
+# + load factor 8 + one merged 8-byte Phi entry
+WALK_BYTES_PER_STEP = 28
 
 
 def grid_laplacian(nx: int, ny: int) -> sp.csr_matrix:
@@ -76,6 +84,20 @@ def load_traffic():
         with open(path) as fh:
             return json.load(fh)
     return {}
+
+
+def workload_config(n_gpus, stats, scale, edges):
+    return {
+        "workload": f"BASELINE.json configs[3]: SNAP-shaped power-law graph (R-MAT 0.57/0.19/0.19/0.05, 2^{scale} = "
+                    f"{1 << scale} nodes, >= {edges / 1e6:.0f} M undirected edges), GRF Phi build node-sharded over "
+                    f"{n_gpus} x B200, walks_per_node=100, max_walk_length=5, p_halt=0.1, learnable modulator, t=16",
+        "graph": stats, "walks_per_node": W, "max_walk_length": L, "p_halt": P_HALT, "rhs_columns": T_RHS,
+        "sharding": f"start nodes in {n_gpus} contiguous range(s) of equal estimated work (strong scaling), CSR "
+                    f"walk graph replicated",
+        "l2": "not flushed: every phase streams 4-17 GB (edge records 2.3 GB, staging 13 GB, Phi entries 4.2 GB), "
+              "far beyond the 126 MB L2; config2 section: flushed (256 MB write) before every timed phase",
+        "host": "Python gc disabled inside the timed region",
+    }
 
 
 class ClockSampler:
@@ -130,9 +152,55 @@ class ClockSampler:
                 if flag.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.out.name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        busy = [x for x in sm if x >= 0.5 * max(mx or [1])] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons),
-                "window": "warm-up + timed steps + the 20 timed CG matvecs (the timed steps alone last a few ms)"}
+                "window": "warm-up + timed steps of the headline workload (20 ms sampling; the median is over the "
+                          "samples taken under load)"}
+
+
+# ------------------------------------------------------------------ the graph of config 4
+def cfg4_walk_graph(scale, edges, dev=None):
+    """(DeviceGraph of the normalized Laplacian, stats) on the GPU; numpy fallback for a box without CUDA."""
+    import torch
+
+    from grf_b200 import synth
+
+    if torch.cuda.is_available():
+        return synth.rmat_walk_graph(scale, int(edges), seed=RMAT_SEED, device=dev)
+    raise RuntimeError("config 4 is drawn on the GPU")
+
+
+def cfg4_host_laplacian(scale, edges):
+    """The same graph as a host scipy CSR (for the CPU arm): drawn on the GPU when there is one (seconds), else
+    with the same R-MAT recipe in numpy (a minute)."""
+    import torch
+
+    if torch.cuda.is_available():
+        g, stats = cfg4_walk_graph(scale, edges, torch.device("cuda", 0))
+        lap = g.to_scipy()
+        del g
+        torch.cuda.empty_cache()
+        return lap, stats
+    from efficient_graph_gp_sparse.utils_sparse.graph_utils import get_normalized_laplacian
+
+    rng = np.random.default_rng(RMAT_SEED)
+    n, m = 1 << scale, int(edges * 1.06)
+    src = np.zeros(m, dtype=np.int64)
+    dst = np.zeros(m, dtype=np.int64)
+    for bit in range(scale):
+        r = rng.random(m)
+        src |= (r >= 0.76).astype(np.int64) << bit
+        dst |= (((r >= 0.57) & (r < 0.76)) | (r >= 0.95)).astype(np.int64) << bit
+    keep = src != dst
+    lo, hi = np.minimum(src[keep], dst[keep]), np.maximum(src[keep], dst[keep])
+    key = np.unique(lo * n + hi)
+    lo, hi = key // n, key % n
+    adj = sp.csr_matrix((np.ones(2 * key.size), (np.r_[lo, hi], np.r_[hi, lo])), shape=(n, n))
+    deg = np.diff(adj.indptr)
+    stats = {"n_nodes": n, "undirected_edges": int(key.size), "max_degree": int(deg.max()),
+             "isolated_nodes": int((deg == 0).sum()), "generator": "numpy fallback (no GPU)"}
+    return get_normalized_laplacian(adj), stats
 
 
 # ------------------------------------------------------------------ reference arm
@@ -142,50 +210,59 @@ def run_reference(args):
         return
     from oracle import cpu_baseline
 
-    n_gpus = args.gpus
-    lap = grid_laplacian(GRID_NX, GRID_NY * n_gpus)
+    lap, stats = cfg4_host_laplacian(args.scale, args.edges)
     n = lap.shape[0]
     cores = os.cpu_count() or 1
-    n_sample = min(n, 2 * GRID_NX * cores)          # two grid lines of start nodes per core and step
-    starts = np.arange(n_sample)
+    rng = np.random.default_rng(7)
+    per_step = 3000 * cores                        # ~1.2e6 walk-steps per core and step: a few seconds
     times, visits = [], 0
     for i in range(args.warmup + args.steps):
+        starts = np.sort(rng.choice(n, size=min(n, per_step), replace=False))
         dt, vis = cpu_baseline.time_sampler(lap, W, P_HALT, L, starts, n_processes=cores)
         if i >= args.warmup:
             times.append(dt)
             visits += vis
     total = sum(times)
     value = visits / total
-    sample = (f"{n_sample} of {n} start nodes per step (x{W} walks), oracle/cpu_baseline.py fork-pool port of "
-              f"sparse_sampler.py:72-132, {cores} processes")
+    sample = (f"{min(n, per_step)} of {n} start nodes per step, drawn uniformly (x{W} walks), oracle/cpu_baseline.py "
+              f"fork-pool port of sparse_sampler.py:72-132, {cores} processes")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n_gpus, n),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, stats, args.scale, args.edges),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, n_nodes):
-    return {
-        "workload": "BASELINE.json configs[1]: sparse CSR GRF on 2D grid graph N=100k (316x316 per GPU), "
-                    "walks_per_node=100, max_walk_length=5, p_halt=0.1, learnable modulator, t=16",
-        "n_nodes": int(n_nodes), "walks_per_node": W, "max_walk_length": L, "p_halt": P_HALT, "rhs_columns": T_RHS,
-        "sharding": f"start nodes row-sharded over {n_gpus} GPU(s), CSR graph replicated",
-        "l2": "flushed (256 MB write) before every timed phase; staging (480 MB) exceeds L2 as well",
-        "host": "Python gc disabled inside the timed region",
-    }
-
-
 # ------------------------------------------------------------------ GPU arm
+class PhaseClock:
+    """CUDA events at the phase boundaries engine.build_phi_blocks reports (walk / compact / transpose per row
+    block), summed per phase."""
+
+    def __init__(self, torch, stream):
+        self.torch, self.stream, self.marks = torch, stream, []
+
+    def __call__(self, name):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.stream)
+        self.marks.append((name, ev))
+
+    def totals(self):
+        out = {}
+        for (name, a), (_, b) in zip(self.marks[:-1], self.marks[1:]):
+            if name != "end":
+                out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from grf_b200 import _lib, engine
+    from grf_b200 import _lib, engine, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,149 +273,146 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    lap = grid_laplacian(GRID_NX, GRID_NY * world)
-    n = lap.shape[0]
-    rows_per = n // world
-    lo, hi = rank * rows_per, (rank + 1) * rows_per if rank < world - 1 else n
-    graph = engine.DeviceGraph.from_scipy(lap, dev)
-    cfg = engine.WalkConfig(W, P_HALT, L, seed=SEED)
-    # rows of Phi^T V the ranks must sum: nodes within L - 1 hops of two or more row shards.  A property of
-    # the graph and the sharding (like the Laplacian itself), so computed once here, not per step.
-    bounds = [r * rows_per for r in range(world)] + [n]
-    shared_hint = graph.shared_columns(bounds, L) if world > 1 else None
-    torch.manual_seed(42)
-    f = torch.randn(L).to(dev)                         # learnable modulator init, sparse_grf_kernel.py:14-17
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    v = torch.randn(hi - lo, T_RHS, device=dev, generator=gen)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    group = True if world > 1 else None
     stream = torch.cuda.current_stream(dev)
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
-
-    def timed(fn):
-        flush.fill_(1)                                  # L2 flush, outside the timed bracket
-        a, b = ev(), ev()
-        a.record(stream)
-        out = fn()
-        b.record(stream)
-        return out, (a, b)
-
-    lib = _lib.lib()
-    stride = lib.grf_walk_stage_stride(W, L)
-
-    def one_step():
-        """walker -> Phi blocks -> Phi^T blocks -> one Phi(Phi^T V).  Returns events + the visit counter only,
-        so every step reuses the previous step's device memory (no cudaMalloc in the timed region)."""
-        visits = torch.zeros(1, dtype=torch.int64, device=dev)
-        st, e_walk = timed(lambda: engine.run_walker(graph, cfg, lo, hi, visits=visits, count_columns=True))
-        phi, e_comp = timed(lambda: engine._blocks_from_staging(st, cfg, graph.n_nodes, _lib.SCALE_MUL_RECIP))
-        del st
-        phi.row_lo = lo
-        def transpose_and_prepare():
-            # Phi^T blocks + the one-off matvec preparation (row census, workspaces; with several ranks the
-            # list of columns shared between row shards) -- all of it inside the timed phase
-            phi.build_transpose()
-            return phi.plan(f, T_RHS, group=True if world > 1 else None, merged=False)   # f applied per entry
-
-        plan, e_tr = timed(transpose_and_prepare)
-        out = torch.empty((hi - lo, T_RHS), dtype=torch.float32, device=dev)
-        _, e_mv = timed(lambda: plan(v, out))
-        return dict(visits=visits, nnz=phi.nnz, n_rows=phi.n_rows,
-                    events=dict(walk=e_walk, compact=e_comp, transpose=e_tr, matvec=e_mv))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---------------- config 4: the graph, the shards ----------------
+    t_gen = time.perf_counter()
+    graph, stats = cfg4_walk_graph(args.scale, args.edges, dev)
+    torch.cuda.synchronize(dev)
+    stats["generated_on_device_s"] = round(time.perf_counter() - t_gen, 2)
+    n = graph.n_nodes
+    bounds = sharding.balanced_bounds(graph, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    cfg = engine.WalkConfig(W, P_HALT, L, seed=SEED)
+    graph.edge_records(P_HALT)                           # per graph and p_halt, like the Laplacian itself
+    torch.manual_seed(42)
+    f = torch.randn(L).to(dev)                           # learnable modulator init, sparse_grf_kernel.py:14-17
+
+    def rhs_of(r):
+        g = torch.Generator(device=dev).manual_seed(1234 + r)
+        return torch.randn(bounds[r + 1] - bounds[r], T_RHS, device=dev, generator=g)
+
+    v = rhs_of(rank)
+    out = torch.empty((hi - lo, T_RHS), dtype=torch.float32, device=dev)
+    exchange = sharding.make_exchange(n, (T_RHS + 3) // 4 * 4, dev, group) if world > 1 else None
+
+    def one_step(keep=False):
+        """One pass of the hot path.  Returns events and counters only (unless ``keep``), so that every step
+        reuses the previous step's device memory: no cudaMalloc inside the timed region."""
+        clock = PhaseClock(torch, stream)
+        a, b = ev(), ev()
+        a.record(stream)
+        phi = engine.build_phi_blocks(graph, cfg, lo, hi, phase_hook=clock)
+        clock("plan")
+        plan = phi.plan(f, T_RHS, group=group, merged=False, exchange=exchange)     # f applied per entry
+        clock("matvec")
+        plan(v, out)
+        clock("end")
+        b.record(stream)
+        res = dict(visits=phi.visits, nnz=phi.nnz, n_rows=phi.n_rows, step=(a, b), clock=clock)
+        if keep:
+            res.update(phi=phi, plan=plan)
+        return res
+
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()                                 # nvidia-smi needs ~0.1 s to start: launch it before warm-up
+        sampler.start()
     for _ in range(args.warmup):
         r = one_step()
         del r
     if rank == 0:
         sampler.wait_first_sample()
-    # no Python garbage-collector pause inside the timed region (a gen-2 collection on one rank stalls the
-    # other ranks in the matvec's all-reduce for about a millisecond)
     gc.collect()
     gc.disable()
     barrier()
     t_wall0 = time.perf_counter()
-    results = [one_step() for _ in range(args.steps)]
+    results = [one_step(keep=(i == args.steps - 1)) for i in range(args.steps)]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     gc.enable()
-
-    phase_ms = {k: sum(r["events"][k][0].elapsed_time(r["events"][k][1]) for r in results)
-                for k in ("walk", "compact", "transpose", "matvec")}
-    step_ms_total = sum(phase_ms.values())
-    if os.environ.get("GRF_BENCH_DEBUG"):
-        print(f"[rank {rank}] per-phase ms over {args.steps} steps: "
-              + ", ".join(f"{k} {v:.3f}" for k, v in phase_ms.items()), file=sys.stderr, flush=True)
-    visits_total = sum(int(r["visits"].item()) for r in results)
-    nnz = results[-1]["nnz"]
-    n_rows = results[-1]["n_rows"]
-
-    # ---- the matvec as a CG solve uses it: Phi_f merged on the union pattern once per modulator, then
-    # many products; every product timed separately with an L2 flush in front
-    st = engine.run_walker(graph, cfg, lo, hi)
-    phi_cg = engine._blocks_from_staging(st, cfg, graph.n_nodes, _lib.SCALE_MUL_RECIP)
-    del st
-    phi_cg.row_lo = lo
-    phi_cg.shared_hint = shared_hint
-    phi_cg.build_transpose()
-    _, e_union = timed(lambda: phi_cg.build_union())
-    cg_plan, e_mat = timed(lambda: phi_cg.plan(f, T_RHS, group=True if world > 1 else None, merged=True))
-    out_cg = torch.empty((hi - lo, T_RHS), dtype=torch.float32, device=dev)
-    for _ in range(3):
-        cg_plan(v, out_cg)
-    cg_events = [timed(lambda: cg_plan(v, out_cg))[1] for _ in range(20)]
-    torch.cuda.synchronize(dev)
-    cg_ms = sorted(a.elapsed_time(b) for a, b in cg_events)
-    cg_info = {"union_build_ms": e_union[0].elapsed_time(e_union[1]), "materialize_ms": e_mat[0].elapsed_time(e_mat[1]),
-               "matvec_ms_median": cg_ms[len(cg_ms) // 2], "matvec_ms_min": cg_ms[0], "nnz_union": phi_cg.nnz_union}
-    del phi_cg, cg_plan
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: the public drop-in call with HOST buffers (host CSR in, scipy CSR list out) + host matvec
-    from efficient_graph_gp_sparse.random_walk_samplers_sparse.sparse_sampler import SparseRandomWalk
+    step_ms_total = sum(r["step"][0].elapsed_time(r["step"][1]) for r in results)
+    phase_ms = {}
+    for r in results:
+        for k, ms in r["clock"].totals().items():
+            phase_ms[k] = phase_ms.get(k, 0.0) + ms
+    visits_total = sum(int(r["visits"].item()) for r in results)
+    nnz, n_rows = results[-1]["nnz"], results[-1]["n_rows"]
+    phi, plan = results[-1]["phi"], results[-1]["plan"]
 
-    del results
+    # ---- the matvec alone, 20 products (the CG steady state: same Phi, same plan) and its two halves
+    mv_events = []
+    for _ in range(3):
+        plan(v, out)
+    for _ in range(20):
+        a, b = ev(), ev()
+        a.record(stream)
+        plan(v, out)
+        b.record(stream)
+        mv_events.append((a, b))
+    halves = []
+    for which in (1, 2):
+        a, b = ev(), ev()
+        a.record(stream)
+        for _ in range(5):
+            plan._call(v, out, which)
+        b.record(stream)
+        halves.append((a, b))
+    torch.cuda.synchronize(dev)
+    mv_ms = sorted(a.elapsed_time(b) for a, b in mv_events)
+    half_ms = [a.elapsed_time(b) / 5 for a, b in halves]
+
+    # ---- N ranks == 1 rank: rank 0 rebuilds the whole Phi on its GPU and multiplies the concatenated V
+    check = None
+    if world > 1:
+        plan(v, out)
+        gathered = [torch.empty((bounds[r + 1] - bounds[r], T_RHS), dtype=torch.float32, device=dev)
+                    for r in range(world)] if rank == 0 else None
+        dist.gather(out, gathered, dst=0)
+        if rank == 0:
+            del results, phi, plan
+            torch.cuda.empty_cache()
+            full = engine.build_phi_blocks(graph, cfg)
+            v_all = torch.cat([rhs_of(r) for r in range(world)])
+            want = full.plan(f, T_RHS, merged=False)(v_all)
+            got = torch.cat(gathered)
+            scale_ = float(want.abs().max())
+            check = {"max_abs_diff_over_max": float((got - want).abs().max()) / scale_,
+                     "checksum_n_ranks": float(got.double().sum()), "checksum_1_rank": float(want.double().sum()),
+                     "tolerance": 2e-5, "ok": bool(float((got - want).abs().max()) <= 2e-5 * scale_)}
+            del full, want, got, v_all, gathered
+        phi = plan = None
+    results = None
     torch.cuda.empty_cache()
-    e2e_time, e2e_visits, h2d, d2h = 0.0, 0, 0, 0
-    v_host = v.cpu().pin_memory()
-    out_host = torch.empty((hi - lo, T_RHS), dtype=torch.float32).pin_memory()   # the product is read back here
-    e2e_steps = max(1, min(args.steps, 3))
-    for i in range(1 + e2e_steps):
-        barrier()
-        t0 = time.perf_counter()
-        rw = SparseRandomWalk(lap, seed=SEED, device=dev)
-        steps = rw.get_step_matrices_device(W, P_HALT, L, start_lo=lo, start_hi=hi)
-        mats = steps.to_scipy()                          # D2H of every M_l (float64 + int32 + offsets)
-        phi_e = engine.PhiBlocks.from_step_matrices(steps)
-        phi_e.row_lo = lo
-        phi_e.shared_hint = shared_hint
-        vd = v_host.to(dev, non_blocking=True)
-        out_host.copy_(phi_e.plan(f, T_RHS, group=True if world > 1 else None, merged=False)(vd),
-                       non_blocking=True)                # one product, read back into pinned memory
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        if i > 0:
-            e2e_time += dt
-            e2e_visits += steps.visits
-            h2d = lap.indptr.nbytes + lap.indices.nbytes + lap.data.nbytes + v_host.numel() * 4
-            d2h = steps.offsets.numel() * 8 + steps.col.numel() * 4 + steps.val.numel() * 8 + out_host.numel() * 4
-        del rw, steps, mats, phi_e
+
+    # ---- e2e: the public drop-in call with HOST buffers: GraphPreprocessor(host scipy adjacency) -> operators on
+    # the device, then one kernel matvec with V from pinned host memory and the product read back
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(args, torch, dist, engine, sharding, dev, world, rank, bounds, f, v, group, exchange, barrier)
+
+    # ---- config 2 section
+    cfg2 = None if args.no_config2 else config2_leg(torch, engine, _lib, dev, rank)
 
     # ---- reduce over ranks: max time, sum of work
-    red = torch.tensor([step_ms_total, phase_ms["walk"], phase_ms["compact"], phase_ms["transpose"],
-                        phase_ms["matvec"], e2e_time, cg_info["matvec_ms_median"], cg_info["matvec_ms_min"],
-                        cg_info["union_build_ms"], cg_info["materialize_ms"]], dtype=torch.float64, device=dev)
-    work = torch.tensor([visits_total, e2e_visits, nnz], dtype=torch.float64, device=dev)
+    keys = ["walk", "compact", "transpose", "plan", "matvec"]
+    red = torch.tensor([step_ms_total] + [phase_ms.get(k, 0.0) for k in keys] +
+                       [mv_ms[len(mv_ms) // 2], mv_ms[0], half_ms[0], half_ms[1]], dtype=torch.float64, device=dev)
+    work = torch.tensor([visits_total, nnz, n_rows], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([step_ms_total / args.steps, float(nnz), float(n_rows)], dtype=torch.float64, device=dev)
+    all_ranks = [torch.empty_like(per_rank) for _ in range(world)] if world > 1 else [per_rank]
     if world > 1:
+        dist.all_gather(all_ranks, per_rank)
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     red, work = red.tolist(), work.tolist()
@@ -346,84 +420,211 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = peaks()
         K = args.steps
-        step_ms, walk_ms, comp_ms, tr_ms, mv_ms = (x / K for x in red[:5])
+        step_ms = red[0] / K
+        walk_ms, comp_ms, tr_ms, plan_ms, mv_step_ms = (x / K for x in red[1:6])
+        mv_med, mv_min, h1, h2 = red[6:10]
         value = work[0] / (red[0] * 1e-3)
-        # matvec algorithmic bytes, this rank's launch pair: 2*nnz*8 + 2*L*(rows+1)*4 + 4*N_eff*t*4
-        n_cols = graph.n_nodes
-        mv_bytes = 2 * nnz * 8 + L * (n_rows + 1) * 4 + L * (n_cols + 1) * 4 + (2 * n_rows + 2 * n_cols) * T_RHS * 4
-        mv_gbs = mv_bytes / (mv_ms * 1e-3) / 1e9
-        cg_ms_med, cg_ms_min, union_ms, mat_ms = red[6], red[7], red[8], red[9]
-        cg_gbs = mv_bytes / (cg_ms_med * 1e-3) / 1e9
-        nnz_u = cg_info["nnz_union"]
-        layout_bytes = 2 * nnz_u * 8 + (n_rows + 1) * 4 + (n_cols + 1) * 4 + (2 * n_rows + 2 * n_cols) * T_RHS * 4
+        nnz_all, rows_all = work[1], work[2]
+        # matvec algorithmic bytes of the whole product: 2*nnz*8 + 2*L*(rows+1)*4 + 4*N*t*4, summed over
+        # the ranks (every rank reads its entries twice and its row pointers; V, U, U, out are N x t each)
+        mv_bytes = 2 * nnz_all * 8 + L * (rows_all + world) * 4 + L * (n + 1) * 4 * world + 4 * n * T_RHS * 4
+        mv_gbs = mv_bytes / (mv_med * 1e-3) / 1e9
         traffic = load_traffic()
-        walk_bytes = (work[0] / world / K) * WALK_BYTES_PER_STEP
-        walk_gbs = walk_bytes / (walk_ms * 1e-3) / 1e9
+        walk_bytes = (work[0] / K) * WALK_BYTES_PER_STEP
+        walk_gbs = walk_bytes / (walk_ms * 1e-3) / 1e9 / world          # per GPU: max-over-ranks walker time
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 walk loads / f32 matvec", "data": "synthetic",
-            "config": workload_config(world, n),
-            "phases_ms": {"walk_merge": walk_ms, "compact_blocks": comp_ms, "transpose_blocks": tr_ms,
-                          "matvec_phi_phiT_v": mv_ms},
+            "config": workload_config(world, stats, args.scale, args.edges),
+            "phases_ms": {"walk_merge": walk_ms, "compact_entries": comp_ms, "transpose_radix_sort": tr_ms,
+                          "matvec_plan": plan_ms, "matvec_phi_phiT_v": mv_step_ms,
+                          "note": "max over ranks of each phase; the step is bracketed by its own event pair"},
             "phi_build_ms": walk_ms + comp_ms + tr_ms,
+            "walk_steps_per_step": work[0] / K, "nnz_phi": nnz_all,
             "walker_steps_per_sec": (work[0] / K) / (walk_ms * 1e-3),
-            "matvec": {"ms": mv_ms, "algorithmic_gbs": mv_gbs, "nnz_phi_rank0": nnz, "t": T_RHS,
-                       "includes_allreduce": world > 1,
-                       "what": "per-length Phi blocks, modulator applied per entry (inside the timed step)"},
-            "cg_matvec": {"ms": cg_ms_med, "ms_min": cg_ms_min, "algorithmic_gbs": cg_gbs,
-                          "layout_gbs": layout_bytes / (cg_ms_med * 1e-3) / 1e9, "nnz_union_rank0": nnz_u,
-                          "union_build_ms_once_per_phi": union_ms, "materialize_ms_once_per_modulator": mat_ms,
-                          "includes_allreduce": world > 1,
-                          "what": "Phi_f merged on the union pattern (MatvecPlan default): 20 products, L2 flushed "
-                                  "before each, median"},
-            "roofline": {"kernel": "walk_merge_kernel (dominant by time)", "bound": "hbm", "achieved": walk_gbs,
-                         "peak": peak, "unit": "GB/s", "frac": walk_gbs / peak,
-                         "traffic": traffic.get("walk_merge_bytes"),
-                         "peak_source": peak_src,
-                         "note": "latency/sector-bound random gathers: 32 algorithmic B per walk-step, "
-                                 "graph L2-resident at this size"},
-            "roofline_matvec": {"kernel": "spmm_blocks_kernel x2 (Phi^T V, Phi U) on merged Phi_f (CG path)",
-                                "bound": "hbm", "achieved": cg_gbs, "peak": peak, "unit": "GB/s",
-                                "frac": cg_gbs / peak, "traffic": traffic.get("spmm_merged_pair_bytes"),
+            "per_rank": [{"ms_per_step": a[0], "nnz": a[1], "rows": a[2]} for a in (x.tolist() for x in all_ranks)],
+            "matvec": {"ms": mv_med, "ms_min": mv_min, "phiT_v_ms": h1, "phi_u_ms": h2, "algorithmic_gbs": mv_gbs,
+                       "t": T_RHS, "includes_exchange": world > 1,
+                       "exchange": None if exchange is None else exchange.describe(),
+                       "what": "per-length Phi blocks, modulator applied per entry; 20 products after 3 warm-up, median "
+                               "(every product streams 8 GB of entries: nothing survives in L2 between products)"},
+            "cross_rank_check": check,
+            "roofline": {"kernel": "walk_merge_kernel (largest share of the step)", "bound": "hbm",
+                         "achieved": walk_gbs, "peak": peak, "unit": "GB/s", "frac": walk_gbs / peak,
+                         "traffic": traffic.get("cfg4_walk_merge_bytes"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_walk_step": WALK_BYTES_PER_STEP,
+                         "note": "per GPU; random-gather bound: two dependent 32-byte sectors per walk-step (row "
+                                 "pointers, edge record) for 20 useful bytes -> read-side sector efficiency 31 %"},
+            "roofline_matvec": {"kernel": "spmm_blocks_kernel (Phi^T V main + hub-column chunks, Phi U)",
+                                "bound": "hbm", "achieved": mv_gbs / world, "peak": peak, "unit": "GB/s",
+                                "frac": mv_gbs / world / peak, "traffic": traffic.get("cfg4_spmm_product_bytes"),
                                 "peak_source": peak_src, "algorithmic_bytes": mv_bytes,
-                                "layout_bytes": layout_bytes,
-                                "note": "algorithmic bytes = SURVEY 8d formula on the per-length matrices "
-                                        "(2*nnz*8 + 2*L*(n+1)*4 + 4*N*t*4); the merged layout streams fewer "
-                                        "(layout_bytes); per-length kernel: see matvec"},
-            "e2e": {"value": work[1] / red[5], "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * red[5] / e2e_steps,
-                    "what": "SparseRandomWalk(host scipy CSR) -> list of host scipy CSR step matrices, plus one "
-                            "host-V -> Phi(Phi^T V) -> host matvec"},
-            "gpu_launches": K * 18,
-            "gpu_launches_per_step": {"walk_merge": 1, "scan": 3 + 3, "compact_blocks": 1,
-                                      "transpose_fill": 1, "transpose_sort": 5, "row_census": 2, "spmm_blocks": 2},
+                                "note": "per GPU.  The formula counts the X gathers as free; on this graph they are not: "
+                                        "2 x nnz x 64 B = 67 GB of gathered rows per product, 33 GB of them from DRAM "
+                                        "(hub columns of Phi^T gather V rows spread over all 268 MB of V)"},
+            "e2e": e2e, "config2": cfg2,
+            "gpu_launches": None,
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        line["gpu_launches"] = count_launches(line, world)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg(lap)
+            line["cpu_baseline"] = cpu_baseline_leg(args)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline_leg(lap):
+def count_launches(line, world):
+    """Kernels of libgrf_b200.so launched per step on one rank, counted from the call structure (not a timer):
+    walker 1, row-count scan 3, compaction 1, Phi^T: offsets scan 3 + census 2 + key pass 1 + 3 radix passes x
+    (histogram 1 + scan 3 + scatter 1), matvec: 2 main passes + 2 hub-chunk passes + 2 ordered reductions,
+    exchange 1 when sharded."""
+    per_step = 1 + 3 + 1 + (3 + 2 + 1 + 3 * 5) + 6 + (1 if world > 1 else 0)
+    return {"per_step_per_rank": per_step, "timed_region": per_step * line["steps"] * world}
+
+
+def e2e_leg(args, torch, dist, engine, sharding, dev, world, rank, bounds, f, v, group, exchange, barrier):
+    """Host buffers in, host buffers out, wall clock, max over ranks: the adjacency leaves host memory as scipy
+    CSR arrays, V leaves pinned host memory, the product comes back to pinned host memory."""
+    from efficient_graph_gp_sparse.preprocessor import GraphPreprocessor
+
+    lo, hi = bounds[rank], bounds[rank + 1]
+    adj_dev = None
+    from grf_b200 import synth
+
+    adj_dev = synth.rmat_adjacency(args.scale, int(args.edges), seed=RMAT_SEED, device=dev)
+    adj = adj_dev.to_scipy()                                  # the user's host graph (setup, not timed)
+    del adj_dev
+    torch.cuda.empty_cache()
+    v_host = v.cpu().pin_memory()
+    out_host = torch.empty((hi - lo, T_RHS), dtype=torch.float32).pin_memory()
+    steps = max(1, min(args.steps, 3))
+    total, visits, h2d, d2h = 0.0, 0, 0, 0
+    for i in range(1 + steps):
+        barrier()
+        t0 = time.perf_counter()
+        pp = GraphPreprocessor(adj, walks_per_node=W, p_halt=P_HALT, max_walk_length=L, random_walk_seed=SEED,
+                               use_tqdm=False, device=dev)
+        phi = pp.preprocess_phi(start_lo=lo, start_hi=hi)     # H2D adjacency -> Laplacian -> walks -> Phi blocks
+        vd = v_host.to(dev, non_blocking=True)
+        prod = phi.plan(f, T_RHS, group=group, merged=False, exchange=exchange)(vd)
+        out_host.copy_(prod, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        barrier()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            total += dt
+            visits += int(phi.visits)
+            h2d = adj.indptr.nbytes + adj.indices.nbytes + adj.data.nbytes + v_host.numel() * 4
+            d2h = out_host.numel() * 4
+        del pp, phi, prod, vd
+    t = torch.tensor([total], dtype=torch.float64, device=dev)
+    vis = torch.tensor([float(visits)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(vis, op=dist.ReduceOp.SUM)
+    return {"value": float(vis) / float(t), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": 1e3 * float(t) / steps, "steps": steps,
+            "what": "GraphPreprocessor(host scipy adjacency) -> device Laplacian -> walks -> Phi blocks (+ Phi^T), then "
+                    "one Phi(Phi^T V) with V from pinned host memory and the product read back to pinned host memory; "
+                    "wall clock, max over ranks (every rank uploads the whole adjacency)"}
+
+
+def config2_leg(torch, engine, _lib, dev, rank):
+    """BASELINE.json configs[1] on this GPU: 316 x 316 grid, per-phase device times with an L2 flush in front."""
+    lap = grid_laplacian(GRID_NX, GRID_NY)
+    n = lap.shape[0]
+    graph = engine.DeviceGraph.from_scipy(lap, dev)
+    cfg = engine.WalkConfig(W, P_HALT, L, seed=SEED)
+    torch.manual_seed(42)
+    f = torch.randn(L).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    v = torch.randn(n, T_RHS, device=dev, generator=gen)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        res = fn()
+        b.record(stream)
+        return res, (a, b)
+
+    def one():
+        visits = torch.zeros(1, dtype=torch.int64, device=dev)
+        st, e_walk = timed(lambda: engine.run_walker(graph, cfg, 0, n, visits=visits, count_columns=True,
+                                                     entries_scale_mode=_lib.SCALE_MUL_RECIP))
+        phi, e_comp = timed(lambda: engine._blocks_from_staging(st, cfg, n, _lib.SCALE_MUL_RECIP))
+        del st
+
+        def tr():
+            phi.build_transpose()
+            return phi.plan(f, T_RHS, merged=False)
+
+        plan, e_tr = timed(tr)
+        out = torch.empty((n, T_RHS), dtype=torch.float32, device=dev)
+        _, e_mv = timed(lambda: plan(v, out))
+        return visits, phi, dict(walk=e_walk, compact=e_comp, transpose=e_tr, matvec=e_mv)
+
+    for _ in range(3):
+        one()
+    runs = [one() for _ in range(5)]
+    torch.cuda.synchronize(dev)
+    ms = {k: sum(r[2][k][0].elapsed_time(r[2][k][1]) for r in runs) / len(runs) for k in ("walk", "compact", "transpose", "matvec")}
+    visits = int(runs[-1][0].item())
+    phi = runs[-1][1]
+    nnz = phi.nnz
+    _, e_union = timed(lambda: phi.build_union())
+    cg_plan, e_mat = timed(lambda: phi.plan(f, T_RHS, merged=True))
+    out = torch.empty((n, T_RHS), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        cg_plan(v, out)
+    cg_events = [timed(lambda: cg_plan(v, out))[1] for _ in range(20)]
+    torch.cuda.synchronize(dev)
+    cg_ms = sorted(a.elapsed_time(b) for a, b in cg_events)
+    step = sum(ms.values())
+    mv_bytes = 2 * nnz * 8 + 2 * L * (n + 1) * 4 + 4 * n * T_RHS * 4
+    nnz_u = phi.nnz_union
+    layout_bytes = 2 * nnz_u * 8 + 2 * (n + 1) * 4 + 4 * n * T_RHS * 4
+    peak, _ = peaks()
+    return {
+        "workload": "BASELINE.json configs[1]: sparse CSR GRF on 2D grid graph N=100k (316x316), walks_per_node=100, "
+                    "max_walk_length=5, p_halt=0.1, learnable modulator, t=16; one GPU (every rank measures its own copy; "
+                    "rank 0 reported); L2 flushed before every timed phase",
+        "value": visits / (step * 1e-3), "unit": UNIT, "ms_per_step": step, "phases_ms": ms,
+        "walker_steps_per_sec": visits / (ms["walk"] * 1e-3),
+        "matvec_per_length": {"ms": ms["matvec"], "algorithmic_gbs": mv_bytes / ms["matvec"] / 1e6,
+                              "frac": mv_bytes / ms["matvec"] / 1e6 / peak},
+        "cg_matvec_merged": {"ms": cg_ms[len(cg_ms) // 2], "ms_min": cg_ms[0],
+                             "algorithmic_gbs": mv_bytes / cg_ms[len(cg_ms) // 2] / 1e6,
+                             "frac": mv_bytes / cg_ms[len(cg_ms) // 2] / 1e6 / peak,
+                             "layout_gbs": layout_bytes / cg_ms[len(cg_ms) // 2] / 1e6,
+                             "layout_frac": layout_bytes / cg_ms[len(cg_ms) // 2] / 1e6 / peak,
+                             "nnz_union": nnz_u, "union_build_ms_once_per_phi": e_union[0].elapsed_time(e_union[1]),
+                             "materialize_ms_once_per_modulator": e_mat[0].elapsed_time(e_mat[1])},
+    }
+
+
+def cpu_baseline_leg(args):
     """The reference's CPU algorithm on this box's host cores, bounded sample (about 10-30 s)."""
     from oracle import cpu_baseline
 
+    lap, _ = cfg4_host_laplacian(args.scale, args.edges)
     cores = os.cpu_count() or 1
     n = lap.shape[0]
-    n_sample = 4 * GRID_NX * cores                        # four grid lines per core: ~1.3e4 walk-steps/core/line
-    starts = np.arange(min(n, n_sample))
+    rng = np.random.default_rng(11)
+    starts = np.sort(rng.choice(n, size=min(n, 8000 * cores), replace=False))
     dt, visits = cpu_baseline.time_sampler(lap, W, P_HALT, L, starts, n_processes=cores)
     out = {"value": visits / dt, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": f"{len(starts)} of {n} start nodes (x{W} walks, {visits} walk-steps, {dt:.1f} s), pure-Python "
-                     f"fork-pool port of sparse_sampler.py:72-132 in oracle/cpu_baseline.py"}
-    # the C restatement of the same algorithm, single thread, for scale
+           "sample": f"{len(starts)} of {n} start nodes drawn uniformly (x{W} walks, {visits} walk-steps, {dt:.1f} s), "
+                     f"pure-Python fork-pool port of sparse_sampler.py:72-132 in oracle/cpu_baseline.py"}
     from oracle import c_oracle
 
     t0 = time.perf_counter()
-    _, vis_c = c_oracle.step_matrices(lap, W, P_HALT, L, seed=SEED, start_lo=0, start_hi=min(n, 20 * GRID_NX),
+    sl = int(starts[len(starts) // 2])
+    _, vis_c = c_oracle.step_matrices(lap, W, P_HALT, L, seed=SEED, start_lo=sl, start_hi=min(n, sl + 20000),
                                       return_visits=True)
     out["c_port_single_thread"] = {"value": vis_c / (time.perf_counter() - t0), "unit": UNIT, "cores": 1}
     return out
@@ -435,7 +636,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=RMAT_SCALE, help="log2 of the node count of the R-MAT graph")
+    ap.add_argument("--edges", type=float, default=RMAT_EDGES, help="undirected edges (at least)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config2", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -177,6 +177,33 @@ __global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *stag
     }
 }
 
+// staging already holds finished entries (GrfWalkCfg.stage_entries): one warp moves a row's run
+__global__ void __launch_bounds__(256) compact_entries_kernel(const int2 *__restrict__ stage,
+                                                              const int32_t *__restrict__ blk_ptr, int64_t n_rows,
+                                                              int32_t L, int64_t stride, int2 *__restrict__ entries) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        const int2 *src = stage + r * stride;
+        const int32_t dst = __ldg(blk_ptr + r * L);
+        const int32_t c = __ldg(blk_ptr + (r + 1) * L) - dst;
+        for (int i0 = 0; i0 < c; i0 += 128) {  // four independent 8-byte loads per lane in flight
+            int2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < c) v[u] = __ldcs(src + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < c) entries[dst + i] = v[u];
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) count_from_steps_kernel(const int64_t *off_sm, int64_t n_rows, int32_t L,
                                                                int32_t *row_cnt) {
     const int64_t n = n_rows * L;
@@ -202,289 +229,6 @@ __global__ void __launch_bounds__(256) blocks_from_steps_kernel(const int64_t *o
                 e.col = pack_col(col[src + i], s);
                 e.val = (float)val[src + i];  // torch .float(): round to nearest even
                 entries[dst + i] = e;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Phi^T blocks
-// ---------------------------------------------------------------------------
-// A row's L per-length segments are contiguous and every entry carries its length in the top bits
-// of `col`, so a warp takes the whole row as one flat run: ~2 rounds of 32 entries per row at
-// config 2 instead of one (mostly short) round per length -- the kernels are bound by the latency
-// of the atomic round trips, i.e. by the number of rounds.
-__global__ void __launch_bounds__(256) transpose_count_kernel(const int32_t *blk_ptr, const GrfEntry *entries,
-                                                              int64_t n_rows, int32_t L, int32_t *tcnt) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        const int32_t b = blk_ptr[r * L], e = blk_ptr[(r + 1) * L];
-        for (int32_t i = b + lane; i < e; i += 32) {
-            const int32_t packed = entries[i].col;
-            atomicAdd(&tcnt[(int64_t)entry_col(packed) * L + entry_step(packed)], 1);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) transpose_fill_kernel(const int32_t *blk_ptr, const GrfEntry *entries,
-                                                             int64_t n_rows, int32_t L, int32_t *cursor,
-                                                             GrfEntry *tentries) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        const int32_t b = blk_ptr[r * L], e = blk_ptr[(r + 1) * L];
-        for (int32_t i = b + lane; i < e; i += 32) {
-            const GrfEntry src = entries[i];
-            const int s = entry_step(src.col);
-            const int32_t slot = atomicAdd(&cursor[(int64_t)entry_col(src.col) * L + s], 1);
-            GrfEntry dst;
-            dst.col = pack_col((int32_t)r, s);
-            dst.val = src.val;
-            tentries[slot] = dst;
-        }
-    }
-}
-
-// Slots inside one (column, length) segment were claimed in arbitrary order;
-// order them by row so that the layout (and the fp32 summation order of
-// Phi^T V) is deterministic.  Three tiers by segment length:
-//   <= 32   one thread per segment: keys (row << 5 | slot) sorted by a register
-//           sorting network (rows are unique and < 2^27, so the key is 32 bits),
-//           values re-read through the sorted slot index;
-//   <= 256  one warp per segment, register bitonic sort with shuffles;
-//   longer  (hub columns) one CTA per segment, bitonic network in global memory.
-// (v1 used a per-thread insertion sort in global memory: 420 us at config 2.)
-constexpr int kTinySeg = 8;
-constexpr int kShortSeg = 32;
-constexpr int kMidSeg = 256;
-
-template <int C>
-__device__ __forceinline__ void sort_segment_regs(GrfEntry *seg, int len) {
-    uint32_t key[C];
-    const uint32_t step_bits = (uint32_t)seg[0].col & ~kColMask;
-#pragma unroll
-    for (int i = 0; i < C; ++i)
-        key[i] = i < len ? ((((uint32_t)seg[i].col & kColMask) << 5) | (uint32_t)i) : 0xffffffffu;
-    sort_network_u32<C>(key);
-    float val[C];
-#pragma unroll
-    for (int i = 0; i < C; ++i) val[i] = i < len ? seg[key[i] & 31u].val : 0.f;
-#pragma unroll
-    for (int i = 0; i < C; ++i) {
-        if (i < len) {
-            GrfEntry e;
-            e.col = (int32_t)(step_bits | (key[i] >> 5));
-            e.val = val[i];
-            seg[i] = e;
-        }
-    }
-}
-
-// lists: [0] = number of mid segments, [1] = number of long segments, then the two lists
-//
-// A warp takes 32 consecutive segments (one per lane).  Their entries are one contiguous stretch of
-// tentries: it is copied to shared memory with coalesced 8-byte loads, every lane sorts its own
-// segment there, and the stretch is written back coalesced.  (One thread per segment straight on
-// global memory -- 32 lanes striding through 32 different segments -- took 66 us at config 2.)
-constexpr int kSortStage = 1024;  // entries a warp stages (32 segments of <= 32 entries always fit)
-
-__global__ void __launch_bounds__(128) transpose_sort_short_kernel(const int32_t *tblk_ptr, int64_t n_segs,
-                                                                   GrfEntry *tentries, int32_t *counts,
-                                                                   int32_t *mid_list, int32_t *long_list) {
-    __shared__ int2 stage_all[4][kSortStage];
-    const int lane = threadIdx.x & 31;
-    int2 *stage = stage_all[threadIdx.x >> 5];
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int2 *ent2 = reinterpret_cast<int2 *>(tentries);
-    for (int64_t g0 = warp0 * 32; g0 < n_segs; g0 += nwarps * 32) {
-        const int64_t g = g0 + lane;
-        int32_t b = 0, len = 0;
-        if (g < n_segs) {
-            b = tblk_ptr[g];
-            len = tblk_ptr[g + 1] - b;
-        }
-        // longer segments go to the warp / CTA tiers; their entries are staged and written back untouched
-        if (len > kMidSeg)
-            long_list[-atomicAdd(&counts[1], 1)] = (int32_t)g;  // grows downwards from the end
-        else if (len > kShortSeg)
-            mid_list[atomicAdd(&counts[0], 1)] = (int32_t)g;   // grows upwards
-        const bool mine = len > 1 && len <= kShortSeg;
-        if (!__any_sync(0xffffffffu, mine)) continue;
-        const int32_t base = __shfl_sync(0xffffffffu, b, 0);
-        const int last = (int)min((int64_t)31, n_segs - 1 - g0);
-        const int32_t total = __shfl_sync(0xffffffffu, b + len, last) - base;
-        const bool staged = total <= kSortStage;
-        GrfEntry *seg = tentries + b;
-        if (staged) {
-            for (int32_t i = lane; i < total; i += 32) stage[i] = ent2[base + i];
-            __syncwarp();
-            seg = reinterpret_cast<GrfEntry *>(stage) + (b - base);
-        }
-        if (mine) {
-            if (len <= kTinySeg)
-                sort_segment_regs<kTinySeg>(seg, len);
-            else if (len <= 16)
-                sort_segment_regs<16>(seg, len);
-            else
-                sort_segment_regs<kShortSeg>(seg, len);
-        }
-        if (staged) {
-            __syncwarp();
-            for (int32_t i = lane; i < total; i += 32) ent2[base + i] = stage[i];
-            __syncwarp();
-        }
-    }
-}
-
-template <int KPL>
-__device__ __forceinline__ void sort_segment_warp(GrfEntry *seg, int len, int lane) {
-    unsigned long long key[KPL];
-#pragma unroll
-    for (int r = 0; r < KPL; ++r) {
-        const int i = r * 32 + lane;
-        unsigned long long kk = ~0ull;
-        if (i < len) {
-            const GrfEntry e = seg[i];
-            kk = ((unsigned long long)(uint32_t)e.col << 32) | (unsigned long long)(uint32_t)__float_as_int(e.val);
-        }
-        key[r] = kk;
-    }
-    __syncwarp();
-    warp_bitonic_sort<unsigned long long, KPL>(key, lane);
-#pragma unroll
-    for (int r = 0; r < KPL; ++r) {
-        const int i = lane * KPL + r;
-        if (i < len) {
-            GrfEntry e;
-            e.col = (int32_t)(uint32_t)(key[r] >> 32);
-            e.val = __int_as_float((int)(uint32_t)key[r]);
-            seg[i] = e;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128) transpose_sort_mid_kernel(const int32_t *tblk_ptr, GrfEntry *tentries,
-                                                                 const int32_t *counts, const int32_t *mid_list) {
-    const int lane = threadIdx.x & 31;
-    const int n_mid = counts[0];
-    const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-    for (int li = warp0; li < n_mid; li += nwarps) {
-        const int32_t g = mid_list[li];
-        const int32_t b = tblk_ptr[g];
-        const int len = tblk_ptr[g + 1] - b;
-        GrfEntry *seg = tentries + b;
-        if (len <= 64)
-            sort_segment_warp<2>(seg, len, lane);
-        else if (len <= 128)
-            sort_segment_warp<4>(seg, len, lane);
-        else
-            sort_segment_warp<8>(seg, len, lane);
-        __syncwarp();
-    }
-}
-
-// One CTA per long segment.  Segments of up to kSmemSortCap entries (128 KB) are staged in shared
-// memory, sorted there and written back; only longer ones run the network on global memory.  (On an
-// R-MAT graph of 2^20 nodes 71 k segments hold 60 % of all entries, the largest 83 k entries: the
-// global-memory network took 26.9 ms for them.)
-// Three launches by size class, (256, 1024] with 256 threads, (1024, 4096] with 512, the rest with
-// 1024: a small segment spends its time in the ~50 barriers of the network, which cost less with
-// fewer warps, and the small classes leave room for several CTAs per SM.
-constexpr int kSmemSortCap = 16384;
-
-// Bitonic network in its all-ascending form (mirror step, then half-cleaners): every comparator
-// moves the smaller key to the lower index, so the virtual +inf padding at [len, np2) never moves
-// and comparators that touch it are simply skipped.  All threads of the CTA call these together.
-__device__ __forceinline__ void sort_compare_swap(GrfEntry *seg, uint32_t lo, uint32_t hi) {
-    const GrfEntry a = seg[lo], bb = seg[hi];
-    if (a.col > bb.col) {
-        seg[lo] = bb;
-        seg[hi] = a;
-    }
-}
-
-__device__ __forceinline__ void sort_mirror_stage(GrfEntry *seg, uint32_t len, uint32_t np2, uint32_t k) {
-    const uint32_t half = k >> 1;
-    for (uint32_t c = threadIdx.x; c < np2 / 2; c += blockDim.x) {
-        const uint32_t blk = c / half, off = c - blk * half;
-        const uint32_t lo = blk * k + off, hi = blk * k + k - 1 - off;
-        if (hi < len) sort_compare_swap(seg, lo, hi);
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void sort_clean_stages(GrfEntry *seg, uint32_t len, uint32_t np2, uint32_t j_from,
-                                                  uint32_t j_to) {
-    for (uint32_t j = j_from; j >= j_to && j > 0; j >>= 1) {
-        for (uint32_t c = threadIdx.x; c < np2 / 2; c += blockDim.x) {
-            const uint32_t lo = ((c & ~(j - 1)) << 1) | (c & (j - 1));
-            const uint32_t hi = lo + j;
-            if (hi < len) sort_compare_swap(seg, lo, hi);
-        }
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ void sort_copy(GrfEntry *dst, const GrfEntry *src, uint32_t n) {
-    const int2 *s2 = reinterpret_cast<const int2 *>(src);
-    int2 *d2 = reinterpret_cast<int2 *>(dst);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d2[i] = s2[i];
-    __syncthreads();
-}
-
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads) transpose_sort_long_kernel(const int32_t *tblk_ptr, GrfEntry *tentries,
-                                                                       const int32_t *counts,
-                                                                       const int32_t *long_list, uint32_t len_above,
-                                                                       uint32_t len_upto, uint32_t smem_cap) {
-    extern __shared__ __align__(16) unsigned char sort_smem[];
-    GrfEntry *sbuf = reinterpret_cast<GrfEntry *>(sort_smem);
-    const int32_t n_long = counts[1];
-    for (int32_t li = blockIdx.x; li < n_long; li += gridDim.x) {
-        const int32_t g = long_list[-li];
-        const int32_t b = tblk_ptr[g];
-        const uint32_t len = (uint32_t)(tblk_ptr[g + 1] - b);
-        if (len <= len_above || len > len_upto) continue;  // another launch's size class (uniform over the CTA)
-        GrfEntry *seg = tentries + b;
-        if (len <= smem_cap) {
-            // the whole segment fits: one trip through shared memory
-            const uint32_t np2 = next_pow2(len);
-            sort_copy(sbuf, seg, len);
-            for (uint32_t k = 2; k <= np2; k <<= 1) {
-                sort_mirror_stage(sbuf, len, np2, k);
-                sort_clean_stages(sbuf, len, np2, k >> 2, 1);
-            }
-            sort_copy(seg, sbuf, len);
-            continue;
-        }
-        // Longer than the staging area (smem_cap = T entries, a power of two): every stage whose
-        // comparators stay inside a T-aligned tile runs on the tile in shared memory; only the
-        // mirror steps and the half-cleaners at distance >= T touch global memory.  For the 83 k-entry
-        // hub segment of the R-MAT test graph that is 6 global stages instead of 153.
-        const uint32_t T = smem_cap;
-        const uint32_t np2 = next_pow2(len);
-        for (uint32_t t0 = 0; t0 < len; t0 += T) {  // tiles sorted on their own (k = 2 .. T)
-            const uint32_t tl = min(T, len - t0);
-            sort_copy(sbuf, seg + t0, tl);
-            for (uint32_t k = 2; k <= T; k <<= 1) {
-                sort_mirror_stage(sbuf, tl, T, k);
-                sort_clean_stages(sbuf, tl, T, k >> 2, 1);
-            }
-            sort_copy(seg + t0, sbuf, tl);
-        }
-        for (uint32_t k = 2 * T; k <= np2; k <<= 1) {
-            sort_mirror_stage(seg, len, np2, k);
-            sort_clean_stages(seg, len, np2, k >> 2, T);  // distances k/4 .. T on global memory
-            for (uint32_t t0 = 0; t0 < len; t0 += T) {      // distances T/2 .. 1 inside the tiles
-                const uint32_t tl = min(T, len - t0);
-                sort_copy(sbuf, seg + t0, tl);
-                sort_clean_stages(sbuf, tl, T, T >> 1, 1);
-                sort_copy(seg + t0, sbuf, tl);
             }
         }
     }
@@ -610,6 +354,17 @@ extern "C" int grf_compact_blocks(const int32_t *stage_col, const double *stage_
     return check_cuda(cudaGetLastError(), "compact_blocks_kernel launch");
 }
 
+extern "C" int grf_compact_entries(const GrfEntry *stage_entries, const int32_t *blk_ptr, int64_t n_rows,
+                                   int32_t n_steps, int64_t stage_stride, GrfEntry *entries, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream);
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && stage_stride >= 1, "grf_compact_entries: bad shape");
+    if (n_rows == 0) return GRF_OK;
+    GRF_REQUIRE(stage_entries && blk_ptr && entries, "grf_compact_entries: null buffer");
+    compact_entries_kernel<<<grid_for_warps(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const int2 *)stage_entries, blk_ptr, n_rows, n_steps, stage_stride, (int2 *)entries);
+    return check_cuda(cudaGetLastError(), "compact_entries_kernel launch");
+}
+
 extern "C" int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps,
                                     int32_t *row_cnt, void *stream) {
     GRF_ON_STREAM_DEVICE(stream);
@@ -665,90 +420,4 @@ extern "C" int grf_nonempty_rows(const int32_t *blk_ptr, int64_t n_rows, int32_t
     if (rc != GRF_OK) return rc;
     scatter_ids_kernel<<<(int)g, 256, 0, st>>>(flags, pos, n_rows, ids);
     return check_cuda(cudaGetLastError(), "nonempty_rows kernels launch");
-}
-
-static int64_t transpose_cursor_bytes(int64_t n_cols, int32_t n_steps) {
-    return ((n_cols * n_steps + 2) * (int64_t)sizeof(int32_t) + 15) / 16 * 16;
-}
-
-extern "C" int64_t grf_transpose_workspace_bytes(int64_t n_cols, int32_t n_steps) {
-    // [segment counts, later the fill cursor / sort work lists: n_cols*L + 2 ints][scan workspace][census: 8 ints]
-    return transpose_cursor_bytes(n_cols, n_steps) + grf_scan_workspace_bytes(n_cols * n_steps) + 32;
-}
-
-extern "C" int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                                     int32_t n_steps, const int32_t *col_counts, int32_t *tblk_ptr, void *workspace,
-                                     int32_t census_threshold, int32_t *census_host, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
-    GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_offsets: bad shape");
-    GRF_REQUIRE(tblk_ptr && workspace, "grf_transpose_offsets: null buffer");
-    GRF_REQUIRE(!census_host || census_threshold >= 1, "grf_transpose_offsets: bad census threshold");
-    cudaStream_t st = (cudaStream_t)stream;
-    int32_t *tcnt = (int32_t *)workspace;
-    char *scan_ws = (char *)workspace + transpose_cursor_bytes(n_cols, n_steps);
-    int32_t *census = (int32_t *)(scan_ws + grf_scan_workspace_bytes(n_cols * n_steps));
-    if (col_counts) {
-        tcnt = const_cast<int32_t *>(col_counts);  // the walker counted while it emitted the entries
-    } else if (n_cols > 0) {
-        GRF_CUDA_OK(cudaMemsetAsync(tcnt, 0, (size_t)n_cols * n_steps * sizeof(int32_t), st));
-        if (n_rows > 0) {
-            GRF_REQUIRE(blk_ptr, "grf_transpose_offsets: null blk_ptr");
-            transpose_count_kernel<<<grid_for_warps(n_rows, 256), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps,
-                                                                                 tcnt);
-            GRF_CUDA_OK(cudaGetLastError());
-        }
-    }
-    int rc = grf_scan_counts(tcnt, n_cols, n_steps, GRF_ORDER_ROW_MAJOR, tblk_ptr, 0, scan_ws, stream);
-    if (rc != GRF_OK) return rc;
-    if (census_host) {
-        // row statistics of both sides while the fill / sort kernels that follow keep the GPU busy: the
-        // host reads them from pinned memory after an event recorded behind this call
-        rc = grf_row_census(blk_ptr, n_rows, n_steps, census_threshold, census, stream);
-        if (rc != GRF_OK) return rc;
-        rc = grf_row_census(tblk_ptr, n_cols, n_steps, census_threshold, census + 3, stream);
-        if (rc != GRF_OK) return rc;
-        GRF_CUDA_OK(cudaMemcpyAsync(census_host, census, 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    }
-    return GRF_OK;
-}
-
-extern "C" int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                                  int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor, GrfEntry *tentries,
-                                  void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
-    GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_fill: bad shape");
-    if (n_cols == 0 || n_rows == 0) return GRF_OK;
-    GRF_REQUIRE(blk_ptr && tblk_ptr && cursor, "grf_transpose_fill: null buffer");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n_segs = n_cols * n_steps;
-    GRF_CUDA_OK(cudaMemcpyAsync(cursor, tblk_ptr, (size_t)n_segs * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    transpose_fill_kernel<<<grid_for_warps(n_rows, 256), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps, cursor,
-                                                                        tentries);
-    GRF_CUDA_OK(cudaGetLastError());
-    // deterministic order inside every segment; `cursor` is dead now and is reused for the
-    // work lists: [n_mid, n_long | mid list growing up ... long list growing down]; at most
-    // n_segs segments are listed in total, which is what the n_segs + 2 ints of scratch hold
-    GRF_CUDA_OK(cudaMemsetAsync(cursor, 0, 2 * sizeof(int32_t), st));
-    if (n_segs >= 2) {
-        int64_t g = (n_segs + 127) / 128;
-        if (g > (int64_t)kSmCount * 64) g = (int64_t)kSmCount * 64;
-        int32_t *mid_list = cursor + 2;
-        int32_t *long_list = cursor + 2 + (n_segs - 1);
-        transpose_sort_short_kernel<<<(int)g, 128, 0, st>>>(tblk_ptr, n_segs, tentries, cursor, mid_list, long_list);
-        GRF_CUDA_OK(cudaGetLastError());
-        transpose_sort_mid_kernel<<<kSmCount * 8, 128, 0, st>>>(tblk_ptr, tentries, cursor, mid_list);
-        GRF_CUDA_OK(cudaGetLastError());
-        const size_t big_smem = (size_t)kSmemSortCap * sizeof(GrfEntry);
-        GRF_CUDA_OK(cudaFuncSetAttribute(transpose_sort_long_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)big_smem));
-        transpose_sort_long_kernel<256><<<kSmCount * 8, 256, 1024 * sizeof(GrfEntry), st>>>(
-            tblk_ptr, tentries, cursor, long_list, (uint32_t)kMidSeg, 1024u, 1024u);
-        GRF_CUDA_OK(cudaGetLastError());
-        transpose_sort_long_kernel<512><<<kSmCount * 4, 512, 4096 * sizeof(GrfEntry), st>>>(
-            tblk_ptr, tentries, cursor, long_list, 1024u, 4096u, 4096u);
-        GRF_CUDA_OK(cudaGetLastError());
-        transpose_sort_long_kernel<1024><<<kSmCount, 1024, big_smem, st>>>(
-            tblk_ptr, tentries, cursor, long_list, 4096u, 0xffffffffu, (uint32_t)kSmemSortCap);
-    }
-    return check_cuda(cudaGetLastError(), "transpose kernels launch");
 }

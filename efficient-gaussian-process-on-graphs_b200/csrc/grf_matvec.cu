@@ -47,8 +47,27 @@ struct Vec<4> {
     float4 v;
     __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void load(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+    // gathered once, never again from this SM: do not allocate the line in L1 (a miss then costs one pass
+    // through the L1 data stage instead of two -- fill, then read; ncu on the power-law Phi: 1.75
+    // wavefronts per gathered entry at a 27 % hit rate)
+    __device__ __forceinline__ void load_stream(const float *p) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "l"(p));
+    }
     __device__ __forceinline__ void load_shared(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
     __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+    __device__ __forceinline__ void add_from(const float *p, int ncols, bool vec_ok) {
+        if (ncols >= 4 && vec_ok) {
+            const float4 o = *reinterpret_cast<const float4 *>(p);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        } else {
+            v.x += p[0];
+            if (ncols > 1) v.y += p[1];
+            if (ncols > 2) v.z += p[2];
+            if (ncols > 3) v.w += p[3];
+        }
+    }
     // first `ncols` (1..4) columns; vector store only when all four are valid and p is 16-byte aligned
     __device__ __forceinline__ void store_cols(float *p, int ncols, bool vec_ok) const {
         if (ncols >= 4 && vec_ok) {
@@ -75,8 +94,12 @@ struct Vec<1> {
     float v;
     __device__ __forceinline__ void zero() { v = 0.f; }
     __device__ __forceinline__ void load(const float *p) { v = __ldg(p); }
+    __device__ __forceinline__ void load_stream(const float *p) {
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    }
     __device__ __forceinline__ void load_shared(const float *p) { v = *p; }
     __device__ __forceinline__ void store(float *p) const { *p = v; }
+    __device__ __forceinline__ void add_from(const float *p, int, bool) { v += *p; }
     __device__ __forceinline__ void store_cols(float *p, int, bool) const { *p = v; }
     __device__ __forceinline__ void fma(float a, const Vec &x) { v = fmaf(a, x.v, v); }
     __device__ __forceinline__ float dot(const Vec &x) const { return v * x.v; }
@@ -115,7 +138,8 @@ __host__ __device__ constexpr int epl(int tpr) { return tpr >= 16 ? 1 : (tpr >= 
 // longest row of the warp's 32/TPR rows decides), so every shuffle uses the constant full
 // mask: with a per-group mask nvcc expands each __shfl_sync into a MATCH/REDUX/VOTE loop
 // (ncu: ~10 extra instructions per shuffle, 4.6 warp-instructions per entry).
-template <int TPR, int VEC, bool kShared>
+constexpr int kGatherCached = 0, kGatherShared = 1, kGatherStream = 2;
+template <int TPR, int VEC, int kMode>
 __device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int32_t b, int32_t e,
                                              int2 (&nxt)[epl(TPR)], int32_t next_b, int32_t next_e,
                                              const float *__restrict__ fs, const float *X, uint32_t ldx,
@@ -173,8 +197,10 @@ __device__ __forceinline__ Vec<VEC> spmm_row(const int2 *__restrict__ ent2, int3
                 const int q = (m0 + m) / TPR, j = (m0 + m) % TPR;
                 const uint32_t off = TPR == 1 ? cl[q] : __shfl_sync(gmask, cl[q], j, TPR);
                 a[m] = TPR == 1 ? sv[q] : __shfl_sync(gmask, sv[q], j, TPR);
-                if (kShared)
+                if (kMode == kGatherShared)
                     x[m].load_shared(X + (off + (uint32_t)c0));
+                else if (kMode == kGatherStream)
+                    x[m].load_stream(X + (off + (uint32_t)c0));
                 else
                     x[m].load(X + (off + (uint32_t)c0));
             }
@@ -197,7 +223,7 @@ __device__ __forceinline__ void load_first_round(const int2 *__restrict__ ent2, 
     }
 }
 
-template <int TPR, int VEC>
+template <int TPR, int VEC, bool kStream = false>
 __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(const int32_t *__restrict__ ptr,
                                                           const GrfEntry *__restrict__ ent,
                                                           const float *__restrict__ f, int32_t L,
@@ -207,7 +233,8 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
                                                           float *__restrict__ Y, int64_t ldy, int32_t t,
                                                           int32_t t_store, int32_t vec_store, int32_t long_thresh,
                                                           const int2 *__restrict__ chunk_bounds,
-                                                          int32_t out_by_row, int32_t *__restrict__ sched) {
+                                                          int32_t out_by_row, int32_t *__restrict__ sched,
+                                                          int32_t accumulate) {
     // sched != NULL: {ticket, finished warps}, both zero at launch and zero again at exit.  The first
     // GRF_SPMM_STATIC_PCT % of the row groups go to the warps by fixed stride (neighbouring rows stay
     // on one SM), the rest by an atomic ticket fetched one iteration ahead: with skewed row lengths
@@ -333,9 +360,14 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
             const int c0 = (tile * TPR + sub) * VEC;
             const bool live = mine && c0 < t;
             const bool last_tile = tile + 1 == n_tiles;
-            const Vec<VEC> acc = spmm_row<TPR, VEC, false>(ent2, b, e, nxt, last_tile ? nb : b, last_tile ? ne : e,
-                                                           fs, X, (uint32_t)ldx, 0, c0 < t ? c0 : 0, live, sub);
-            if (live && c0 < t_store) acc.store_cols(Y + orow * ldy + c0, t_store - c0, vec_store != 0);
+            Vec<VEC> acc = spmm_row<TPR, VEC, kStream ? kGatherStream : kGatherCached>(
+                ent2, b, e, nxt, last_tile ? nb : b, last_tile ? ne : e, fs, X, (uint32_t)ldx, 0, c0 < t ? c0 : 0, live,
+                sub);
+            if (live && c0 < t_store) {
+                // accumulate: Y += (the second and later row blocks of a block-wise Phi^T add to U)
+                if (accumulate) acc.add_from(Y + orow * ldy + c0, t_store - c0, vec_store != 0);
+                acc.store_cols(Y + orow * ldy + c0, t_store - c0, vec_store != 0);
+            }
         }
         b = nb;
         e = ne;
@@ -428,9 +460,9 @@ __global__ void __launch_bounds__(512, 1) spmm_tiled_kernel(const int32_t *__res
                 const bool live = row < r1 && col_live;
                 Vec<4> acc;
                 if (tiled)
-                    acc = spmm_row<TPR, 4, true>(ent2, b, e, nxt, nb, ne, fs, tile, (uint32_t)ldt, cmin, c0, live, sub);
+                    acc = spmm_row<TPR, 4, kGatherShared>(ent2, b, e, nxt, nb, ne, fs, tile, (uint32_t)ldt, cmin, c0, live, sub);
                 else
-                    acc = spmm_row<TPR, 4, false>(ent2, b, e, nxt, nb, ne, fs, X, (uint32_t)ldx, 0, c0, live, sub);
+                    acc = spmm_row<TPR, 4, kGatherCached>(ent2, b, e, nxt, nb, ne, fs, X, (uint32_t)ldx, 0, c0, live, sub);
                 if (live) acc.store(Y + row * ldy + c0);
                 b = nb;
                 e = ne;
@@ -483,7 +515,7 @@ __global__ void __launch_bounds__(256) spmv_coop_kernel(const int32_t *__restric
                                                         int64_t row_lo, int64_t n_rows, const float *__restrict__ X,
                                                         int64_t ldx, float *__restrict__ Y, int64_t ldy,
                                                         int32_t long_thresh, const int2 *__restrict__ chunk_bounds,
-                                                        int32_t out_by_row) {
+                                                        int32_t out_by_row, int32_t accumulate) {
     __shared__ float fs[kMaxSteps];
     if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
     __syncthreads();
@@ -551,7 +583,7 @@ __global__ void __launch_bounds__(256) spmv_coop_kernel(const int32_t *__restric
         }
         if (mine && sub == 0) {
 #pragma unroll
-            for (int j = 0; j < T; ++j) Y[orow * ldy + j] = acc[j];
+            for (int j = 0; j < T; ++j) Y[orow * ldy + j] = accumulate ? Y[orow * ldy + j] + acc[j] : acc[j];
         }
     }
 }
@@ -641,7 +673,7 @@ __global__ void __launch_bounds__(256) long_reduce_kernel(const int32_t *__restr
                                                           const int32_t *__restrict__ chunk_ptr,
                                                           const float *__restrict__ partial, int64_t ldp,
                                                           float *__restrict__ Y, int64_t ldy, int32_t t,
-                                                          int32_t n_long) {
+                                                          int32_t n_long, int32_t accumulate) {
     const int64_t total = (int64_t)n_long * t;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
          g += (int64_t)gridDim.x * blockDim.x) {
@@ -649,7 +681,8 @@ __global__ void __launch_bounds__(256) long_reduce_kernel(const int32_t *__restr
         const int c = (int)(g - (int64_t)i * t);
         float acc = 0.f;
         for (int32_t k = chunk_ptr[i]; k < chunk_ptr[i + 1]; ++k) acc += partial[(int64_t)k * ldp + c];
-        Y[(int64_t)rows[i] * ldy + c] = acc;
+        float *dst = Y + (int64_t)rows[i] * ldy + c;
+        *dst = accumulate ? *dst + acc : acc;
     }
 }
 
@@ -802,6 +835,23 @@ static inline bool aligned16(const void *p);
         }                                                                        \
     } while (0)
 
+// the streaming-gather instantiations exist for the float4 shapes only (t > 2)
+#define GRF_DISPATCH_SPMM(shape, stream_gather, ...)                                                \
+    do {                                                                                            \
+        if ((stream_gather) && (shape).vec == 4) {                                                  \
+            switch ((shape).tpr) {                                                                  \
+                case 1: spmm_blocks_kernel<1, 4, true> __VA_ARGS__; break;                          \
+                case 2: spmm_blocks_kernel<2, 4, true> __VA_ARGS__; break;                          \
+                case 4: spmm_blocks_kernel<4, 4, true> __VA_ARGS__; break;                          \
+                case 8: spmm_blocks_kernel<8, 4, true> __VA_ARGS__; break;                          \
+                case 16: spmm_blocks_kernel<16, 4, true> __VA_ARGS__; break;                        \
+                default: spmm_blocks_kernel<32, 4, true> __VA_ARGS__; break;                        \
+            }                                                                                       \
+        } else {                                                                                    \
+            GRF_DISPATCH_SHAPE(spmm_blocks_kernel, shape, __VA_ARGS__);                             \
+        }                                                                                           \
+    } while (0)
+
 }  // namespace grf
 
 using namespace grf;
@@ -812,7 +862,7 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
                             const int32_t *row_ids, int64_t n_tasks, int64_t row_lo, int64_t n_rows,
                             const GrfLongRows *lr, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t t_valid,
                             bool vec_ok, bool out_by_row, int64_t avg_row_len, int64_t x_rows, int32_t *sched,
-                            cudaStream_t st) {
+                            bool accumulate, bool stream_gather, cudaStream_t st) {
     // vec_ok: X rows are 16-byte aligned and padded to a multiple of 4 columns -> compute the padded
     // column count with float4 gathers; only the t_valid real columns are stored to Y
     const bool split = lr && lr->n_long > 0 && (!row_ids || out_by_row);
@@ -848,16 +898,16 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
         GRF_COOP_T(8, GRID, __VA_ARGS__)        \
     }
         GRF_COOP_LAUNCH(grid_of(n_tasks), ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy,
-                        split ? lr->threshold : 0, nullptr, out_by_row ? 1 : 0);
+                        split ? lr->threshold : 0, nullptr, out_by_row ? 1 : 0, accumulate ? 1 : 0);
         GRF_CUDA_OK(cudaGetLastError());
         if (split) {
             GRF_COOP_LAUNCH(grid_of(lr->n_chunks), ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
-                            lr->partial, lr->ld, 0, (const int2 *)lr->chunk_bounds, 0);
+                            lr->partial, lr->ld, 0, (const int2 *)lr->chunk_bounds, 0, 0);
             GRF_CUDA_OK(cudaGetLastError());
             int64_t g = ((int64_t)lr->n_long * t_valid + 255) / 256;
             if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
             long_reduce_kernel<<<(int)g, 256, 0, st>>>(lr->rows, lr->chunk_ptr, lr->partial, lr->ld, Y, ldy, t_valid,
-                                                       lr->n_long);
+                                                       lr->n_long, accumulate ? 1 : 0);
             GRF_CUDA_OK(cudaGetLastError());
         }
 #undef GRF_COOP_LAUNCH
@@ -869,24 +919,24 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
     const int32_t vec_store = (ldy % 4 == 0) && aligned16(Y);
     const Shape sh = pick_shape(t, vec_ok);
     const int grid = spmm_grid(n_tasks, sh.tpr);
-    GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
-                       <<<grid, 256, 0, st>>>(ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy, t,
-                                              ldy >= t ? t : t_valid, vec_store, split ? lr->threshold : 0, nullptr,
-                                              out_by_row ? 1 : 0, sched));
+    GRF_DISPATCH_SPMM(sh, stream_gather,
+                      <<<grid, 256, 0, st>>>(ptr, ent, f, L, row_ids, n_tasks, row_lo, n_rows, X, ldx, Y, ldy, t,
+                                             ldy >= t ? t : t_valid, vec_store, split ? lr->threshold : 0, nullptr,
+                                             out_by_row ? 1 : 0, sched, accumulate ? 1 : 0));
     GRF_CUDA_OK(cudaGetLastError());
     if (split) {
         GRF_REQUIRE(lr->ld >= t, "grf_phi_matvec: long-row partial buffer narrower than the padded column count");
         const int32_t pvec = (lr->ld % 4 == 0) && aligned16(lr->partial);
         const int gridc = spmm_grid(lr->n_chunks, sh.tpr);
-        GRF_DISPATCH_SHAPE(spmm_blocks_kernel, sh,
-                           <<<gridc, 256, 0, st>>>(ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
-                                                   lr->partial, lr->ld, t, t, pvec, 0,
-                                                   (const int2 *)lr->chunk_bounds, 0, sched));
+        GRF_DISPATCH_SPMM(sh, stream_gather,
+                          <<<gridc, 256, 0, st>>>(ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
+                                                  lr->partial, lr->ld, t, t, pvec, 0,
+                                                  (const int2 *)lr->chunk_bounds, 0, sched, 0));
         GRF_CUDA_OK(cudaGetLastError());
         int64_t g = ((int64_t)lr->n_long * t + 255) / 256;
         if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
         long_reduce_kernel<<<(int)g, 256, 0, st>>>(lr->rows, lr->chunk_ptr, lr->partial, lr->ld, Y, ldy,
-                                                   ldy >= t ? t : t_valid, lr->n_long);
+                                                   ldy >= t ? t : t_valid, lr->n_long, accumulate ? 1 : 0);
         GRF_CUDA_OK(cudaGetLastError());
     }
     return GRF_OK;
@@ -898,7 +948,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
     GRF_ON_STREAM_DEVICE(stream);
     GRF_REQUIRE(phi && f, "grf_phi_matvec: null phi/f");
     GRF_REQUIRE(t >= 1, "grf_phi_matvec: t must be >= 1");
-    GRF_REQUIRE((which & 3) >= 1 && which <= 15, "grf_phi_matvec: which must be 1, 2 or 3 (+4, +8 flags)");
+    GRF_REQUIRE((which & 3) >= 1 && which <= 63, "grf_phi_matvec: which must be 1, 2 or 3 (+4, +8, +16, +32 flags)");
     GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_matvec: n_steps out of range");
     GRF_REQUIRE(phi->n_cols <= (1ll << kStepShift) && phi->n_rows <= (1ll << kStepShift),
                 "grf_phi_matvec: more than 2^27 rows or columns per GPU");
@@ -910,6 +960,8 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
     const int64_t avg_len = phi->nnz > 0 && phi->n_rows > 0 ? phi->nnz / phi->n_rows : 0;  // entries per row of Phi
     const int tile_mode = (which >> 2) & 1;  // +4: never use the shared-memory-tiled kernel
     const bool x2_unique = (which >> 3) & 1;  // +8: x2 has no repeated ids and vfull was zeroed once
+    const bool accumulate = (which >> 4) & 1;  // +16: U += (later row blocks of a block-wise Phi^T)
+    const bool stream_gather = (which >> 5) & 1;  // +32: L1::no_allocate gathers
     which &= 3;
 
     if (which & 1) {
@@ -920,7 +972,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         const bool scatter_half = x2 && phi->blk_ptr && n2 * 16 < phi->n_rows;
         if (scatter_half) {
             // small row subset: scatter from the selected rows of Phi instead of a pass over Phi^T
-            GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
+            if (!accumulate) GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
             if (n2 > 0) {
                 int64_t g = (n2 + 7) / 8;
                 if (g > (int64_t)kSmCount * 8) g = (int64_t)kSmCount * 8;
@@ -959,15 +1011,16 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
             // done above
         } else if (phi->n_cols > 0 && phi->n_rows == 0) {
             // empty shard: its partial sum is zero (and there is no row of V to read)
-            GRF_CUDA_OK(cudaMemset2DAsync(u, (size_t)ldu * sizeof(float), 0, (size_t)t * sizeof(float),
-                                          (size_t)phi->n_cols, st));
+            if (!accumulate)
+                GRF_CUDA_OK(cudaMemset2DAsync(u, (size_t)ldu * sizeof(float), 0, (size_t)t * sizeof(float),
+                                              (size_t)phi->n_cols, st));
         } else if (phi->n_cols > 0) {
             const int32_t t4 = (t + 3) & ~3;
             // one or two columns: scalar lanes beat float4 gathers that are 3/4 padding
             const bool vec_ok = t > 2 && (lds % 4 == 0) && (ldu % 4 == 0) && lds >= t4 && ldu >= t4 && aligned16(src) &&
                                 aligned16(u);
             int tiled = 0;
-            if (vec_ok && t % 4 == 0 && !(tile_mode & 1)) {
+            if (vec_ok && t % 4 == 0 && !(tile_mode & 1) && !accumulate) {
                 tiled = try_launch_tiled(phi->tblk_ptr, phi->tentries, f, L, phi->n_cols, phi->twin,
                                          phi->twin_max_width, src, lds, u, ldu, t, st);
                 if (tiled < 0) return tiled;
@@ -976,15 +1029,17 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
                 int rc;
                 if (phi->tcols) {
                     // only the listed columns (those this shard touches, in any order); the others are zero
-                    if (phi->n_tcols < phi->n_cols)
+                    if (phi->n_tcols < phi->n_cols && !accumulate)
                         GRF_CUDA_OK(cudaMemsetAsync(u, 0, (size_t)phi->n_cols * ldu * sizeof(float), st));
                     rc = phi->n_tcols == 0
                              ? GRF_OK
                              : launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, phi->tcols, phi->n_tcols, 0,
-                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, avg_len, phi->n_rows, phi->sched, st);
+                                                phi->n_cols, phi->long_t, src, lds, u, ldu, t, vec_ok, true, avg_len, phi->n_rows, phi->sched,
+                                                accumulate, stream_gather, st);
                 } else {
                     rc = launch_spmm_pass(phi->tblk_ptr, phi->tentries, f, L, nullptr, phi->n_cols, 0, phi->n_cols,
-                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, avg_len, phi->n_rows, phi->sched, st);
+                                          phi->long_t, src, lds, u, ldu, t, vec_ok, false, avg_len, phi->n_rows, phi->sched,
+                                          accumulate, stream_gather, st);
                 }
                 if (rc != GRF_OK) return rc;
             }
@@ -1003,7 +1058,8 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
         }
         if (!tiled) {
             const int rc = launch_spmm_pass(phi->blk_ptr, phi->entries, f, L, x1, n1, phi->row_lo, phi->n_rows,
-                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, avg_len, phi->n_cols, phi->sched, st);
+                                            phi->long_fwd, u, ldu, out, ldo, t, vec_ok, false, avg_len, phi->n_cols, phi->sched,
+                                            false, stream_gather, st);
             if (rc != GRF_OK) return rc;
         }
     }

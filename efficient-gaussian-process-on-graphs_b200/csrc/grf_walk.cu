@@ -27,6 +27,8 @@
 // + col 4 B + val 8 B + staging write 12 B/(merged entry); three dependent
 // random 32-B sectors per step => latency / sector bound, not bandwidth bound.
 
+#include <stdlib.h>
+
 #include "grf_common.cuh"
 
 namespace grf {
@@ -35,7 +37,7 @@ struct WalkParams {
     const int32_t *row_ptr;
     const int32_t *col_idx;
     const double *val;
-    const double *scaled_val;
+    const GrfEdge *edges;
     int64_t start_lo;
     int64_t n_local;
     int32_t W, L, Wp, wbits;
@@ -52,7 +54,42 @@ struct WalkParams {
     unsigned long long *visits;
     uint32_t group_bytes, loads_bytes, nodes_bytes, sorted_bytes;
     int32_t *col_counts;  // optional [n_nodes][L]: entries per (column, length), for the Phi^T offsets
+    long long trace_base;  // replay: trace element 0 belongs to this walk id
+    GrfEntry *stage_ent;   // optional: finished Phi entries instead of (stage_col, stage_sum)
+    int32_t scale_mode;
+    double recip_w, w_as_double;
 };
+
+// L2 eviction hints (createpolicy + ld.global.L2::cache_hint).  On a graph that does not fit L2 (config 4:
+// 0.6 GB of columns, 1.2 GB of load factors) every gathered edge is used once and streams through; the
+// 17 MB row-pointer array is hit by every step and should stay -- without the hints ncu shows a 15 % L2 hit
+// rate and three DRAM sectors per walk-step.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int32_t ld_keep_s32(const int32_t *ptr, uint64_t pol) {
+    int32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ GrfEdge ld_stream_edge(const GrfEdge *ptr, uint64_t pol) {
+    int4 raw;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                 : "l"(ptr), "l"(pol));
+    GrfEdge e;
+    e.scaled = __hiloint2double(raw.y, raw.x);
+    e.col = raw.z;
+    e.pad = 0;
+    return e;
+}
 
 template <bool kBlock>
 __device__ __forceinline__ void group_sync() {
@@ -99,8 +136,13 @@ __device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) 
 #endif
 // kFast: Philox draws, cumulative load, per-edge factors precomputed (the production setting) --
 // strips the per-step mode tests; the generic instantiation serves replay / ablation / sequential.
-template <bool kBlock, typename KeyT, int KPL, bool kFast>
+// kWide: a lane advances up to four of its walks together (graphs that miss L2: the walker is bound by DRAM
+// latency and needs the independent gathers); otherwise one walk at a time (an L2-resident graph: the walker is
+// bound by instruction issue, and the bookkeeping of four interleaved walks costs more than it hides).
+template <bool kBlock, typename KeyT, int KPL, bool kFast, bool kWide>
 __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINBLOCKS) walk_merge_kernel(const WalkParams p) {
+    constexpr int kIlp = !kWide ? 1 : (kBlock ? 4 : (KPL < 4 ? KPL : 4));
+    const uint64_t keep = l2_policy_keep(), stream_pol = l2_policy_stream();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int GS = kBlock ? (int)blockDim.x : 32;
     const int tg = kBlock ? (int)threadIdx.x : (int)(threadIdx.x & 31);
@@ -133,67 +175,133 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
             for (int i = tg; i < n_vec; i += GS) n4[i] = make_int4(-1, -1, -1, -1);
         }
         group_sync<kBlock>();
-        for (int w = tg; w < W; w += GS) {
-            const unsigned long long walk_id = (unsigned long long)start * (unsigned long long)W + (unsigned)w;
-            int32_t cur = (int32_t)start;
-            double load = 1.0;
-            ++my_visits;  // the length-0 visit (start, 1.0)
-            int step = 0;
-            // one transition: false = the walk ends before a visit at length step + 1
-            auto advance = [&](const uint32_t xh, const uint32_t xk) -> bool {
-                const int32_t rs = __ldg(p.row_ptr + cur);
-                const int32_t re = __ldg(p.row_ptr + cur + 1);
-                const int32_t deg = re - rs;
-                if (deg == 0) return false;  // dead end: stop without drawing (sparse_sampler.py:47)
-                int32_t k;
-                if (!kFast && p.draw_mode == GRF_DRAW_REPLAY) {
-                    const unsigned long long ti = walk_id * (unsigned)L + (unsigned)step;
-                    if (__ldg(p.trace_u + ti) < p.p_halt) return false;
-                    k = __ldg(p.trace_k + ti);
-                } else {
-                    if ((unsigned long long)xh < p.halt_thr) return false;
-                    k = (int32_t)__umulhi(xk, (uint32_t)deg);
+        // kIlp walks per lane advance in lockstep, one transition at a time: the row-pointer pairs of
+        // all of them are requested first, then the edges -- kIlp independent gathers in flight per lane
+        // instead of one dependent chain (config 4: the walker is bound by DRAM latency, ncu 9 warps
+        // stalled on long scoreboard per issue with one walk per lane).
+        for (int w0 = tg; w0 < W; w0 += GS * kIlp) {
+            int32_t cur[kIlp];
+            double load[kIlp];
+            uint32_t x2[kIlp], x3[kIlp];  // second half of a Philox block, used by the odd step
+            bool alive[kIlp];
+#pragma unroll
+            for (int r = 0; r < kIlp; ++r) {
+                alive[r] = w0 + r * GS < W;
+                cur[r] = (int32_t)start;
+                load[r] = 1.0;
+                x2[r] = x3[r] = 0u;
+                my_visits += alive[r];  // the length-0 visit (start, 1.0)
+            }
+            for (int step = 0; step < L - 1; ++step) {
+                int32_t rs[kIlp], deg[kIlp];
+#pragma unroll
+                for (int r = 0; r < kIlp; ++r) {
+                    rs[r] = deg[r] = 0;
+                    if (alive[r]) {
+                        rs[r] = ld_keep_s32(p.row_ptr + cur[r], keep);
+                        deg[r] = ld_keep_s32(p.row_ptr + cur[r] + 1, keep) - rs[r];
+                    }
                 }
-                const int64_t e = (int64_t)rs + k;
-                const int32_t nxt = __ldg(p.col_idx + e);
-                // load *= degree * weight / (1 - p_halt), evaluated left to right in float64 with
-                // no contraction (sparse_sampler.py:54).  (deg * w) / (1 - p) depends on the edge
-                // only, so grf_edge_scale may have computed it once per edge (same roundings).
-                if (!kFast && p.load_mode == GRF_LOAD_ABLATION) {
-                    load = __ldg(p.val + e);
-                } else {
-                    const double scaled = (kFast || p.scaled_val)
-                                              ? __ldg(p.scaled_val + e)
-                                              : __ddiv_rn(__dmul_rn((double)deg, __ldg(p.val + e)), p.one_minus_p);
-                    load = (kFast || p.load_mode == GRF_LOAD_CUMULATIVE) ? __dmul_rn(load, scaled) : scaled;
+                int64_t e[kIlp];
+#pragma unroll
+                for (int r = 0; r < kIlp; ++r) {
+                    e[r] = 0;
+                    if (!alive[r]) continue;
+                    if (deg[r] == 0) {  // dead end: stop without drawing (sparse_sampler.py:47)
+                        alive[r] = false;
+                        continue;
+                    }
+                    const unsigned long long walk_id =
+                        (unsigned long long)start * (unsigned long long)W + (unsigned)(w0 + r * GS);
+                    int32_t k;
+                    if (!kFast && p.draw_mode == GRF_DRAW_REPLAY) {
+                        const long long ti = ((long long)walk_id - p.trace_base) * L + step;
+                        if (__ldg(p.trace_u + ti) < p.p_halt) {
+                            alive[r] = false;
+                            continue;
+                        }
+                        k = __ldg(p.trace_k + ti);
+                    } else {
+                        // one Philox block serves two consecutive steps: words (0,1) the even one, (2,3) the odd one
+                        uint32_t xh, xk;
+                        if ((step & 1) == 0) {
+                            uint32_t x[4];
+                            philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)(step >> 1), 0u,
+                                          p.k0, p.k1, x);
+                            xh = x[0];
+                            xk = x[1];
+                            x2[r] = x[2];
+                            x3[r] = x[3];
+                        } else {
+                            xh = x2[r];
+                            xk = x3[r];
+                        }
+                        if ((unsigned long long)xh < p.halt_thr) {
+                            alive[r] = false;
+                            continue;
+                        }
+                        k = (int32_t)__umulhi(xk, (uint32_t)deg[r]);
+                    }
+                    e[r] = (int64_t)rs[r] + k;
                 }
-                cur = nxt;
-                nodes[step * W + w] = cur;  // the visit at length step+1
-                loads[step * W + w] = load;
-                ++my_visits;
-                ++step;
-                return true;
-            };
-            if (!kFast && p.draw_mode == GRF_DRAW_REPLAY) {
-                while (step < L - 1 && advance(0u, 0u)) {
+                // the edges: neighbour + load factor.  load *= degree * weight / (1 - p_halt), evaluated left
+                // to right in float64 with no contraction (sparse_sampler.py:54); (deg * w) / (1 - p) depends
+                // on the edge only, so grf_edge_records may have computed it once per edge (same roundings).
+                int32_t nxt[kIlp];
+                double fac[kIlp];
+#pragma unroll
+                for (int r = 0; r < kIlp; ++r) {
+                    nxt[r] = 0;
+                    fac[r] = 0.0;
+                    if (!alive[r]) continue;
+                    if (kFast || p.edges) {
+                        const GrfEdge ed = ld_stream_edge(p.edges + e[r], stream_pol);
+                        nxt[r] = ed.col;
+                        fac[r] = ed.scaled;
+                        if (!kFast && p.load_mode == GRF_LOAD_ABLATION) fac[r] = __ldg(p.val + e[r]);
+                    } else {
+                        nxt[r] = __ldg(p.col_idx + e[r]);
+                        const double wv = __ldg(p.val + e[r]);
+                        fac[r] = p.load_mode == GRF_LOAD_ABLATION
+                                     ? wv
+                                     : __ddiv_rn(__dmul_rn((double)deg[r], wv), p.one_minus_p);
+                    }
                 }
-            } else {
-                // one Philox block serves two consecutive steps: words (0,1) the even one, (2,3) the odd one
-                while (step < L - 1) {
-                    uint32_t x[4];
-                    philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)(step >> 1), 0u, p.k0, p.k1,
-                                  x);
-                    if (!advance(x[0], x[1])) break;
-                    if (step >= L - 1 || !advance(x[2], x[3])) break;
+                bool any = false;
+#pragma unroll
+                for (int r = 0; r < kIlp; ++r) {
+                    if (!alive[r]) continue;
+                    load[r] = (kFast || p.load_mode == GRF_LOAD_CUMULATIVE) ? __dmul_rn(load[r], fac[r]) : fac[r];
+                    cur[r] = nxt[r];
+                    const int w = w0 + r * GS;
+                    nodes[step * W + w] = cur[r];  // the visit at length step + 1
+                    loads[step * W + w] = load[r];
+                    ++my_visits;
+                    any = true;
                 }
+                if (!any) break;
             }
         }
 
-        int32_t *out_col = p.stage_col + row * p.stride;
-        double *out_sum = p.stage_sum + row * p.stride;
+        int32_t *out_col = p.stage_ent ? nullptr : p.stage_col + row * p.stride;
+        double *out_sum = p.stage_ent ? nullptr : p.stage_sum + row * p.stride;
+        GrfEntry *out_ent = p.stage_ent ? p.stage_ent + row * p.stride : nullptr;
+        // one merged record: (column, unscaled float64 sum) for the reference layout, or the finished
+        // float32 Phi entry -- (float)(sum * (1/W)) or (float)(sum / W), the arithmetic of grf_compact_blocks
+        auto emit = [&](int slot, int32_t node, double sum, int length) {
+            if (out_ent) {
+                GrfEntry en;
+                en.col = pack_col(node, length);
+                en.val = (float)(p.scale_mode == GRF_SCALE_MUL_RECIP ? __dmul_rn(sum, p.recip_w)
+                                                                      : __ddiv_rn(sum, p.w_as_double));
+                out_ent[slot] = en;
+            } else {
+                out_col[slot] = node;
+                out_sum[slot] = sum;
+            }
+        };
         if (tg == 0) {
-            out_col[0] = (int32_t)start;  // M_0 = I: W visits of load 1.0, summed exactly
-            out_sum[0] = (double)W;
+            emit(0, (int32_t)start, (double)W, 0);  // M_0 = I: W visits of load 1.0, summed exactly
             p.row_cnt[row * L] = 1;
             if (p.col_counts) atomicAdd(p.col_counts + start * L, 1);
         }
@@ -240,13 +348,17 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 int totals;
                 int rank = group_excl_scan<false>(counts, scan_scratch, totals) & 0xffff;
                 const int total = totals & 0xffff, n_valid = totals >> 16;
+                // run_start[j] = first sorted position of run j, run_node[j] = its node (the key area holds
+                // 32 * KPL keys of >= 4 bytes: room for both int32 tables, runs <= 32 * KPL - 1 when n_valid
+                // leaves one slot for the terminator; see the sizing of n_keys on the host)
                 int32_t *run_start = reinterpret_cast<int32_t *>(keys);  // [total + 1]
+                int32_t *run_node = run_start + 32 * KPL + 1;             // [total]
 #pragma unroll
                 for (int r = 0; r < KPL; ++r) {
                     if (head[r]) {
                         run_start[rank] = lane * KPL + r;
                         const int32_t node = (int32_t)(key[r] >> wbits);
-                        out_col[off + rank] = node;
+                        run_node[rank] = node;
                         if (p.col_counts) atomicAdd(p.col_counts + (int64_t)node * L + si + 1, 1);
                         ++rank;
                     }
@@ -257,7 +369,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                     const int qb = run_start[j], qe = run_start[j + 1];
                     double sum = 0.0;
                     for (int q = qb; q < qe; ++q) sum = __dadd_rn(sum, sorted_loads[q]);
-                    out_sum[off + j] = sum;
+                    emit(off + j, run_node[j], sum, si + 1);
                 }
                 if (lane == 0) p.row_cnt[row * L + si + 1] = total;
                 off += total;
@@ -310,8 +422,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                             if ((kq >> wbits) != node) break;
                             sum = __dadd_rn(sum, loads[si * W + (int)(kq & wmask)]);
                         }
-                        out_col[off + rank] = (int32_t)node;
-                        out_sum[off + rank] = sum;
+                        emit(off + rank, (int32_t)node, sum, si + 1);
                         if (p.col_counts) atomicAdd(p.col_counts + (int64_t)node * L + si + 1, 1);
                         ++rank;
                     }
@@ -330,9 +441,9 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
     }
 }
 
-template <bool kBlock, typename KeyT, int KPL, bool kFast = false>
+template <bool kBlock, typename KeyT, int KPL, bool kFast = false, bool kWide = false>
 static int launch_walk(const WalkParams &p, size_t smem, int threads, int grid, cudaStream_t stream) {
-    auto kern = walk_merge_kernel<kBlock, KeyT, KPL, kFast>;
+    auto kern = walk_merge_kernel<kBlock, KeyT, KPL, kFast, kWide>;
     GRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(p);
     return check_cuda(cudaGetLastError(), "walk_merge_kernel launch");
@@ -369,14 +480,20 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
                 "grf_walk: stage_stride too small");
     const int64_t n_local = cfg->start_hi - cfg->start_lo;
     if (n_local == 0) return GRF_OK;
-    GRF_REQUIRE(graph->row_ptr && stage_col && stage_sum && row_cnt, "grf_walk: null buffer");
+    GRF_REQUIRE(graph->row_ptr && row_cnt && (cfg->stage_entries || (stage_col && stage_sum)), "grf_walk: null buffer");
+    GRF_REQUIRE(cfg->scale_mode == GRF_SCALE_MUL_RECIP || cfg->scale_mode == GRF_SCALE_DIV, "grf_walk: bad scale_mode");
     GRF_REQUIRE(graph->nnz == 0 || (graph->col_idx && graph->val), "grf_walk: null edge arrays");
 
     WalkParams p;
     p.row_ptr = graph->row_ptr;
     p.col_idx = graph->col_idx;
     p.val = graph->val;
-    p.scaled_val = cfg->scaled_val;
+    p.edges = cfg->edges;
+    p.trace_base = cfg->trace_walk_base;
+    p.stage_ent = cfg->stage_entries;
+    p.scale_mode = cfg->scale_mode;
+    p.recip_w = 1.0 / (double)cfg->walks_per_node;
+    p.w_as_double = (double)cfg->walks_per_node;
     p.start_lo = cfg->start_lo;
     p.n_local = n_local;
     p.W = cfg->walks_per_node;
@@ -411,8 +528,9 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     const int kpl = p.Wp <= 32 ? 1 : p.Wp / 32;  // warp variant sorts 32*kpl keys
     const size_t n_keys = warp_variant ? (size_t)32 * kpl : (size_t)p.Wp;
     p.sorted_bytes = warp_variant ? (uint32_t)(n_keys * 8) : 0u;
-    // + 4: the warp variant reuses the key area as run_start[runs + 1] (runs <= n_keys)
-    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + p.sorted_bytes + n_keys * key_size + 4 + 15) & ~(size_t)15;
+    // the warp variant sorts in registers and reuses the key area as run_start[n_keys + 1] + run_node[n_keys]
+    const size_t key_area = warp_variant ? (2 * n_keys + 1) * 4 : n_keys * key_size;
+    const size_t gb = ((size_t)p.loads_bytes + p.nodes_bytes + p.sorted_bytes + key_area + 15) & ~(size_t)15;
     p.group_bytes = (uint32_t)gb;
     const size_t kMaxSmem = 227 * 1024 - 256;
     GRF_REQUIRE((uint64_t)p.W * (uint64_t)p.L < (1ull << 31), "grf_walk: W*L too large");
@@ -424,13 +542,19 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
         const int grid = (int)(want < (int64_t)kSmCount * 64 ? want : (int64_t)kSmCount * 64);
         const size_t smem = warps * gb;
         const int threads = warps * 32;
-        const bool fast = p.draw_mode == GRF_DRAW_PHILOX && p.load_mode == GRF_LOAD_CUMULATIVE && p.scaled_val;
-#define GRF_WALK_CASE(K)                                                                              \
-    case K:                                                                                           \
-        if (fast)                                                                                     \
-            return key32 ? launch_walk<false, uint32_t, K, true>(p, smem, threads, grid, st)         \
-                         : launch_walk<false, unsigned long long, K, true>(p, smem, threads, grid, st); \
-        return key32 ? launch_walk<false, uint32_t, K>(p, smem, threads, grid, st)                   \
+        const bool fast = p.draw_mode == GRF_DRAW_PHILOX && p.load_mode == GRF_LOAD_CUMULATIVE && p.edges;
+        // the edge records of this graph do not fit L2 (126 MB, shared with staging writes): latency-bound regime
+        const char *ilp_env = getenv("GRF_B200_WALK_WIDE");
+        const bool wide = ilp_env ? ilp_env[0] == '1' : graph->nnz * (int64_t)sizeof(GrfEdge) > (48ll << 20);
+#define GRF_WALK_CASE(K)                                                                                    \
+    case K:                                                                                                 \
+        if (fast && wide)                                                                                   \
+            return key32 ? launch_walk<false, uint32_t, K, true, true>(p, smem, threads, grid, st)         \
+                         : launch_walk<false, unsigned long long, K, true, true>(p, smem, threads, grid, st); \
+        if (fast)                                                                                           \
+            return key32 ? launch_walk<false, uint32_t, K, true>(p, smem, threads, grid, st)               \
+                         : launch_walk<false, unsigned long long, K, true>(p, smem, threads, grid, st);     \
+        return key32 ? launch_walk<false, uint32_t, K>(p, smem, threads, grid, st)                         \
                      : launch_walk<false, unsigned long long, K>(p, smem, threads, grid, st)
         switch (kpl) {
             GRF_WALK_CASE(1);
@@ -447,35 +571,42 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
                     kMaxSmem);
     const int64_t want = n_local;
     const int grid = (int)(want < (int64_t)kSmCount * 32 ? want : (int64_t)kSmCount * 32);
-    return key32 ? launch_walk<true, uint32_t, 0>(p, gb, 256, grid, st)
-                 : launch_walk<true, unsigned long long, 0>(p, gb, 256, grid, st);
+    return key32 ? launch_walk<true, uint32_t, 0, false, true>(p, gb, 256, grid, st)
+                 : launch_walk<true, unsigned long long, 0, false, true>(p, gb, 256, grid, st);
 }
 
 namespace grf {
-__global__ void __launch_bounds__(256) edge_scale_kernel(const int32_t *__restrict__ row_ptr,
-                                                         const double *__restrict__ val, int64_t n_nodes,
-                                                         double one_minus_p, double *__restrict__ out) {
+__global__ void __launch_bounds__(256) edge_records_kernel(const int32_t *__restrict__ row_ptr,
+                                                           const int32_t *__restrict__ col,
+                                                           const double *__restrict__ val, int64_t n_nodes,
+                                                           double one_minus_p, GrfEdge *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp0; r < n_nodes; r += nwarps) {
         const int32_t b = row_ptr[r], e = row_ptr[r + 1];
         const double deg = (double)(e - b);
-        for (int32_t i = b + lane; i < e; i += 32) out[i] = __ddiv_rn(__dmul_rn(deg, val[i]), one_minus_p);
+        for (int32_t i = b + lane; i < e; i += 32) {
+            GrfEdge ed;
+            ed.scaled = __ddiv_rn(__dmul_rn(deg, val[i]), one_minus_p);
+            ed.col = col[i];
+            ed.pad = 0;
+            out[i] = ed;
+        }
     }
 }
 }  // namespace grf
 
-extern "C" int grf_edge_scale(const GrfGraph *graph, double p_halt, double *scaled_val, void *stream) {
+extern "C" int grf_edge_records(const GrfGraph *graph, double p_halt, GrfEdge *edges, void *stream) {
     GRF_ON_STREAM_DEVICE(stream);
     using namespace grf;
-    GRF_REQUIRE(graph, "grf_edge_scale: null graph");
-    GRF_REQUIRE(p_halt >= 0.0 && p_halt <= 1.0, "grf_edge_scale: p_halt must be in [0, 1]");
+    GRF_REQUIRE(graph, "grf_edge_records: null graph");
+    GRF_REQUIRE(p_halt >= 0.0 && p_halt <= 1.0, "grf_edge_records: p_halt must be in [0, 1]");
     if (graph->n_nodes == 0 || graph->nnz == 0) return GRF_OK;
-    GRF_REQUIRE(graph->row_ptr && graph->val && scaled_val, "grf_edge_scale: null buffer");
+    GRF_REQUIRE(graph->row_ptr && graph->col_idx && graph->val && edges, "grf_edge_records: null buffer");
     int64_t g = (graph->n_nodes + 7) / 8;
     if (g > (int64_t)kSmCount * 32) g = (int64_t)kSmCount * 32;
-    edge_scale_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(graph->row_ptr, graph->val, graph->n_nodes,
-                                                               1.0 - p_halt, scaled_val);
-    return check_cuda(cudaGetLastError(), "edge_scale_kernel launch");
+    edge_records_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(graph->row_ptr, graph->col_idx, graph->val,
+                                                                 graph->n_nodes, 1.0 - p_halt, edges);
+    return check_cuda(cudaGetLastError(), "edge_records_kernel launch");
 }

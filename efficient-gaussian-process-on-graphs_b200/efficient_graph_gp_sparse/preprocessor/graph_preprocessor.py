@@ -58,7 +58,7 @@ class GraphPreprocessor:
         self.max_walk_length = max_walk_length
         self.random_walk_seed = random_walk_seed
         self.use_tqdm = use_tqdm
-        self.cache_filename = cache_filename or self._generate_cache_filename()
+        self._cache_filename = cache_filename      # default name: hashed from the graph on first use (see below)
         self.n_processes = n_processes
         self.device = device
         self._scipy = None
@@ -70,6 +70,19 @@ class GraphPreprocessor:
                 self.step_matrices_torch = self._wrap(self.step_matrices_scipy, None)
             else:
                 raise FileNotFoundError(f"Cache file {self.cache_filename} not found.")
+
+    @property
+    def cache_filename(self) -> str:
+        """Same default as the reference (an md5 over the adjacency arrays, graph_preprocessor.py:64,75-83), but
+        computed when a cache file is first named rather than in the constructor: hashing the 2 GB of a
+        70 M-edge adjacency takes 3 s on the host -- 50x the whole Phi build it would precede."""
+        if self._cache_filename is None:
+            self._cache_filename = self._generate_cache_filename()
+        return self._cache_filename
+
+    @cache_filename.setter
+    def cache_filename(self, value) -> None:
+        self._cache_filename = value
 
     def _generate_cache_filename(self) -> str:
         """Same key as the reference (graph_preprocessor.py:75-83), so caches are interchangeable."""
@@ -129,6 +142,19 @@ class GraphPreprocessor:
         self.step_matrices_torch = self._wrap_device(self._steps_device,
                                                      PhiBlocks.from_step_matrices(self._steps_device))
         return self.step_matrices_torch
+
+    def preprocess_phi(self, start_lo: int = 0, start_hi: Optional[int] = None, *, trace=None) -> PhiBlocks:
+        """The pipeline of ``preprocess_graph`` kept in the matvec layout only: host adjacency -> device
+        Laplacian -> walks -> Phi blocks (+ Phi^T) for the start nodes ``[start_lo, start_hi)`` -- what a
+        row-sharded run (one process per GPU) or a graph whose float64 step matrices are not wanted
+        calls.  No host copy, no torch CSR tensors; ``SparseGRFKernel`` accepts the result's operators."""
+        from grf_b200.engine import build_phi_blocks
+
+        graph = DeviceGraph.laplacian_of(self.adj_matrix, self.device)
+        cfg = WalkConfig(int(self.walks_per_node), float(self.p_halt), int(self.max_walk_length),
+                         seed=self.random_walk_seed or 42,
+                         draw_mode=_lib.DRAW_PHILOX if trace is None else _lib.DRAW_REPLAY, trace=trace)
+        return build_phi_blocks(graph, cfg, start_lo, start_hi)
 
     @staticmethod
     def from_scipy_csr(scipy_csr: sp.csr_matrix) -> torch.Tensor:

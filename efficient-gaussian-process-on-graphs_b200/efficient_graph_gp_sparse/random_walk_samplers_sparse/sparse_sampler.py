@@ -57,20 +57,23 @@ class SparseRandomWalk:
             self._graph = DeviceGraph(self.indptr, self.indices, self.data, self.num_nodes, self._device)
         return self._graph
 
-    def _config(self, num_walks, p_halt, max_walk_length, trace) -> WalkConfig:
+    def _config(self, num_walks, p_halt, max_walk_length, trace, trace_start=0) -> WalkConfig:
         return WalkConfig(
             walks_per_node=int(num_walks), p_halt=float(p_halt), max_walk_length=int(max_walk_length),
-            seed=self.seed, draw_mode=_lib.DRAW_PHILOX if trace is None else _lib.DRAW_REPLAY, trace=trace)
+            seed=self.seed, draw_mode=_lib.DRAW_PHILOX if trace is None else _lib.DRAW_REPLAY, trace=trace,
+            trace_start=int(trace_start))
 
     def get_step_matrices_device(self, num_walks, p_halt, max_walk_length, start_lo=0, start_hi=None,
-                                 trace=None) -> StepMatrices:
-        """The step matrices left in HBM (rows [start_lo, start_hi) only)."""
-        return build_step_matrices(self.graph, self._config(num_walks, p_halt, max_walk_length, trace),
+                                 trace=None, trace_start=0) -> StepMatrices:
+        """The step matrices left in HBM (rows [start_lo, start_hi) only).  ``trace_start``: the first start
+        node the replayed trace covers (a trace recorded for a row slice is indexed from there)."""
+        return build_step_matrices(self.graph, self._config(num_walks, p_halt, max_walk_length, trace, trace_start),
                                    start_lo, start_hi, scale_mode=_lib.SCALE_MUL_RECIP)
 
-    def get_phi_blocks(self, num_walks, p_halt, max_walk_length, start_lo=0, start_hi=None, trace=None) -> PhiBlocks:
+    def get_phi_blocks(self, num_walks, p_halt, max_walk_length, start_lo=0, start_hi=None, trace=None,
+                       trace_start=0) -> PhiBlocks:
         """Phi in the matvec layout, built without leaving the device."""
-        return build_phi_blocks(self.graph, self._config(num_walks, p_halt, max_walk_length, trace),
+        return build_phi_blocks(self.graph, self._config(num_walks, p_halt, max_walk_length, trace, trace_start),
                                 start_lo, start_hi)
 
     def get_random_walk_matrices(

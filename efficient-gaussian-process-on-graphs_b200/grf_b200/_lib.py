@@ -21,15 +21,16 @@ LOAD_CUMULATIVE, LOAD_LAST_STEP, LOAD_ABLATION = 0, 1, 2
 SCALE_MUL_RECIP, SCALE_DIV = 0, 1
 ORDER_ROW_MAJOR, ORDER_STEP_MAJOR = 0, 1
 ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
+ABI_VERSION = 3        # GRF_B200_ABI_VERSION
 
 # every symbol include/grf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = (
     "grf_abi_version", "grf_last_error", "grf_walk_stage_stride", "grf_walk", "grf_scan_workspace_bytes",
     "grf_scan_counts", "grf_compact_steps", "grf_compact_blocks", "grf_blocks_from_steps", "grf_count_from_steps",
     "grf_row_census", "grf_nonempty_rows", "grf_transpose_workspace_bytes", "grf_transpose_offsets", "grf_transpose_fill",
-    "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_scale", "grf_union_rank", "grf_union_fill",
+    "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_records", "grf_compact_entries", "grf_union_rank", "grf_union_fill",
     "grf_union_materialize", "grf_cg_num_partials", "grf_cg_dot", "grf_cg_update", "grf_cg_direction",
-    "grf_laplacian_count", "grf_laplacian_fill", "grf_shard_reach",
+    "grf_laplacian_count", "grf_laplacian_fill", "grf_shard_reach", "grf_exchange_flag_bytes", "grf_exchange_sum",
 )
 
 
@@ -41,7 +42,9 @@ class GrfGraph(Structure):
 class GrfWalkCfg(Structure):
     _fields_ = [("start_lo", c_int64), ("start_hi", c_int64), ("walks_per_node", c_int32),
                 ("max_walk_length", c_int32), ("p_halt", c_double), ("draw_mode", c_int32), ("load_mode", c_int32),
-                ("seed", c_uint64), ("trace_u", c_void_p), ("trace_k", c_void_p), ("scaled_val", c_void_p), ("col_counts", c_void_p)]
+                ("seed", c_uint64), ("trace_u", c_void_p), ("trace_k", c_void_p), ("edges", c_void_p),
+                ("col_counts", c_void_p), ("trace_walk_base", c_int64), ("stage_entries", c_void_p),
+                ("scale_mode", c_int32)]
 
 
 class GrfLongRows(Structure):
@@ -116,11 +119,11 @@ def lib():
     L.grf_nonempty_rows.restype = i32
     L.grf_nonempty_rows.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp]
     L.grf_transpose_workspace_bytes.restype = i64
-    L.grf_transpose_workspace_bytes.argtypes = [i64, i32]
+    L.grf_transpose_workspace_bytes.argtypes = [i64, i32, i64]
     L.grf_transpose_offsets.restype = i32
     L.grf_transpose_offsets.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, i32, vp, vp]
     L.grf_transpose_fill.restype = i32
-    L.grf_transpose_fill.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, vp]
+    L.grf_transpose_fill.argtypes = [vp, vp, i64, i64, i32, i64, i64, vp, vp, vp]
     L.grf_phi_matvec.restype = i32
     L.grf_phi_matvec.argtypes = [POINTER(GrfPhi), vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, vp]
     L.grf_union_rank.restype = i32
@@ -141,13 +144,19 @@ def lib():
     L.grf_laplacian_count.argtypes = [POINTER(GrfGraph), vp, vp, vp, vp]
     L.grf_laplacian_fill.restype = i32
     L.grf_laplacian_fill.argtypes = [POINTER(GrfGraph), vp, vp, vp, vp, vp, vp]
-    L.grf_edge_scale.restype = i32
-    L.grf_edge_scale.argtypes = [POINTER(GrfGraph), c_double, vp, vp]
+    L.grf_edge_records.restype = i32
+    L.grf_edge_records.argtypes = [POINTER(GrfGraph), c_double, vp, vp]
+    L.grf_compact_entries.restype = i32
+    L.grf_compact_entries.argtypes = [vp, vp, i64, i32, i64, vp, vp]
+    L.grf_exchange_flag_bytes.restype = i64
+    L.grf_exchange_flag_bytes.argtypes = [i32]
+    L.grf_exchange_sum.restype = i32
+    L.grf_exchange_sum.argtypes = [POINTER(vp), POINTER(vp), i32, i32, i64, ctypes.c_uint32, vp]
     L.grf_block_windows.restype = i32
     L.grf_block_windows.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.grf_phi_fgrad.restype = i32
     L.grf_phi_fgrad.argtypes = [POINTER(GrfPhi), vp, i64, vp, i64, vp, i64, i32, vp, vp]
-    if L.grf_abi_version() != 2:
+    if L.grf_abi_version() != ABI_VERSION:
         raise RuntimeError("grf_b200: ABI version mismatch between _lib.py and libgrf_b200.so")
     _lib = L
     return _lib

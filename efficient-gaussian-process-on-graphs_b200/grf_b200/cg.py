@@ -65,8 +65,24 @@ def linear_cg_fused(plan, rhs: torch.Tensor, sigma2: float = 0.0, tolerance: flo
 
     if plan.n1 != plan.n2:
         raise ValueError("linear_cg_fused needs a square operator (x1 and x2 of equal length)")
+    # a row-sharded plan: the vectors hold this rank's rows; every dot product is one t-float all-reduce
+    # of the per-rank partial sums (two per iteration), the rest is the same three fused launches
+    group = None
     if plan.group is not None:
-        raise ValueError("linear_cg_fused is the single-GPU path; use linear_cg with a sharded matvec")
+        import torch.distributed as dist
+
+        group = (None if plan.group is True else plan.group, dist)
+        use_graph = False
+
+    def allsum(partials):
+        """[n_part, t] per-rank partial sums -> the same buffer holding the global sum in row 0."""
+        if group is None:
+            return
+        total = partials.sum(dim=0)
+        group[1].all_reduce(total, group=group[0])
+        partials.zero_()
+        partials[0] = total
+
     L = _lib.lib()
     dev = plan._dev
     squeeze = rhs.dim() == 1
@@ -74,7 +90,10 @@ def linear_cg_fused(plan, rhs: torch.Tensor, sigma2: float = 0.0, tolerance: flo
     n, t = b.shape
     if t != plan.t or n != plan.n2:
         raise ValueError("rhs shape does not match the plan")
-    norm = b.norm(dim=0, keepdim=True)
+    sq = (b * b).sum(dim=0, keepdim=True)
+    if group is not None:
+        group[1].all_reduce(sq, group=group[0])
+    norm = sq.sqrt()
     norm = torch.where(norm < eps, torch.ones_like(norm), norm)
     b = (b / norm).contiguous()
     x = torch.zeros_like(b)
@@ -82,6 +101,8 @@ def linear_cg_fused(plan, rhs: torch.Tensor, sigma2: float = 0.0, tolerance: flo
     d = b.clone()
     kd = torch.empty_like(b)
     rs = (r * r).sum(dim=0).contiguous()
+    if group is not None:
+        group[1].all_reduce(rs, group=group[0])
     rs_next = torch.empty_like(rs)
     n_part = L.grf_cg_num_partials(n, t)
     pa = torch.empty((n_part, t), dtype=torch.float32, device=dev)
@@ -96,8 +117,10 @@ def linear_cg_fused(plan, rhs: torch.Tensor, sigma2: float = 0.0, tolerance: flo
         for _ in range(count):
             plan(d, kd)
             check(L.grf_cg_dot(P(kd), t, P(d), t, float(sigma2), n, t, P(pa), stream_of()))
+            allsum(pa)
             check(L.grf_cg_update(P(x), t, P(r), t, P(d), t, P(kd), t, P(state["rs"]), P(pa), n, t, float(eps),
                                   P(pb), stream_of()))
+            allsum(pb)
             check(L.grf_cg_direction(P(d), t, P(r), t, P(state["rs"]), P(pb), n, t, float(eps),
                                      P(state["rs_next"]), stream_of()))
             state["rs"], state["rs_next"] = state["rs_next"], state["rs"]

@@ -26,8 +26,13 @@ from . import _lib
 from ._lib import GrfGraph, GrfLongRows, GrfPhi, GrfWalkCfg, check
 
 LONG_ROW_THRESHOLD = 256   # rows of Phi / Phi^T with more entries are split into chunks of this size
-_MAX_STAGE_BYTES = 6 << 30  # staging budget per walker launch; larger shards are walked in row chunks
+_MAX_STAGE_BYTES = 16 << 30  # staging budget per walker launch; larger shards are walked in row chunks
 _LAZY_ENTRY_BYTES = 1 << 30  # up to this bound the Phi entries are allocated by capacity (no host wait for the count)
+# Rows per Phi^T block.  Transposing a shard in row blocks bounds the sort workspace (24 bytes per entry of a
+# block) and lets a shard exceed 2^31 entries on the Phi^T side; it does NOT pay as cache blocking of V: with 2^19-row
+# blocks the first half of the config-4 product went from 7.4 to 12.8 ms (every block re-reads the 21 M segment
+# pointers and read-modify-writes all of U, and most columns hold ~1 entry per block).  Hence one block up to 2^22 rows.
+T_BLOCK_ROWS = 1 << 22
 
 
 def _device(device=None) -> torch.device:
@@ -44,12 +49,24 @@ def _device(device=None) -> torch.device:
 
 
 _pending_host = []
+_free_small_pinned = []
+
+
+def _small_pinned() -> torch.Tensor:
+    """64 bytes of pinned host memory for a count / census that the GPU copies back asynchronously.  Recycled:
+    cudaHostAlloc costs ~0.1 ms and serialises with the device, and every Phi build needs two or three."""
+    done = [(b, e) for b, e in _pending_host if e.query()]
+    if done:
+        _pending_host[:] = [(b, e) for b, e in _pending_host if not e.query()]
+        _free_small_pinned.extend(b for b, _ in done if b.numel() == 16 and b.dtype == torch.int32)
+    if _free_small_pinned:
+        return _free_small_pinned.pop()
+    return torch.empty(16, dtype=torch.int32, pin_memory=True)
 
 
 def _keep_until_done(buf: torch.Tensor, event: torch.cuda.Event) -> None:
     """The C library copies into ``buf`` (pinned) asynchronously, which torch's host allocator does
     not see: hold a reference until the copy's event has completed, whoever drops the owner first."""
-    _pending_host[:] = [(b, e) for b, e in _pending_host if not e.query()]
     _pending_host.append((buf, event))
 
 
@@ -77,7 +94,8 @@ class WalkConfig:
     seed: int = 42
     draw_mode: int = _lib.DRAW_PHILOX
     load_mode: int = _lib.LOAD_CUMULATIVE
-    trace: Optional[Tuple] = None  # (trace_u float64, trace_k int32), [walk_id*L + step]
+    trace: Optional[Tuple] = None  # (trace_u float64, trace_k int32), [(walk_id - trace_start*W)*L + step]
+    trace_start: int = 0           # first start node the trace covers (a trace recorded for a row slice)
 
     def validate(self):
         if int(self.walks_per_node) < 1:
@@ -193,27 +211,29 @@ class DeviceGraph:
             self._shared = {key: "all" if shared.numel() > max_fraction * self.n_nodes else shared}
         return self._shared[key]
 
-    def scaled_val(self, p_halt: float) -> torch.Tensor:
-        """(deg * w) / (1 - p_halt) per edge (cached per p_halt): the load-update factor."""
+    def edge_records(self, p_halt: float) -> torch.Tensor:
+        """{(deg * w) / (1 - p_halt), neighbour} per edge, 16 bytes each (cached per p_halt): what the walker
+        gathers per step."""
         key = float(p_halt)
         if key not in self._scaled:
-            out = torch.empty(max(1, self.nnz), dtype=torch.float64, device=self.device)
+            out = torch.empty((max(1, self.nnz), 2), dtype=torch.float64, device=self.device)
             g = self.c_struct()
-            check(_lib.lib().grf_edge_scale(ctypes.byref(g), key, _ptr(out), _stream(self.device)))
+            check(_lib.lib().grf_edge_records(ctypes.byref(g), key, _ptr(out), _stream(self.device)))
             self._scaled = {key: out}
         return self._scaled[key]
 
 
 @dataclass
 class Staging:
-    stage_col: torch.Tensor   # int32 [n_rows * stride]
-    stage_sum: torch.Tensor   # float64 [n_rows * stride]
+    stage_col: Optional[torch.Tensor]   # int32 [n_rows * stride]      (reference layout: column + float64 sum)
+    stage_sum: Optional[torch.Tensor]   # float64 [n_rows * stride]
     row_cnt: torch.Tensor     # int32 [n_rows * L]
     stride: int
     n_rows: int
     row_lo: int
     visits: torch.Tensor      # int64 [1] walk-steps executed
     col_counts: Optional[torch.Tensor] = None   # int32 [n_nodes * L] entries per (column, length), if counted
+    stage_ent: Optional[torch.Tensor] = None    # int32 [n_rows * stride, 2]: finished Phi entries (matvec layout)
 
 
 def scan_counts(row_cnt: torch.Tensor, n_rows: int, n_steps: int, order: int, i64: bool,
@@ -231,46 +251,59 @@ def scan_counts(row_cnt: torch.Tensor, n_rows: int, n_steps: int, order: int, i6
 
 def run_walker(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
                visits: Optional[torch.Tensor] = None, col_counts: Optional[torch.Tensor] = None,
-               count_columns: bool = False) -> Staging:
+               count_columns: bool = False, entries_scale_mode: Optional[int] = None) -> Staging:
     """One grf_walk launch over start nodes [start_lo, start_hi).  ``count_columns`` (or a zeroed /
     partially accumulated ``col_counts`` int32 [n_nodes * L]) also counts the entries per (column,
-    length) while they are emitted: the segment sizes of the Phi^T blocks, for free."""
+    length) while they are emitted: the segment sizes of the Phi^T blocks, for free.
+    ``entries_scale_mode`` (SCALE_*): the walker leaves finished float32 Phi entries in staging
+    (8 bytes per record instead of 12) -- the matvec layout needs nothing else."""
     cfg.validate()
     L = _lib.lib()
     dev = graph.device
     start_hi = graph.n_nodes if start_hi is None else start_hi
     n_rows = start_hi - start_lo
     stride = L.grf_walk_stage_stride(cfg.walks_per_node, cfg.max_walk_length)
-    stage_col = torch.empty(max(1, n_rows * stride), dtype=torch.int32, device=dev)
-    stage_sum = torch.empty(max(1, n_rows * stride), dtype=torch.float64, device=dev)
+    stage_col = stage_sum = stage_ent = None
+    if entries_scale_mode is None:
+        stage_col = torch.empty(max(1, n_rows * stride), dtype=torch.int32, device=dev)
+        stage_sum = torch.empty(max(1, n_rows * stride), dtype=torch.float64, device=dev)
+    else:
+        stage_ent = torch.empty((max(1, n_rows * stride), 2), dtype=torch.int32, device=dev)
     row_cnt = torch.empty(max(1, n_rows * cfg.max_walk_length), dtype=torch.int32, device=dev)
     if visits is None:
         visits = torch.zeros(1, dtype=torch.int64, device=dev)
     if col_counts is None and count_columns:
         col_counts = torch.zeros(max(1, graph.n_nodes * cfg.max_walk_length), dtype=torch.int32, device=dev)
     tu = tk = None
+    trace_base = 0
     if cfg.draw_mode == _lib.DRAW_REPLAY:
         tu = torch.as_tensor(cfg.trace[0], dtype=torch.float64).to(dev).contiguous()
         tk = torch.as_tensor(cfg.trace[1], dtype=torch.int32).to(dev).contiguous()
-        need = graph.n_nodes * cfg.walks_per_node * cfg.max_walk_length
-        if tu.numel() < need or tk.numel() < need:
-            raise ValueError("trace arrays must have n_nodes * W * L entries")
+        if start_lo < cfg.trace_start and n_rows > 0:
+            raise ValueError("trace starts after the first start node of this launch")
+        trace_base = int(cfg.trace_start) * cfg.walks_per_node
+        need = (start_hi - int(cfg.trace_start)) * cfg.walks_per_node * cfg.max_walk_length
+        if n_rows > 0 and (tu.numel() < need or tk.numel() < need):
+            raise ValueError("trace arrays must cover the walks of start nodes trace_start .. start_hi - 1 "
+                             "((start_hi - trace_start) * W * L entries)")
     g = graph.c_struct()
-    scaled = None
+    edges = None
     if cfg.load_mode != _lib.LOAD_ABLATION and cfg.max_walk_length > 1 and graph.nnz > 0 and cfg.p_halt < 1.0:
-        scaled = graph.scaled_val(cfg.p_halt)
+        edges = graph.edge_records(cfg.p_halt)
     c = GrfWalkCfg(start_lo, start_hi, cfg.walks_per_node, cfg.max_walk_length, float(cfg.p_halt), cfg.draw_mode,
                    cfg.load_mode, int(cfg.seed) & 0xFFFFFFFFFFFFFFFF,
                    None if tu is None else tu.data_ptr(), None if tk is None else tk.data_ptr(),
-                   None if scaled is None else scaled.data_ptr(),
-                   None if col_counts is None else col_counts.data_ptr())
+                   None if edges is None else edges.data_ptr(),
+                   None if col_counts is None else col_counts.data_ptr(), trace_base,
+                   None if stage_ent is None else stage_ent.data_ptr(),
+                   _lib.SCALE_MUL_RECIP if entries_scale_mode is None else int(entries_scale_mode))
     check(L.grf_walk(ctypes.byref(g), ctypes.byref(c), stride, _ptr(stage_col), _ptr(stage_sum), _ptr(row_cnt),
                      _ptr(visits), _stream(dev)))
-    return Staging(stage_col, stage_sum, row_cnt, stride, n_rows, start_lo, visits, col_counts)
+    return Staging(stage_col, stage_sum, row_cnt, stride, n_rows, start_lo, visits, col_counts, stage_ent)
 
 
-def _row_chunks(start_lo: int, start_hi: int, stride: int, max_stage_bytes: int):
-    rows_per = max(1, max_stage_bytes // (stride * 12))
+def _row_chunks(start_lo: int, start_hi: int, stride: int, max_stage_bytes: int, slot_bytes: int = 12):
+    rows_per = max(1, max_stage_bytes // (stride * slot_bytes))
     lo = start_lo
     while lo < start_hi:
         hi = min(start_hi, lo + rows_per)
@@ -400,6 +433,22 @@ def build_step_matrices(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, 
     return out
 
 
+class TBlock:
+    """Phi^T of the rows [r0, r0 + n_rows) of a shard: block CSR over (column, walk length), entries
+    {length << 27 | row - r0, value}, every segment ordered by row.  A large shard keeps one per
+    T_BLOCK_ROWS rows (the first half of the product then gathers V one L2-sized row block at a time)."""
+
+    def __init__(self, r0: int, n_rows: int, nnz: int, tblk_ptr: torch.Tensor, tentries: torch.Tensor):
+        self.r0, self.n_rows, self.nnz = int(r0), int(n_rows), int(nnz)
+        self.tblk_ptr, self.tentries = tblk_ptr, tentries
+        self.census = None      # (pinned int32[6], event): rows of Phi in this block [0:3], of this Phi^T [3:6]
+        self.long = None        # chunk table of the columns longer than LONG_ROW_THRESHOLD (dict) or None
+        self.long_c = {}        # ld -> (GrfLongRows, partial buffer)
+        self.tcols = None       # non-empty columns (int32) when they are a small fraction of N (single block only)
+        self.touched = None     # int32 0/1 per column, set together with tcols
+        self.tcols_cap = None
+
+
 class PhiBlocks:
     """Phi in the matvec layout: block CSR over (row, walk length) with
     {int32 col, float32 val} entries, plus the same for Phi^T (built once --
@@ -415,8 +464,7 @@ class PhiBlocks:
         self.blk_ptr, self._entries = blk_ptr, entries
         self._nnz_pending = None   # (pinned int64[1], event): `_entries` has spare capacity until this resolves
         self.n_rows, self.n_cols, self.n_steps, self.row_lo = n_rows, n_cols, n_steps, row_lo
-        self.tblk_ptr = None
-        self.tentries = None
+        self.tblocks: Optional[List[TBlock]] = None   # Phi^T, one block per T_BLOCK_ROWS rows (build_transpose)
         self.win = self.twin = None
         self.win_max_width = self.twin_max_width = 0
         # shared-memory-tiled matvec for banded Phi: correct and tested, but measured equal to the
@@ -425,19 +473,21 @@ class PhiBlocks:
         # hand the last rows of every matvec pass out by ticket (GrfPhi.sched); env GRF_B200_DYNAMIC=0
         # keeps the fixed stride (for A/B timing)
         self.dynamic_rows = os.environ.get("GRF_B200_DYNAMIC", "1") != "0"
+        # gather the right-hand side with L1::no_allocate loads, per half (Phi^T V, Phi U).  Opt-in experiment
+        # (env GRF_B200_STREAM=11): measured 3-5x SLOWER on the power-law Phi (40.6 / 26.3 ms against 12.8 / 5.0),
+        # so the cached loads stay the default; MatvecPlan._tune_gathers() measures both on request.
+        env = os.environ.get("GRF_B200_STREAM", "00")
+        self.stream_gather = (env[0] == "1", env[-1] == "1")
         self._sched = None
-        self._census = None     # (pinned int32[6], event): row statistics of both sides, see _start_census
         self._col_counts = None  # int32 [n_cols * L] from the walker (GrfWalkCfg.col_counts), used once by build_transpose
         self.visits = visits
         self._union = None
-        self._tcols = None      # non-empty columns of this shard (int32) when that is a small fraction of N
-        self._touched = None    # int32 0/1 per column, set together with _tcols
-        self._tcols_cap = None  # id list with spare capacity, written before the census says how many there are
         # sharded matvec: columns to exchange between the ranks, if known up front (tensor of ids or
         # "all"; DeviceGraph.shared_columns); None = the plan finds them with one all-reduce
         self.shared_hint = None
-        self._long = None       # [fwd, transposed] long-row metadata (dicts) or None per side
-        self._long_c = {}       # ld -> (ctypes structs, partial buffers) kept alive for the calls
+        self._long_fwd = None   # chunk table of the rows of Phi longer than LONG_ROW_THRESHOLD
+        self._long_built = False
+        self._long_fwd_c = {}   # ld -> (GrfLongRows, partial buffer) kept alive for the calls
         self._ws = {}
 
     @property
@@ -465,65 +515,143 @@ class PhiBlocks:
     def nnz(self) -> int:
         return int(self.entries.shape[0])
 
-    def build_transpose(self) -> "PhiBlocks":
-        """Phi^T blocks (once per Phi).  Two C calls on one workspace; the row census of both sides is
-        copied to pinned host memory behind the offsets, so build_long_rows() reads it while the
-        fill / sort kernels still run instead of draining the GPU."""
-        if self.tblk_ptr is not None:
+    # ---- the transposed side: one block, or one per T_BLOCK_ROWS rows -----------------------------
+    def _tb0(self) -> Optional[TBlock]:
+        if self.tblocks is None:
+            return None
+        if len(self.tblocks) != 1:
+            raise ValueError("this Phi^T is stored in several row blocks; the single-block view does not exist")
+        return self.tblocks[0]
+
+    @property
+    def tblk_ptr(self):
+        tb = self._tb0()
+        return None if tb is None else tb.tblk_ptr
+
+    @property
+    def tentries(self):
+        tb = self._tb0()
+        return None if tb is None else tb.tentries
+
+    @property
+    def _tcols(self):
+        return self.tblocks[0].tcols if self.tblocks is not None and len(self.tblocks) == 1 else None
+
+    @_tcols.setter
+    def _tcols(self, value):
+        self._tb0().tcols = value
+
+    @property
+    def _touched(self):
+        return self.tblocks[0].touched if self.tblocks is not None and len(self.tblocks) == 1 else None
+
+    @property
+    def _long(self):
+        """[long rows of Phi, long columns of the (single) Phi^T block] once build_long_rows() has run."""
+        if not self._long_built:
+            return None
+        return [self._long_fwd, self.tblocks[0].long if self.tblocks else None]
+
+    @_long.setter
+    def _long(self, value):
+        self._long_built = value is not None
+        self._long_fwd = None if value is None else value[0]
+        if self.tblocks:
+            for tb in self.tblocks:
+                tb.long = None
+            if value is not None:
+                self.tblocks[0].long = value[1]
+
+    @property
+    def _long_c(self):
+        return self._long_fwd_c
+
+    @_long_c.setter
+    def _long_c(self, value):
+        self._long_fwd_c = value
+        for tb in self.tblocks or []:
+            tb.long_c = {}
+
+    def build_transpose(self, block_rows: Optional[int] = None) -> "PhiBlocks":
+        """Phi^T blocks (once per Phi): per row block, two C calls on one workspace -- segment offsets, then
+        a stable radix sort of the block's entries by (column, length).  The row census of both sides is
+        copied to pinned host memory behind the offsets, so build_long_rows() reads it while the sort
+        still runs instead of draining the GPU."""
+        if self.tblocks is not None:
             return self
+        block_rows = T_BLOCK_ROWS if block_rows is None else int(block_rows)
+        n_blocks = 1 if self.n_rows <= block_rows + block_rows // 2 else -(-self.n_rows // block_rows)
+        rows = [self.n_rows * b // n_blocks for b in range(n_blocks + 1)]
+        if n_blocks == 1:
+            bounds = [0, self.nnz]
+        else:
+            idx = torch.tensor([r * self.n_steps for r in rows], dtype=torch.int64, device=self.device)
+            bounds = self.blk_ptr[idx].cpu().tolist()
+        counts = self._col_counts if n_blocks == 1 else None   # the walker's counts cover the whole shard
+        self._col_counts = None
+        self.tblocks = [self._build_tblock(rows[b], rows[b + 1], bounds[b], bounds[b + 1], counts)
+                        for b in range(n_blocks)]
+        tb = self.tblocks[0]
+        if n_blocks == 1 and tb.nnz and self.n_rows < self.n_cols:
+            # a row shard: list its non-empty columns now (capacity n_cols, the census gives the length
+            # later), while the host would otherwise wait for the sort
+            self._list_nonempty_columns(tb, self.n_cols)
+        return self
+
+    def _build_tblock(self, r0: int, r1: int, e0: int, e1: int, col_counts) -> TBlock:
         L = _lib.lib()
         dev, st = self.device, _stream(self.device)
         n_seg = self.n_cols * self.n_steps
-        ws = torch.empty(L.grf_transpose_workspace_bytes(self.n_cols, self.n_steps), dtype=torch.uint8, device=dev)
-        self.tblk_ptr = torch.empty(n_seg + 1, dtype=torch.int32, device=dev)
-        self.tentries = torch.empty((max(1, self.nnz), 2), dtype=torch.int32, device=dev)[: self.nnz]
-        host = torch.empty(6, dtype=torch.int32, pin_memory=True) if self.nnz else None
-        check(L.grf_transpose_offsets(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
-                                      _ptr(self._col_counts), _ptr(self.tblk_ptr), _ptr(ws), LONG_ROW_THRESHOLD,
-                                      _ptr(host), st))
-        self._col_counts = None
+        nnz = e1 - e0
+        ws = torch.empty(L.grf_transpose_workspace_bytes(self.n_cols, self.n_steps, nnz), dtype=torch.uint8, device=dev)
+        tblk_ptr = torch.empty(n_seg + 1, dtype=torch.int32, device=dev)
+        tentries = torch.empty((max(1, nnz), 2), dtype=torch.int32, device=dev)[:nnz]
+        tb = TBlock(r0, r1 - r0, nnz, tblk_ptr, tentries)
+        base = _small_pinned() if nnz else None
+        host = None if base is None else base[:6]
+        ptr = ctypes.c_void_p(self.blk_ptr.data_ptr() + 4 * r0 * self.n_steps)
+        ent = _ptr(self.entries) if self.nnz else None
+        check(L.grf_transpose_offsets(ptr, ent, r1 - r0, self.n_cols, self.n_steps, _ptr(col_counts), _ptr(tblk_ptr),
+                                      _ptr(ws), LONG_ROW_THRESHOLD, _ptr(host), st))
         if host is not None:
             arrived = torch.cuda.Event()
             arrived.record(torch.cuda.current_stream(dev))
-            self._census = (host, arrived)
-            _keep_until_done(host, arrived)
-        check(L.grf_transpose_fill(_ptr(self.blk_ptr), _ptr(self.entries), self.n_rows, self.n_cols, self.n_steps,
-                                   _ptr(self.tblk_ptr), _ptr(ws), _ptr(self.tentries), st))
-        if self.nnz and self.n_rows < self.n_cols:
-            # a row shard: list its non-empty columns now (capacity n_cols, the census gives the length
-            # later), while the host would otherwise wait for the fill / sort kernels
-            self._list_nonempty_columns(self.n_cols)
-        return self
+            tb.census = (host, arrived)
+            _keep_until_done(base, arrived)
+        check(L.grf_transpose_fill(ptr, ent, r1 - r0, self.n_cols, self.n_steps, e0, nnz, _ptr(ws), _ptr(tentries), st))
+        return tb
 
-    def _list_nonempty_columns(self, capacity: int) -> None:
+    def _list_nonempty_columns(self, tb: TBlock, capacity: int) -> None:
         lib, dev = _lib.lib(), self.device
-        self._touched = torch.empty(self.n_cols, dtype=torch.int32, device=dev)
+        tb.touched = torch.empty(self.n_cols, dtype=torch.int32, device=dev)
         pos = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
         ws = torch.empty(lib.grf_scan_workspace_bytes(self.n_cols), dtype=torch.uint8, device=dev)
-        self._tcols_cap = torch.empty(max(1, capacity), dtype=torch.int32, device=dev)
-        check(lib.grf_nonempty_rows(_ptr(self.tblk_ptr), self.n_cols, self.n_steps, _ptr(self._touched), _ptr(pos),
-                                    _ptr(ws), _ptr(self._tcols_cap), _stream(dev)))
+        tb.tcols_cap = torch.empty(max(1, capacity), dtype=torch.int32, device=dev)
+        check(lib.grf_nonempty_rows(_ptr(tb.tblk_ptr), self.n_cols, self.n_steps, _ptr(tb.touched), _ptr(pos),
+                                    _ptr(ws), _ptr(tb.tcols_cap), _stream(dev)))
 
-    def _start_census(self) -> None:
-        """Row statistics of both sides for Phi blocks that did not come through build_transpose()."""
-        if self.nnz == 0 or self._census is not None:
+    def _start_census(self, tb: TBlock) -> None:
+        """Row statistics of both sides for a block that did not come through _build_tblock()."""
+        if tb.nnz == 0 or tb.census is not None:
             return
         lib, dev, L = _lib.lib(), self.device, self.n_steps
         census = torch.empty(6, dtype=torch.int32, device=dev)
-        check(lib.grf_row_census(_ptr(self.blk_ptr), self.n_rows, L, LONG_ROW_THRESHOLD, _ptr(census[0:3]),
+        ptr = ctypes.c_void_p(self.blk_ptr.data_ptr() + 4 * tb.r0 * L)
+        check(lib.grf_row_census(ptr, tb.n_rows, L, LONG_ROW_THRESHOLD, _ptr(census[0:3]), _stream(dev)))
+        check(lib.grf_row_census(_ptr(tb.tblk_ptr), self.n_cols, L, LONG_ROW_THRESHOLD, _ptr(census[3:6]),
                                  _stream(dev)))
-        check(lib.grf_row_census(_ptr(self.tblk_ptr), self.n_cols, L, LONG_ROW_THRESHOLD, _ptr(census[3:6]),
-                                 _stream(dev)))
-        host = torch.empty(6, dtype=torch.int32, pin_memory=True)
+        base = _small_pinned()
+        host = base[:6]
         host.copy_(census, non_blocking=True)
         arrived = torch.cuda.Event()
         arrived.record(torch.cuda.current_stream(dev))
-        self._census = (host, arrived)
+        tb.census = (host, arrived)
+        _keep_until_done(base, arrived)
 
     def build_windows(self) -> "PhiBlocks":
         """Column windows per 32 rows of Phi and Phi^T (lets a banded Phi use the tiled matvec)."""
         self.build_transpose()
-        if self.win is not None or self.nnz == 0 or not self.use_tiles:
+        if self.win is not None or self.nnz == 0 or not self.use_tiles or len(self.tblocks) != 1:
             return self
         L = _lib.lib()
         dev = self.device
@@ -543,6 +671,9 @@ class PhiBlocks:
         if self._union is not None:
             return self
         self.build_transpose()
+        if len(self.tblocks) != 1:
+            raise ValueError("the union layout needs a single-block Phi^T (shards beyond ~T_BLOCK_ROWS rows multiply "
+                             "the per-length blocks)")
         L = _lib.lib()
         dev = self.device
         sides = []
@@ -578,7 +709,7 @@ class PhiBlocks:
             ent = torch.empty((max(1, fwd["n_union"]), 2), dtype=torch.int32, device=dev)[:fwd["n_union"]]
             tent = torch.empty((max(1, tr["n_union"]), 2), dtype=torch.int32, device=dev)[:tr["n_union"]]
             into = PhiBlocks(fwd["uptr"], ent, self.n_rows, self.n_cols, 1, self.row_lo)
-            into.tblk_ptr, into.tentries = tr["uptr"], tent
+            into.tblocks = [TBlock(0, self.n_rows, tr["n_union"], tr["uptr"], tent)]
         for side, ent in ((fwd, into.entries), (tr, into.tentries)):
             check(L.grf_union_materialize(_ptr(side["ptr"]), _ptr(side["uptr"]), _ptr(side["uhdr"]),
                                           _ptr(side["mval"]), _ptr(f), side["n"], self.n_steps, _ptr(ent),
@@ -612,61 +743,94 @@ class PhiBlocks:
         """One-off matvec preparation: which rows / columns need the long-row split, and the list of
         non-empty columns when this shard touches few of them.  Reads the census that
         build_transpose() started; the chunk tables are only built when a long row exists."""
-        if self._long is None:
+        if not self._long_built:
             self.build_transpose()
-            self._long = [None, None]
+            self._long_built = True
+            self._long_fwd = None
             if self.nnz == 0:
                 return self
-            L = self.n_steps
-            self._start_census()
-            host, done = self._census
-            done.synchronize()
-            long_f, _, _, long_t, _, cols_used = host.tolist()
-            if long_f:
-                self._long[0] = self._long_rows_of(self.blk_ptr, self.n_rows)
-            if long_t:
-                self._long[1] = self._long_rows_of(self.tblk_ptr, self.n_cols)
-            # columns this (row) shard touches: worth a list when most of the N columns are empty
-            if cols_used < 0.75 * self.n_cols:
-                if self._tcols_cap is None:
-                    self._list_nonempty_columns(cols_used)
-                self._tcols = self._tcols_cap[:cols_used]
-            else:
-                self._touched = None
-            self._tcols_cap = None
+            any_long_fwd = False
+            for tb in self.tblocks:
+                if tb.nnz == 0:
+                    continue
+                self._start_census(tb)
+                host, done = tb.census
+                done.synchronize()
+                long_f, _, _, long_t, _, cols_used = host.tolist()
+                any_long_fwd = any_long_fwd or bool(long_f)
+                tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols) if long_t else None
+                if len(self.tblocks) == 1:
+                    # columns this (row) shard touches: worth a list when most of the N columns are empty
+                    if cols_used < 0.75 * self.n_cols:
+                        if tb.tcols_cap is None:
+                            self._list_nonempty_columns(tb, cols_used)
+                        tb.tcols = tb.tcols_cap[:cols_used]
+                    else:
+                        tb.touched = None
+                    tb.tcols_cap = None
+            if any_long_fwd:
+                self._long_fwd = self._long_rows_of(self.blk_ptr, self.n_rows)
         return self
 
-    def _long_structs(self, ld: int):
-        """ctypes GrfLongRows for both sides with partial buffers of leading dimension ``ld``."""
-        if self._long is None or ld <= 0:
-            return None, None
-        if ld not in self._long_c:
-            out = []
-            for side in self._long:
-                if side is None:
-                    out.append((None, None))
-                    continue
-                partial = torch.empty((side["n_chunks"], ld), dtype=torch.float32, device=self.device)
-                out.append((GrfLongRows(LONG_ROW_THRESHOLD, side["n_long"], side["n_chunks"],
-                                        side["rows"].data_ptr(), side["chunk_ptr"].data_ptr(),
-                                        side["bounds"].data_ptr(), partial.data_ptr(), ld), partial))
-            self._long_c = {ld: out}
-        (fwd, _), (tr, _) = self._long_c[ld]
-        return fwd, tr
+    def _long_struct(self, side: Optional[dict], cache: dict, ld: int):
+        """ctypes GrfLongRows of one side with a partial buffer of leading dimension ``ld`` (cached per ld)."""
+        if side is None or ld <= 0:
+            return None
+        if ld not in cache:
+            partial = torch.empty((side["n_chunks"], ld), dtype=torch.float32, device=self.device)
+            cache.clear()
+            cache[ld] = (GrfLongRows(LONG_ROW_THRESHOLD, side["n_long"], side["n_chunks"], side["rows"].data_ptr(),
+                                     side["chunk_ptr"].data_ptr(), side["bounds"].data_ptr(), partial.data_ptr(), ld),
+                         partial)
+        return cache[ld][0]
 
-    def c_struct(self, ld: int = 0) -> GrfPhi:
-        tiles = self.use_tiles and self.win is not None
-        fwd, tr = self._long_structs(ld)
-        return GrfPhi(self.n_rows, self.n_cols, self.row_lo, self.n_steps, self.blk_ptr.data_ptr(),
+    def c_struct(self, ld: int = 0, block: Optional[int] = None) -> GrfPhi:
+        """The GrfPhi argument block.  ``block`` = None: all rows of Phi with the (single) Phi^T block -- both
+        halves of a product; ``block`` = b: the view of row block b for the first half (its rows of Phi, its
+        Phi^T)."""
+        tb = None
+        if self.tblocks:
+            tb = self.tblocks[0 if block is None else block]
+            if block is None and len(self.tblocks) != 1:
+                tb = None     # second half only: the forward side does not need Phi^T
+        whole = block is None
+        tiles = whole and self.use_tiles and self.win is not None
+        fwd = self._long_struct(self._long_fwd, self._long_fwd_c, ld) if (whole and self._long_built) else None
+        tr = self._long_struct(tb.long, tb.long_c, ld) if (tb is not None and self._long_built) else None
+        r0 = 0 if whole else tb.r0
+        n_rows = self.n_rows if whole else tb.n_rows
+        nnz = self.nnz if whole else tb.nnz
+        tcols = tb.tcols if tb is not None else None
+        return GrfPhi(n_rows, self.n_cols, self.row_lo + r0, self.n_steps,
+                      self.blk_ptr.data_ptr() + 4 * r0 * self.n_steps,
                       self.entries.data_ptr() if self.nnz else None,
-                      None if self.tblk_ptr is None else self.tblk_ptr.data_ptr(),
-                      None if self.tentries is None or not self.nnz else self.tentries.data_ptr(),
+                      None if tb is None else tb.tblk_ptr.data_ptr(),
+                      None if tb is None or not tb.nnz else tb.tentries.data_ptr(),
                       self.win.data_ptr() if tiles else None, self.twin.data_ptr() if tiles else None,
                       self.win_max_width if tiles else 0, self.twin_max_width if tiles else 0,
                       ctypes.pointer(fwd) if fwd is not None else None,
                       ctypes.pointer(tr) if tr is not None else None,
-                      None if self._tcols is None else self._tcols.data_ptr(),
-                      0 if self._tcols is None else self._tcols.numel(), self.nnz, self._sched_ptr())
+                      None if tcols is None else tcols.data_ptr(),
+                      0 if tcols is None else tcols.numel(), nnz, self._sched_ptr())
+
+    def _gather_flags(self):
+        sg = self.stream_gather or (False, False)
+        return (32 if sg[0] else 0), (32 if sg[1] else 0)
+
+    def _first_half(self, f, rows, n2, v, ldv, u, ldu, vfull, t, flags, structs=None):
+        """U = Phi[rows]^T V block by block (the second and later row blocks add to U)."""
+        fn, st = _lib.lib().grf_phi_matvec, _stream(self.device)
+        for b, tb in enumerate(self.tblocks):
+            c = structs[b] if structs is not None else self.c_struct((t + 3) // 4 * 4, block=b)
+            vb, nb = v, n2
+            if rows is None:
+                vb, nb = (None if v is None else v + 4 * tb.r0 * ldv), tb.n_rows
+            vf = None if vfull is None else vfull + 4 * tb.r0 * ldu
+            rc = fn(ctypes.byref(c), _ptr(f), None, tb.n_rows, _ptr(rows), nb,
+                    None if vb is None else ctypes.c_void_p(vb), ldv, None, 0, ctypes.c_void_p(u), ldu,
+                    None if vf is None else ctypes.c_void_p(vf), t, 1 | flags | (16 if b else 0), st)
+            if rc:
+                check(rc)
 
     def _sched_ptr(self):
         # ticket scratch of the matvec kernels (GrfPhi.sched): zero between launches
@@ -719,10 +883,11 @@ class PhiBlocks:
         if rows is not None or t % 4 != 0 or v.stride(0) % 4 != 0:
             # scatter target for a row subset / staging buffer for a V that is not 16-byte friendly
             vfull = torch.zeros((max(1, self.n_rows), u.stride(0)), dtype=torch.float32, device=dev)
-        phi = self.c_struct((t + 3) // 4 * 4)
-        check(_lib.lib().grf_phi_matvec(
-            ctypes.byref(phi), _ptr(f), None, self.n_rows, _ptr(rows), n2, _ptr(v), v.stride(0), None, 0,
-            _ptr(u), u.stride(0), _ptr(vfull), t, 1, _stream(dev)))
+        if self.n_rows == 0 or not self.tblocks:
+            u[:, :t].zero_()
+            return u[:, :t]
+        self._first_half(f, rows, n2, v.data_ptr(), v.stride(0), u.data_ptr(), u.stride(0),
+                         None if vfull is None else vfull.data_ptr(), t, self._gather_flags()[0])
         return u[:, :t]
 
     def apply(self, f, u, rows=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -744,7 +909,7 @@ class PhiBlocks:
         phi = self.c_struct((t + 3) // 4 * 4)
         check(_lib.lib().grf_phi_matvec(
             ctypes.byref(phi), _ptr(f), _ptr(rows), n1, None, self.n_rows, None, 0, _ptr(out), out.stride(0),
-            _ptr(u), u.stride(0), None, t, 2, _stream(dev)))
+            _ptr(u), u.stride(0), None, t, 2 | self._gather_flags()[1], _stream(dev)))
         return out
 
     def matvec(self, f, v, x1=None, x2=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -762,9 +927,11 @@ class PhiBlocks:
         res = self.apply(f, u, rows=x1, out=out)
         return res[:, 0] if squeeze else res
 
-    def plan(self, f, t: int, x1=None, x2=None, group=None, merged: bool = True) -> "MatvecPlan":
-        """Pre-validated kernel matvec for a CG loop: one C call (two launches) per product."""
-        return MatvecPlan(self, f, t, x1, x2, group, merged)
+    def plan(self, f, t: int, x1=None, x2=None, group=None, merged: bool = True, exchange=None) -> "MatvecPlan":
+        """Pre-validated kernel matvec for a CG loop: one C call (two launches) per product.  ``exchange``
+        (sharding.Exchange, with ``group``): the sum of the ranks' partials runs through it -- the plan writes its
+        partial straight into the exchange's (peer-mapped) U."""
+        return MatvecPlan(self, f, t, x1, x2, group, merged, exchange)
 
     def t_matvec(self, f, v, x2=None) -> torch.Tensor:
         """U = Phi[x2]^T v  ([n_cols, t]) in a fresh buffer."""
@@ -821,6 +988,8 @@ class PhiBlocks:
 
     @staticmethod
     def concat_rows(parts: Sequence["PhiBlocks"]) -> "PhiBlocks":
+        """Row chunks of one shard -> one PhiBlocks.  Parts that already carry their Phi^T keep it: the
+        result's Phi^T is the list of those row blocks (nothing is re-sorted)."""
         if len(parts) == 1:
             return parts[0]
         ptrs, base = [], 0
@@ -830,9 +999,18 @@ class PhiBlocks:
         if base >= 2 ** 31:
             raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
         ptrs.append(torch.tensor([base], dtype=torch.int64, device=parts[0].device))
-        return PhiBlocks(torch.cat(ptrs).to(torch.int32), torch.cat([p.entries for p in parts]),
-                         sum(p.n_rows for p in parts), parts[0].n_cols, parts[0].n_steps, parts[0].row_lo,
-                         sum(p.visits for p in parts))
+        out = PhiBlocks(torch.cat(ptrs).to(torch.int32), torch.cat([p.entries for p in parts]),
+                        sum(p.n_rows for p in parts), parts[0].n_cols, parts[0].n_steps, parts[0].row_lo,
+                        sum(p.visits for p in parts))
+        if all(p.tblocks is not None for p in parts):
+            out.tblocks, r0 = [], 0
+            for p in parts:
+                for tb in p.tblocks:
+                    nb = TBlock(r0 + tb.r0, tb.n_rows, tb.nnz, tb.tblk_ptr, tb.tentries)
+                    nb.census = tb.census
+                    out.tblocks.append(nb)
+                r0 += p.n_rows
+        return out
 
     def to_scipy_steps(self):
         """float32 step matrices back on the host (tests / interchange)."""
@@ -857,17 +1035,18 @@ class PhiBlocks:
 
 def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: int) -> PhiBlocks:
     L = cfg.max_walk_length
-    dev = st.stage_col.device
+    dev = st.row_cnt.device
     blk_ptr, total = scan_counts(st.row_cnt, st.n_rows, L, _lib.ORDER_ROW_MAJOR, i64=False, with_total=True)
     capacity = st.n_rows * st.stride            # one entry per staging slot at most
     pending = None
     if 0 < capacity * 8 <= _LAZY_ENTRY_BYTES:
         # small shard: allocate the bound, launch the compaction, and let the count arrive on the side
-        host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+        base = _small_pinned()
+        host = base[:2].view(torch.int64)
         host.copy_(total, non_blocking=True)
         arrived = torch.cuda.Event()
         arrived.record(torch.cuda.current_stream(dev))
-        _keep_until_done(host, arrived)
+        _keep_until_done(base, arrived)
         pending = (host, arrived)
         entries = torch.empty((capacity, 2), dtype=torch.int32, device=dev)
     else:
@@ -875,9 +1054,13 @@ def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: 
         if total >= 2 ** 31:
             raise ValueError("Phi shard exceeds 2^31 entries; shard the start nodes over more GPUs")
         entries = torch.empty((max(1, total), 2), dtype=torch.int32, device=dev)[:total]
-    check(_lib.lib().grf_compact_blocks(_ptr(st.stage_col), _ptr(st.stage_sum), _ptr(st.row_cnt), _ptr(blk_ptr),
-                                        st.n_rows, L, st.stride, cfg.walks_per_node, scale_mode, _ptr(entries),
-                                        _stream(dev)))
+    if st.stage_ent is not None:    # the walker already scaled and packed the entries
+        check(_lib.lib().grf_compact_entries(_ptr(st.stage_ent), _ptr(blk_ptr), st.n_rows, L, st.stride,
+                                             _ptr(entries), _stream(dev)))
+    else:
+        check(_lib.lib().grf_compact_blocks(_ptr(st.stage_col), _ptr(st.stage_sum), _ptr(st.row_cnt), _ptr(blk_ptr),
+                                            st.n_rows, L, st.stride, cfg.walks_per_node, scale_mode, _ptr(entries),
+                                            _stream(dev)))
     phi = PhiBlocks(blk_ptr, entries, st.n_rows, n_cols, L, st.row_lo)
     phi._nnz_pending = pending
     phi._col_counts = st.col_counts
@@ -886,25 +1069,48 @@ def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: 
 
 def build_phi_blocks(graph: DeviceGraph, cfg: WalkConfig, start_lo: int = 0, start_hi: Optional[int] = None,
                      scale_mode: int = _lib.SCALE_MUL_RECIP, transpose: bool = True,
-                     max_stage_bytes: int = _MAX_STAGE_BYTES) -> PhiBlocks:
-    """Walker + compaction straight into the matvec layout (no float64 CSR, no host round trip)."""
+                     max_stage_bytes: int = _MAX_STAGE_BYTES, block_rows: Optional[int] = None,
+                     phase_hook=None) -> PhiBlocks:
+    """Walker + compaction straight into the matvec layout (no float64 CSR, no host round trip).  A shard
+    beyond ~T_BLOCK_ROWS rows is walked, compacted and transposed one row block at a time: the walker counts
+    the Phi^T segment sizes of the block while it emits the entries, and the staging of one block is
+    recycled for the next."""
     cfg.validate()
     start_hi = graph.n_nodes if start_hi is None else start_hi
     stride = _lib.lib().grf_walk_stage_stride(cfg.walks_per_node, cfg.max_walk_length)
     visits = torch.zeros(1, dtype=torch.int64, device=graph.device)
-    col_counts = None
-    if transpose:   # the walker counts the Phi^T segment sizes while it emits the entries
-        col_counts = torch.zeros(max(1, graph.n_nodes * cfg.max_walk_length), dtype=torch.int32, device=graph.device)
+    block_rows = T_BLOCK_ROWS if block_rows is None else int(block_rows)
+    n_rows = start_hi - start_lo
+    n_blocks = 1 if n_rows <= block_rows + block_rows // 2 else -(-n_rows // block_rows)
+    bounds = [start_lo + n_rows * b // n_blocks for b in range(n_blocks + 1)]
     parts = []
-    for lo, hi in _row_chunks(start_lo, start_hi, stride, max_stage_bytes):
-        st = run_walker(graph, cfg, lo, hi, visits=visits, col_counts=col_counts)
-        parts.append(_blocks_from_staging(st, cfg, graph.n_nodes, scale_mode))
-        del st
+    for b in range(n_blocks):
+        col_counts = None
+        if transpose:   # the walker counts the Phi^T segment sizes while it emits the entries
+            col_counts = torch.zeros(max(1, graph.n_nodes * cfg.max_walk_length), dtype=torch.int32,
+                                     device=graph.device)
+        chunks = []
+        for lo, hi in _row_chunks(bounds[b], bounds[b + 1], stride, max_stage_bytes, slot_bytes=8):
+            if phase_hook is not None:
+                phase_hook("walk")
+            st = run_walker(graph, cfg, lo, hi, visits=visits, col_counts=col_counts, entries_scale_mode=scale_mode)
+            if phase_hook is not None:
+                phase_hook("compact")
+            chunks.append(_blocks_from_staging(st, cfg, graph.n_nodes, scale_mode))
+            del st
+        if phase_hook is not None:
+            phase_hook("transpose")
+        part = PhiBlocks.concat_rows(chunks)
+        part._col_counts = col_counts
+        if transpose:
+            part.build_transpose(block_rows=1 << 40)      # this row block is one Phi^T block
+        parts.append(part)
     phi = PhiBlocks.concat_rows(parts)
-    phi._col_counts = col_counts
     phi.row_lo = start_lo
     phi.visits = visits  # device counter; int(phi.visits) syncs
-    return phi.build_transpose() if transpose else phi
+    if phase_hook is not None:
+        phase_hook("end")
+    return phi
 
 
 def phi_blocks_from_scipy(mats, device=None, row_lo: int = 0, transpose: bool = True) -> PhiBlocks:
@@ -965,10 +1171,15 @@ class MatvecPlan:
     pattern of the per-length matrices (``PhiBlocks.merged``), re-materialised by
     ``set_modulator``; ``merged=False`` applies f per entry on the per-length blocks."""
 
-    def __init__(self, phi: PhiBlocks, f, t: int, x1=None, x2=None, group=None, merged: bool = True):
+    def __init__(self, phi: PhiBlocks, f, t: int, x1=None, x2=None, group=None, merged: bool = True, exchange=None):
         dev = phi.device
         self.base, self.merged = phi, bool(merged)
         self.t, self.group = int(t), group
+        self.exchange = exchange if group is not None else None
+        if self.merged:
+            phi.build_transpose()
+            if len(phi.tblocks) != 1:
+                self.merged = False     # a multi-block Phi^T multiplies the per-length blocks
         if self.merged:
             self.phi = phi.merged(f)
             self.f = torch.ones(1, dtype=torch.float32, device=dev)
@@ -983,17 +1194,25 @@ class MatvecPlan:
         self.n1 = phi.n_rows if self.x1 is None else self.x1.numel()
         self.n2 = phi.n_rows if self.x2 is None else self.x2.numel()
         self.ldu = (self.t + 3) // 4 * 4
-        self.u = torch.empty((max(1, phi.n_cols), self.ldu), dtype=torch.float32, device=dev)
+        if self.exchange is not None:
+            if tuple(self.exchange.u.shape) != (max(1, phi.n_cols), self.ldu):
+                raise ValueError("exchange buffer must be [n_cols, (t + 3) // 4 * 4] float32")
+            self.u = self.exchange.u
+        else:
+            self.u = torch.empty((max(1, phi.n_cols), self.ldu), dtype=torch.float32, device=dev)
         self.vfull = (torch.zeros((max(1, phi.n_rows), self.ldu), dtype=torch.float32, device=dev)
                       if (self.x2 is not None or self.t % 4 != 0) else None)
         # no repeated ids in x2 (the usual case: a training set) -> scatter without memset / atomics
         self._flags = 8 if (self.x2 is not None and self.x2.numel() > 0
                             and int(torch.unique(self.x2).numel()) == self.x2.numel()) else 0
-        self._c = self.phi.c_struct(self.ldu)
         self._fn = _lib.lib().grf_phi_matvec
         self._dev = dev
+        self._single = len(self.phi.tblocks) == 1
+        self._c = self.phi.c_struct(self.ldu)                                   # all rows (+ the only Phi^T block)
+        self._cb = [self.phi.c_struct(self.ldu, block=b) for b in range(len(self.phi.tblocks))]
+        self._gt, self._gf = self.phi._gather_flags()
         self._shared = self._shared_buf = None
-        if group is not None:
+        if group is not None and self.exchange is None:
             # exchange only the columns that more than one row shard touches (sharding.shared_columns)
             from . import sharding
 
@@ -1013,13 +1232,47 @@ class MatvecPlan:
         else:
             self.f.copy_(torch.as_tensor(f, device=self._dev).detach().to(torch.float32).reshape(-1))
 
+    def _tune_gathers(self):
+        """(Phi^T V, Phi U): does gathering with L1::no_allocate loads beat the cached loads on this Phi?
+        Measured once per Phi with CUDA events on a random right-hand side (3 products each way)."""
+        dev = self._dev
+        v = torch.randn((max(1, self.n2), self.t), dtype=torch.float32, device=dev)
+        out = torch.empty((max(1, self.n1), self.t), dtype=torch.float32, device=dev)
+        best = []
+        for half in (1, 2):
+            ms = []
+            for flag in (0, 32):
+                self._gt = self._gf = flag
+                self._call(v, out, half)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(torch.cuda.current_stream(dev))
+                for _ in range(3):
+                    self._call(v, out, half)
+                b.record(torch.cuda.current_stream(dev))
+                b.synchronize()
+                ms.append(a.elapsed_time(b))
+            best.append(ms[1] < 0.97 * ms[0])
+        return tuple(best)
+
     def _call(self, v, out, which):
-        rc = self._fn(ctypes.byref(self._c), _ptr(self.f), _ptr(self.x1), self.n1, _ptr(self.x2), self.n2,
-                      None if v is None else ctypes.c_void_p(v.data_ptr()), 0 if v is None else v.stride(0),
-                      None if out is None else ctypes.c_void_p(out.data_ptr()), 0 if out is None else out.stride(0),
-                      _ptr(self.u), self.ldu, _ptr(self.vfull), self.t, which | self._flags, _stream(self._dev))
-        if rc:
-            check(rc)
+        st = _stream(self._dev)
+        if which == 3 and self._single and self._gt == self._gf:
+            rc = self._fn(ctypes.byref(self._c), _ptr(self.f), _ptr(self.x1), self.n1, _ptr(self.x2), self.n2,
+                          ctypes.c_void_p(v.data_ptr()), v.stride(0), ctypes.c_void_p(out.data_ptr()), out.stride(0),
+                          _ptr(self.u), self.ldu, _ptr(self.vfull), self.t, 3 | self._flags | self._gt, st)
+            if rc:
+                check(rc)
+            return
+        if which & 1:
+            self.phi._first_half(self.f, self.x2, self.n2, v.data_ptr(), v.stride(0), self.u.data_ptr(), self.ldu,
+                                 None if self.vfull is None else self.vfull.data_ptr(), self.t,
+                                 self._flags | self._gt, structs=self._cb)
+        if which & 2:
+            rc = self._fn(ctypes.byref(self._c), _ptr(self.f), _ptr(self.x1), self.n1, None, self.phi.n_rows, None, 0,
+                          ctypes.c_void_p(out.data_ptr()), out.stride(0), _ptr(self.u), self.ldu, None, self.t,
+                          2 | self._gf, st)
+            if rc:
+                check(rc)
 
     def __call__(self, v: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """v: float32 [n2, t] with unit column stride; out: float32 [n1, t] (allocated if None)."""
@@ -1034,6 +1287,10 @@ class MatvecPlan:
             from . import sharding
 
             self._call(v, None, 1)
-            sharding.reduce_shared(self.u, self._shared, self._shared_buf, None if self.group is True else self.group)
+            if self.exchange is not None:
+                self.exchange.reduce(_stream(self._dev))
+            else:
+                sharding.reduce_shared(self.u, self._shared, self._shared_buf,
+                                       None if self.group is True else self.group)
             self._call(None, out, 2)
         return out

@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 
 from .engine import PhiBlocks
-from .linop import LinearOperator, _StandInLinearOperator
+from .linop import LinearOperator
 
 
 def _reduce_partial(u: torch.Tensor, group) -> torch.Tensor:
@@ -162,16 +162,13 @@ class GRFKernelOperator(LinearOperator):
     def solve(self, rhs, sigma2: float = 0.0, tolerance: float = 1e-2, max_iter: int = 1000, eps: float = 1e-10,
               return_info: bool = False):
         """(K + sigma2 I)^-1 rhs by conjugate gradients (no gradient tracking)."""
-        from .cg import linear_cg, linear_cg_fused
+        from .cg import linear_cg_fused
 
         with torch.no_grad():
             rhs2 = rhs[:, None] if rhs.dim() == 1 else rhs
-            if self.group is None:
-                out, info = linear_cg_fused(self.plan(rhs2.shape[1]), rhs2, sigma2, tolerance, max_iter, eps,
-                                            return_info=True)
-            else:
-                out, info = linear_cg(lambda v: self._matmul(v) + sigma2 * v, rhs2, tolerance, max_iter, eps,
-                                      return_info=True)
+            # single GPU or row-sharded: the fused vector kernels either way (sharded: dot products all-reduced)
+            out, info = linear_cg_fused(self.plan(rhs2.shape[1]), rhs2, sigma2, tolerance, max_iter, eps,
+                                        return_info=True)
             out = out[:, 0] if rhs.dim() == 1 else out
         return (out, info) if return_info else out
 
@@ -192,7 +189,3 @@ class GRFKernelOperator(LinearOperator):
         n2 = self._size()[1]
         return self._matmul(torch.eye(n2, dtype=torch.float32, device=self.device))
 
-
-if LinearOperator is _StandInLinearOperator:
-    # stand-in algebra: K + c*I etc. come from linop.py
-    pass

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GRF_B200_ABI_VERSION 2
+#define GRF_B200_ABI_VERSION 3
 
 enum {
     GRF_OK = 0,
@@ -73,6 +73,16 @@ typedef struct {
     const double *val;
 } GrfGraph;
 
+/* One edge of the walk graph as the walker reads it: the neighbour and the load factor
+ * (deg(row) * val) / (1 - p_halt) of sparse_sampler.py:54 side by side, so that a step costs one
+ * 16-byte gather instead of two from separate arrays (grf_edge_records builds them once per graph
+ * and p_halt; on graphs that miss L2 every gathered sector is DRAM traffic). */
+typedef struct {
+    double scaled;
+    int32_t col;
+    int32_t pad;
+} GrfEdge;
+
 /* Arguments of _worker_walks (sparse_sampler.py:26-31) plus the shard and the
  * draw source. */
 typedef struct {
@@ -90,12 +100,21 @@ typedef struct {
      * rng.integers(deg) (-1 where none) -- sparse_sampler.py:47,51 */
     const double *trace_u;
     const int32_t *trace_k;
-    /* optional: (deg(row) * val) / (1 - p_halt) per edge from grf_edge_scale (NULL: computed per step) */
-    const double *scaled_val;
+    /* optional: edge records from grf_edge_records for this p_halt (NULL: col_idx / val are gathered
+     * separately and the factor is computed per step, same roundings) */
+    const GrfEdge *edges;
     /* optional (device int32 [n_nodes][L], zeroed by the caller before the first launch of a shard):
      * += 1 per emitted entry at (column, length) -- the segment sizes of the Phi^T blocks, so that
      * grf_transpose_offsets need not re-read the entries to count them */
     int32_t *col_counts;
+    /* replay mode: walk id of element 0 of trace_u / trace_k (0 = the trace covers the whole graph; a
+     * trace recorded for a row slice starts at start_node * W) */
+    int64_t trace_walk_base;
+    /* optional output mode for the matvec layout: merged records leave the walker as finished Phi
+     * entries {length << 27 | col, (float)(sum "/ W")} in stage_entries [n_local * stage_stride]
+     * (same slots as stage_col / stage_sum, which may then be NULL); scale_mode as grf_compact_blocks */
+    GrfEntry *stage_entries;
+    int32_t scale_mode;
 } GrfWalkCfg;
 
 /* Optional split of long rows (hub columns of a power-law Phi^T hold 10^5..10^6 entries): rows
@@ -152,9 +171,9 @@ int grf_laplacian_count(const GrfGraph *adj, double *deg, double *dis, int32_t *
 int grf_laplacian_fill(const GrfGraph *adj, const double *deg, const double *dis, const int32_t *out_ptr,
                        int32_t *out_col, double *out_val, void *stream);
 
-/* Per-edge factor of the load update, (deg * w) / (1 - p_halt) with the reference's rounding
- * order (sparse_sampler.py:54); lets the walker skip a float64 division per step. */
-int grf_edge_scale(const GrfGraph *graph, double p_halt, double *scaled_val /* [nnz] */, void *stream);
+/* Edge records {(deg * w) / (1 - p_halt), neighbour} with the reference's rounding order
+ * (sparse_sampler.py:54): the walker then skips a float64 division and one gather per step. */
+int grf_edge_records(const GrfGraph *graph, double p_halt, GrfEdge *edges /* [nnz] */, void *stream);
 
 /* Staging entries per row the walker may write: 1 + (L-1)*W. */
 int64_t grf_walk_stage_stride(int32_t walks_per_node, int32_t max_walk_length);
@@ -189,6 +208,11 @@ int grf_compact_blocks(const int32_t *stage_col, const double *stage_sum, const 
                        const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int64_t stage_stride,
                        int32_t walks_per_node, int32_t scale_mode, GrfEntry *entries, void *stream);
 
+/* Staging already holds finished entries (GrfWalkCfg.stage_entries): gather every row's run to its
+ * final place. */
+int grf_compact_entries(const GrfEntry *stage_entries, const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps,
+                        int64_t stage_stride, GrfEntry *entries, void *stream);
+
 /* Same conversion from the reference layout (a list of L CSR matrices in
  * device memory, e.g. loaded from one of the reference's pickle caches). */
 int grf_blocks_from_steps(const int64_t *offsets_step_major, const int32_t *col, const double *val,
@@ -222,21 +246,26 @@ int grf_nonempty_rows(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, i
 
 /* Replaces sparse_lo.py:23-25 (.t().to_sparse_csr(), redone on every forward in
  * the reference): build Phi^T blocks once, in two calls that share one workspace of
- * grf_transpose_workspace_bytes(n_cols, L) bytes:
+ * grf_transpose_workspace_bytes(n_cols, L, nnz) bytes:
  *   grf_transpose_offsets  segment sizes per (column, length) and their prefix sum tblk_ptr
  *                          [n_cols*L + 1]; with census_host != NULL (pinned host int32[6]) also the
  *                          grf_row_census of Phi ([0..3)) and Phi^T ([3..6)), copied to the host
  *                          behind the scan so that it arrives while grf_transpose_fill still runs
- *   grf_transpose_fill     scatters the entries (col = local row) and sorts every segment by row;
- *                          `cursor` = the same workspace (its first n_cols*L + 2 ints) */
-int64_t grf_transpose_workspace_bytes(int64_t n_cols, int32_t n_steps);
+ *   grf_transpose_fill     the entries sorted by (column, length) with a stable LSD radix sort, so
+ *                          every segment is ordered by row (the fixed summation order of Phi^T V);
+ *                          tentries[k].col = length << 27 | row, rows counted from the first row passed
+ * Both take a ROW BLOCK of Phi: blk_ptr points at the block's first row pointer, n_rows is the
+ * block's row count, `entries` is the base of the whole entry array and [entry_lo, entry_lo + nnz)
+ * the block's entries.  Transposing a large shard block by block (2^19 rows, say) keeps the rows of V
+ * that one block's Phi^T gathers inside L2, and bounds the sort workspace (24 bytes per entry). */
+int64_t grf_transpose_workspace_bytes(int64_t n_cols, int32_t n_steps, int64_t nnz);
 int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
                           int32_t n_steps, const int32_t *col_counts /* from GrfWalkCfg, or NULL: counted here */,
                           int32_t *tblk_ptr, void *workspace, int32_t census_threshold, int32_t *census_host,
                           void *stream);
 int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
-                       int32_t n_steps, const int32_t *tblk_ptr, int32_t *cursor /* [n_cols*L + 2] scratch */,
-                       GrfEntry *tentries, void *stream);
+                       int32_t n_steps, int64_t entry_lo, int64_t nnz, void *workspace, GrfEntry *tentries,
+                       void *stream);
 
 /* Replaces the 2L SparseLinearOperator._matmul calls (sparse_lo.py:16-18), the
  * ConstantMul/Sum operators (sparse_grf_kernel.py:59-61) and the row selection
@@ -253,7 +282,10 @@ int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t 
  * which: 1 = first half only (U), 2 = second half only (out from U), 3 = both;
  * add 4 to force the global-gather kernel even when column windows are present; add 8 when x2
  * holds no repeated ids and vfull was zero-filled once by the caller (the scatter then needs no
- * memset and no atomics).  When V is not 16-byte friendly (e.g. t = 17) and vfull is given, V is
+ * memset and no atomics); add 16 to ADD the first half's result to U instead of overwriting it (the
+ * second and later row blocks of a shard whose Phi^T was built block by block); add 32 to gather the
+ * right-hand side with L1::no_allocate loads (a Phi without column locality: every gathered row is a
+ * miss, and not parking it in L1 saves the fill pass through the L1 data stage).  When V is not 16-byte friendly (e.g. t = 17) and vfull is given, V is
  * staged there and the product runs on the column count padded to a multiple of 4. */
 int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t n1, const int32_t *x2,
                    int64_t n2, const float *v, int64_t ldv, float *out, int64_t ldo, float *u, int64_t ldu,
@@ -287,6 +319,18 @@ int grf_union_materialize(const int32_t *blk_ptr, const int32_t *uptr, const int
  * P = Phi[x1]^T left) for the full derivative.  grad: float[L], accumulated. */
 int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, const float *left, int64_t ldl, const float *p,
                   int64_t ldp, int32_t t, float *grad, void *stream);
+
+/* The one exchange of the path (no reference counterpart: its matvec runs on one device):
+ * U <- sum over the GPUs of the partials U_g = Phi_g[x2]^T V_g between the two halves of a product, as one
+ * kernel per rank over NVLink peer memory.  peer_u[g] / peer_flags[g] (HOST arrays of `world` DEVICE pointers)
+ * are every rank's U buffer and flag block as mapped into this process (torch symmetric memory, cudaIpc...);
+ * all U buffers hold n_floats floats in the same layout, 16-byte aligned; a flag block has
+ * grf_exchange_flag_bytes(world) bytes, zero-filled once.  Every rank calls this with the same `epoch`,
+ * 1, 2, 3, ... per exchange.  On return (in stream order) this rank's U holds the sum -- added in rank
+ * order on every rank, so all copies are bit-identical.  The call must not be made by ranks that share a GPU. */
+int64_t grf_exchange_flag_bytes(int32_t world);
+int grf_exchange_sum(float *const *peer_u, uint32_t *const *peer_flags, int32_t world, int32_t rank,
+                     int64_t n_floats, uint32_t epoch, void *stream);
 
 /* Fused vector kernels of batched CG on (K + sigma2 I) X = B (csrc/grf_cg.cu); replace the
  * elementwise / reduction launches of upstream linear_cg as called at

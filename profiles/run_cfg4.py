@@ -46,10 +46,13 @@ for rep in range(args.reps):
     visits = int(phi.visits)
     print(f"rep{rep}: walk + compaction {ms:.2f} ms; {visits / 1e9:.3f} G walk-steps -> {visits / ms / 1e6:.2f} G/s; "
           f"nnz(Phi)={phi.nnz / 1e6:.1f} M; peak mem {torch.cuda.max_memory_allocated() / 2 ** 30:.1f} GiB", flush=True)
+    del phi
+for rep in range(args.reps):
+    phi, ms = timed(lambda: engine.build_phi_blocks(g, cfg, transpose=True))
+    print(f"rep{rep}: Phi build incl. Phi^T ({len(phi.tblocks)} row blocks): {ms:.2f} ms; "
+          f"peak mem {torch.cuda.max_memory_allocated() / 2 ** 30:.1f} GiB", flush=True)
     if rep + 1 < args.reps:
         del phi
-_, ms = timed(lambda: phi.build_transpose())
-print(f"Phi^T blocks: {ms:.2f} ms", flush=True)
 n, L, t = phi.n_rows, args.L, args.t
 f = torch.randn(L, device=dev)
 v = torch.randn(n, t, device=dev)
@@ -61,10 +64,13 @@ _, ms = timed(lambda: plan(v, out), 5)
 nb = 2 * phi.nnz * 8 + 2 * L * (n + 1) * 4 + 4 * n * t * 4
 print(f"matvec t={t} per-length blocks: {ms:.3f} ms -> {nb / ms / 1e6:.0f} GB/s algorithmic "
       f"({nb / ms / 1e6 / 6554.6:.3f} of 6554.6)", flush=True)
-_, ms1 = timed(lambda: plan._call(v, None, 1), 5)
-_, ms2 = timed(lambda: plan._call(None, out, 2), 5)
-print(f"   halves: Phi^T V {ms1:.3f} ms, Phi U {ms2:.3f} ms", flush=True)
-if args.merged:
+print(f"   gather variants chosen (Phi^T V, Phi U): stream={phi.stream_gather}", flush=True)
+for mode in ((False, False), (True, True)):
+    plan._gt, plan._gf = (32 if mode[0] else 0), (32 if mode[1] else 0)
+    _, ms1 = timed(lambda: plan._call(v, None, 1), 5)
+    _, ms2 = timed(lambda: plan._call(None, out, 2), 5)
+    print(f"   halves with stream={mode[0]}: Phi^T V {ms1:.3f} ms, Phi U {ms2:.3f} ms", flush=True)
+if args.merged and len(phi.tblocks) == 1:
     _, ms = timed(lambda: phi.build_union())
     print(f"union build {ms:.1f} ms; nnz_union={phi.nnz_union / 1e6:.1f} M of {phi.nnz / 1e6:.1f} M", flush=True)
     mplan = phi.plan(f, t, merged=True)
@@ -85,6 +91,7 @@ if args.stats:
     q = torch.tensor([0.5, 0.9, 0.99, 1.0], device=dev, dtype=torch.float64)
     print(f"   Phi row length: mean {float(rl.mean()):.1f}, quantiles 50/90/99/100 % = {torch.quantile(rl[:1 << 24], q).tolist()}")
     cl = cnt.double()
+    print(f"   Phi^T blocks: {[(tb.r0, tb.n_rows, tb.nnz) for tb in phi.tblocks]}")
     print(f"   Phi^T row length: mean {float(cl.mean()):.1f}, quantiles = {torch.quantile(cl[:1 << 24], q).tolist()}")
     step = (ent[:, 0] >> 27) & 31
     print(f"   entries per length: {torch.bincount(step.to(torch.int64), minlength=L).tolist()}")

@@ -64,6 +64,22 @@ def _worker(rank, world, port, out_dir):
     assert torch.allclose(sharding.reduce_shared(u_g.clone(), None), u_full)
     np.save(os.path.join(out_dir, f"out{rank}.npy"), out_g.numpy())
     np.save(os.path.join(out_dir, f"dots{rank}.npy"), dots.numpy())
+    # the Exchange object of the sharded plan in its all-reduce mode (what a box without peer memory runs)
+    ex = sharding.make_exchange(n, 4, "cpu", True, mode="auto")
+    assert ex.mode == "nccl" and tuple(ex.u.shape) == (n, 4) and "all-reduce" in ex.describe()
+    ex.u.copy_(u_g.float())
+    assert torch.allclose(ex.reduce().double(), u_full, rtol=1e-5, atol=1e-5)
+    # row-sharded CG: (Phi Phi^T + 0.3 I) x = b with all-reduced dot products == the dense solve
+    b_full = torch.tensor(rng.standard_normal((n, 3)), dtype=torch.float32)
+
+    def product(z):      # this rank's rows of K z, float32 vectors as on the GPU
+        u = torch.tensor(phi_g.T @ z.double().numpy())
+        dist.all_reduce(u)
+        return torch.tensor(phi_g @ u.numpy(), dtype=torch.float32) + 0.3 * z
+
+    x_g, info = sharding.sharded_cg(product, b_full[lo:hi].clone(), tolerance=1e-7, max_iter=300, return_info=True)
+    np.save(os.path.join(out_dir, f"cg{rank}.npy"), x_g.numpy())
+    np.save(os.path.join(out_dir, "cg_b.npy"), b_full.numpy())
     dist.destroy_process_group()
 
 
@@ -100,3 +116,26 @@ def test_two_rank_sharded_matvec_equals_unsharded(tmp_path):
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
     dots = [np.load(tmp_path / f"dots{r}.npy") for r in range(world)]
     assert np.allclose(dots[0], dots[1]) and np.allclose(dots[0], (want * v).sum(0))
+    phi = sum(fl * m for fl, m in zip([1.0, -0.5, 0.25], mats)).toarray()
+    b = np.load(tmp_path / "cg_b.npy").astype(np.float64)
+    x_want = np.linalg.solve(phi @ phi.T + 0.3 * np.eye(n), b)
+    x_got = np.concatenate([np.load(tmp_path / f"cg{r}.npy") for r in range(world)])
+    assert np.abs(x_got - x_want).max() <= 1e-4 * np.abs(x_want).max()
+
+
+def test_balanced_bounds_equalise_the_work_estimate():
+    """Strong-scaling shards: contiguous, monotone, equal sums of the per-node work estimate (isolated start nodes
+    count 0.15 of a walking one) -- on a graph whose isolated nodes are all at the high ids."""
+    from types import SimpleNamespace
+
+    from grf_b200 import sharding
+
+    deg = torch.cat([torch.full((1000,), 5), torch.zeros(3000, dtype=torch.int64)])
+    graph = SimpleNamespace(n_nodes=4000, row_ptr=torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)]))
+    b = sharding.balanced_bounds(graph, 4)
+    assert b[0] == 0 and b[-1] == 4000 and all(x <= y for x, y in zip(b, b[1:]))
+    w = torch.where(deg > 0, 1.0, 0.15)
+    loads = [float(w[b[i]:b[i + 1]].sum()) for i in range(4)]
+    assert max(loads) - min(loads) <= 1.0 + 1e-9
+    assert b[1] < 1000 and b[3] > 1000          # not equal counts: the walking nodes are split over several shards
+    assert sharding.balanced_bounds(graph, 1) == [0, 4000]

@@ -87,14 +87,14 @@ def test_transpose_is_exact_and_row_sorted(env, case):
             assert np.array_equal(vals[b:e], mt.data[mt.indptr[c]:mt.indptr[c + 1]])
 
 
-def test_transpose_with_hub_columns_uses_the_long_segment_sort(env):
+def test_transpose_with_hub_columns_is_row_sorted(env):
     eng = env["eng"]
     lap = env["o"].normalized_laplacian_sparse(powerlaw_graph(4000, 30000, 2))
     g = eng.DeviceGraph.from_scipy(lap)
     phi = eng.build_phi_blocks(g, eng.WalkConfig(30, 0.1, 3, seed=3))
     tptr = phi.tblk_ptr.cpu().numpy().astype(np.int64)
     seg = np.diff(tptr)
-    assert seg.max() > 256 and ((seg > 32) & (seg <= 256)).any(), "test graph should exercise every sort tier"
+    assert seg.max() > 256 and ((seg > 32) & (seg <= 256)).any(), "test graph should have hub, mid and short segments"
     rows = phi.tentries.cpu().numpy()[:, 0] & ((1 << 27) - 1)
     for g0 in np.flatnonzero(seg > 1):
         r = rows[tptr[g0]:tptr[g0 + 1]]
@@ -520,3 +520,82 @@ def test_large_grid_roundtrip_properties(env):
     ka, kb = phi.matvec(f, a).clone(), phi.matvec(f, b).clone()
     lhs, rhs = float((b * ka).sum()), float((a * kb).sum())
     assert abs(lhs - rhs) <= 1e-3 * max(abs(lhs), abs(rhs), 1.0)
+
+
+def test_row_blocked_transpose_multiplies_like_the_single_block(env, case):
+    """A shard beyond ~2^19 rows keeps Phi^T as one block per row range (cache blocking of V; bounded sort
+    workspace).  Forced here with tiny blocks: same Phi, the blocks' segments are the single block's segments
+    cut by row range, and every product agrees with the single-block result to fp32 summation-order round-off."""
+    eng, torch = env["eng"], env["torch"]
+    g, cfg, one = case["g"], case["cfg"], case["phi"]
+    many = eng.build_phi_blocks(g, cfg, block_rows=150)                        # walked and transposed block by block
+    split = eng.build_phi_blocks(g, cfg, transpose=False).build_transpose(block_rows=200)   # one Phi, split afterwards
+    assert len(many.tblocks) == 5 and len(split.tblocks) == 4
+    L, n, mask = one.n_steps, one.n_cols, (1 << 27) - 1
+    tptr1 = one.tblk_ptr.cpu().numpy().astype(np.int64)
+    tent1 = one.tentries.cpu().numpy()
+    for phi in (many, split):
+        assert torch.equal(phi.blk_ptr, one.blk_ptr) and torch.equal(phi.entries, one.entries)
+        assert sum(tb.n_rows for tb in phi.tblocks) == one.n_rows and sum(tb.nnz for tb in phi.tblocks) == one.nnz
+        got = [[] for _ in range(n * L)]
+        for tb in phi.tblocks:
+            tp = tb.tblk_ptr.cpu().numpy().astype(np.int64)
+            te = tb.tentries.cpu().numpy()
+            assert tp[-1] == tb.nnz
+            seg_of = np.repeat(np.arange(n * L), np.diff(tp))
+            assert np.all((te[:, 0] >> 27) == seg_of % L)
+            rows = (te[:, 0] & mask) + tb.r0
+            assert rows.min(initial=tb.r0) >= tb.r0 and rows.max(initial=tb.r0) < tb.r0 + tb.n_rows
+            order = np.lexsort((rows, seg_of))
+            assert np.array_equal(order, np.arange(order.size))               # sorted by (segment, row)
+            for k in np.flatnonzero(np.diff(tp)):
+                got[k].append(np.stack([rows[tp[k]:tp[k + 1]], te[tp[k]:tp[k + 1], 1]], axis=1))
+        for k in range(n * L):
+            want = np.stack([tent1[tptr1[k]:tptr1[k + 1], 0] & mask, tent1[tptr1[k]:tptr1[k + 1], 1]], axis=1)
+            have = np.concatenate(got[k]) if got[k] else np.zeros((0, 2), dtype=want.dtype)
+            assert np.array_equal(have, want), k
+    rng = np.random.default_rng(0)
+    f = torch.tensor(rng.standard_normal(L).astype(np.float32)).cuda()
+    x1 = torch.tensor(rng.integers(0, one.n_rows, 90)).cuda()
+    x2 = torch.tensor(np.r_[rng.permutation(one.n_rows)[:300], [5, 5, 7]]).cuda()          # repeated ids too
+    for t in (1, 4, 16, 17):
+        v = torch.tensor(rng.standard_normal((one.n_rows, t)).astype(np.float32)).cuda()
+        v2 = torch.tensor(rng.standard_normal((x2.numel(), t)).astype(np.float32)).cuda()
+        want_u, want = one.apply_t(f, v).clone(), one.matvec(f, v).clone()
+        want_sub = one.matvec(f, v2, x1=x1, x2=x2).clone()
+        want_plan = one.plan(f, t, merged=False)(v).clone()
+        for phi in (many, split):
+            tol = 4e-6 * float(want_u.abs().max())
+            assert float((phi.apply_t(f, v) - want_u).abs().max()) <= tol
+            assert float((phi.matvec(f, v) - want).abs().max()) <= 4e-6 * float(want.abs().max())
+            assert float((phi.matvec(f, v2, x1=x1, x2=x2) - want_sub).abs().max()) <= 4e-6 * float(want_sub.abs().max())
+            plan = phi.plan(f, t)                     # merged=True falls back to the per-length blocks here
+            assert not plan.merged
+            assert float((plan(v) - want_plan).abs().max()) <= 4e-6 * float(want_plan.abs().max())
+            sub = phi.plan(f, t, x1=x1, x2=x2[:300])
+            assert float((sub(v2[:300]) - one.matvec(f, v2[:300], x1=x1, x2=x2[:300])).abs().max()) <= \
+                4e-6 * float(want_sub.abs().max())
+    left = torch.tensor(rng.standard_normal((one.n_rows, 4)).astype(np.float32)).cuda()
+    right = torch.tensor(rng.standard_normal((one.n_rows, 4)).astype(np.float32)).cuda()
+    gw = one.fgrad(f, left, right)
+    assert float((many.fgrad(f, left, right) - gw).abs().max()) <= 1e-4 * float(gw.abs().max())
+
+
+def test_streaming_gathers_are_bit_identical(env, case):
+    """L1::no_allocate gathers (GrfPhi flag +32; picked per Phi by MatvecPlan._tune_gathers) change where a
+    gathered row is cached, not what is computed."""
+    eng, torch = env["eng"], env["torch"]
+    phi = eng.build_phi_blocks(case["g"], case["cfg"])
+    rng = np.random.default_rng(1)
+    f = torch.tensor(rng.standard_normal(phi.n_steps).astype(np.float32)).cuda()
+    for t in (3, 4, 16, 40):
+        v = torch.tensor(rng.standard_normal((phi.n_rows, t)).astype(np.float32)).cuda()
+        phi.stream_gather = (False, False)
+        want = phi.matvec(f, v).clone()
+        for mode in ((True, True), (True, False), (False, True)):
+            phi.stream_gather = mode
+            assert torch.equal(phi.matvec(f, v), want), (t, mode)
+            plan = phi.plan(f, t, merged=False)
+            assert torch.equal(plan(v), want), (t, mode)
+    plan = phi.plan(f, 16, merged=False)
+    assert plan._tune_gathers() in ((False, False), (False, True), (True, False), (True, True))

@@ -50,6 +50,40 @@ def test_replay_is_bit_exact_with_reference_sparse(env, path):
         assert csr_bits_equal(mats[s], golden_csr(z, f"step{s}", shape=(n, n))), (path, s)
 
 
+SLICES = sorted(glob.glob(os.path.join(GOLDEN, "slice_*.npz")))
+
+
+@pytest.mark.parametrize("path", SLICES, ids=[os.path.basename(p)[:-4] for p in SLICES])
+def test_replay_row_slice_of_huge_graph_is_bit_exact(env, path):
+    """One reference worker's rows of a 2^20 .. 2^25-node ring, replayed from a SLICE-LOCAL trace: the
+    64-bit (node, walk) sort keys of both walker variants, and replay without an n_nodes * W * L trace --
+    both layouts the walker can emit (float64 step matrices; finished float32 Phi entries)."""
+    from efficient_graph_gp_sparse.random_walk_samplers_sparse.sparse_sampler import SparseRandomWalk
+
+    o = env["o"]
+    z = np.load(path)
+    n, lo, hi = 1 << int(z["log2_n"]), int(z["lo"]), int(z["hi"])
+    W, p, L = int(z["W"]), float(z["p_halt"]), int(z["L"])
+    lap = o.ring_laplacian_csr(n, float(z["lap_diag"]), float(z["lap_off"]))
+    _, trace = o.worker_slice_rows(lap.indptr, lap.indices, lap.data, n, lo, hi, W, p, L, int(z["worker_seed"]),
+                                   record=True)
+    rw = SparseRandomWalk(lap, seed=1)
+    mats = rw.get_step_matrices_device(W, p, L, start_lo=lo, start_hi=hi, trace=trace, trace_start=lo).to_scipy()
+    want = [sp.csr_matrix((z[f"step{s}_data"], z[f"step{s}_indices"].astype(np.int32),
+                           z[f"step{s}_indptr"].astype(np.int32)), shape=(hi - lo, n)) for s in range(L)]
+    for s in range(L):
+        assert csr_bits_equal(mats[s], want[s]), (path, s)
+    phi = rw.get_phi_blocks(W, p, L, start_lo=lo, start_hi=hi, trace=trace, trace_start=lo)
+    got32 = phi.to_scipy_steps()
+    for s in range(L):
+        w32 = want[s].astype(np.float32)
+        assert np.array_equal(got32[s].indptr, w32.indptr) and np.array_equal(got32[s].indices, w32.indices)
+        assert np.array_equal(got32[s].data.view(np.int32), w32.data.view(np.int32)), (path, s)
+    # a trace that starts after the first start node is refused
+    with pytest.raises(ValueError):
+        rw.get_step_matrices_device(W, p, L, start_lo=lo - 1, start_hi=hi, trace=trace, trace_start=lo)
+
+
 @pytest.mark.parametrize("path", DENSE, ids=[os.path.basename(p)[:-4] for p in DENSE])
 def test_replay_is_bit_exact_with_reference_dense(env, path):
     from efficient_graph_gp.random_walk_samplers.sampler import Graph, RandomWalk
