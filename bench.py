@@ -376,10 +376,13 @@ def run_gpu(args):
     check = None
     if world > 1:
         plan(v, out)
-        gathered = [torch.empty((bounds[r + 1] - bounds[r], T_RHS), dtype=torch.float32, device=dev)
-                    for r in range(world)] if rank == 0 else None
-        dist.gather(out, gathered, dst=0)
+        most = max(bounds[r + 1] - bounds[r] for r in range(world))       # shards differ in size: pad to the largest
+        padded = torch.zeros((most, T_RHS), dtype=torch.float32, device=dev)
+        padded[: hi - lo] = out
+        gathered = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, gathered, dst=0)
         if rank == 0:
+            gathered = [g[: bounds[r + 1] - bounds[r]] for r, g in enumerate(gathered)]
             del results, phi, plan
             torch.cuda.empty_cache()
             full = engine.build_phi_blocks(graph, cfg)

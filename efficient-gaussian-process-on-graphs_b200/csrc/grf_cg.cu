@@ -252,7 +252,7 @@ extern "C" int32_t grf_cg_num_partials(int64_t n, int32_t t) { return cg_blocks(
 
 extern "C" int grf_cg_dot(float *ad, int64_t ldad, const float *d, int64_t ldd, float sigma2, int64_t n, int32_t t,
                           float *partial, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, ad);
     GRF_CG_CHECK("grf_cg_dot");
     GRF_REQUIRE(ad && d && partial && ldad == t && ldd == t, "grf_cg_dot: operands must be contiguous n x t");
     if (t % 4 == 0 && al16(ad) && al16(d))
@@ -265,7 +265,7 @@ extern "C" int grf_cg_dot(float *ad, int64_t ldad, const float *d, int64_t ldd, 
 extern "C" int grf_cg_update(float *x, int64_t ldx, float *r, int64_t ldr, const float *d, int64_t ldd,
                              const float *ad, int64_t ldad, const float *rs, const float *dad_partial, int64_t n,
                              int32_t t, float eps, float *rr_partial, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, x);
     GRF_CG_CHECK("grf_cg_update");
     GRF_REQUIRE(x && r && d && ad && rs && dad_partial && rr_partial, "grf_cg_update: null buffer");
     GRF_REQUIRE(ldx == t && ldr == t && ldd == t && ldad == t, "grf_cg_update: operands must be contiguous n x t");
@@ -279,7 +279,7 @@ extern "C" int grf_cg_update(float *x, int64_t ldx, float *r, int64_t ldr, const
 extern "C" int grf_cg_direction(float *d, int64_t ldd, const float *r, int64_t ldr, const float *rs,
                                 const float *rr_partial, int64_t n, int32_t t, float eps, float *rs_out,
                                 void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, d);
     GRF_CG_CHECK("grf_cg_direction");
     GRF_REQUIRE(d && r && rs && rr_partial && rs_out && rs != rs_out, "grf_cg_direction: bad buffers");
     GRF_REQUIRE(ldd == t && ldr == t, "grf_cg_direction: operands must be contiguous n x t");

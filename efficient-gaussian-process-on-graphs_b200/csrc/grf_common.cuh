@@ -32,28 +32,42 @@ struct StreamDeviceGuard {
     int prev = -1;
     bool switched = false;
     int rc = GRF_OK;
-    explicit StreamDeviceGuard(void *stream) {
+    // `anchor`: any device buffer of the call.  torch's current stream is usually the null stream, which names no
+    // device: then the device is the one that owns the anchor (cudaPointerGetAttributes, ~1 us).
+    StreamDeviceGuard(void *stream, const void *anchor) {
         int dev = -1;
         if (cudaGetDevice(&prev) != cudaSuccess) {
             cudaGetLastError();  // no usable device: argument checks still run, the first CUDA call reports it
             return;
         }
-        // the legacy / per-thread default stream handles belong to whatever device is current
-        if (stream == nullptr || stream == (void *)cudaStreamLegacy || stream == (void *)cudaStreamPerThread) return;
-        // a capturing stream is left alone: the capture was begun with its device current, and stream
-        // queries other than this one may invalidate the capture
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) {
-            cudaGetLastError();
+        const bool null_stream =
+            stream == nullptr || stream == (void *)cudaStreamLegacy || stream == (void *)cudaStreamPerThread;
+        if (!null_stream) {
+            // a capturing stream is left alone: the capture was begun with its device current, and stream
+            // queries other than this one may invalidate the capture
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) {
+                cudaGetLastError();
+                return;
+            }
+            if (cap != cudaStreamCaptureStatusNone) return;
+            if (cudaStreamGetDevice((cudaStream_t)stream, &dev) != cudaSuccess) {
+                cudaGetLastError();
+                return;
+            }
+        } else if (anchor != nullptr) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, anchor) != cudaSuccess) {
+                cudaGetLastError();
+                return;
+            }
+            if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) return;
+            dev = attr.device;
+        } else {
             return;
         }
-        if (cap != cudaStreamCaptureStatusNone) return;
-        if (cudaStreamGetDevice((cudaStream_t)stream, &dev) != cudaSuccess) {
-            cudaGetLastError();
-            return;
-        }
-        if (dev != prev) {
-            rc = check_cuda(cudaSetDevice(dev), "cudaSetDevice(stream's device)");
+        if (dev >= 0 && dev != prev) {
+            rc = check_cuda(cudaSetDevice(dev), "cudaSetDevice(device of the call's buffers)");
             switched = rc == GRF_OK;
         }
     }
@@ -62,8 +76,8 @@ struct StreamDeviceGuard {
     }
 };
 
-#define GRF_ON_STREAM_DEVICE(stream)                 \
-    ::grf::StreamDeviceGuard _grf_guard(stream);     \
+#define GRF_ON_STREAM_DEVICE(stream, anchor)                 \
+    ::grf::StreamDeviceGuard _grf_guard(stream, anchor);     \
     if (_grf_guard.rc != GRF_OK) return _grf_guard.rc
 
 // Phi / Phi^T entries carry their walk length in the top bits of `col`

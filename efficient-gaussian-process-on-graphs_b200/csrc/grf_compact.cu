@@ -296,7 +296,7 @@ extern "C" int64_t grf_scan_workspace_bytes(int64_t n_items) {
 
 extern "C" int grf_scan_counts(const int32_t *row_cnt, int64_t n_rows, int32_t n_steps, int32_t order, void *offsets,
                                int32_t out_is_i64, void *workspace, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, offsets);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_scan_counts: bad shape");
     GRF_REQUIRE(order == GRF_ORDER_ROW_MAJOR || order == GRF_ORDER_STEP_MAJOR, "grf_scan_counts: bad order");
     GRF_REQUIRE(offsets && workspace, "grf_scan_counts: null buffer");
@@ -327,7 +327,7 @@ extern "C" int grf_compact_steps(const int32_t *stage_col, const double *stage_s
                                  const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps,
                                  int64_t stage_stride, int32_t walks_per_node, int32_t scale_mode, int32_t *out_col,
                                  double *out_val, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, row_cnt);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && walks_per_node >= 1, "grf_compact_steps: bad shape");
     GRF_REQUIRE(scale_mode == GRF_SCALE_MUL_RECIP || scale_mode == GRF_SCALE_DIV, "grf_compact_steps: bad scale_mode");
     if (n_rows == 0) return GRF_OK;
@@ -342,7 +342,7 @@ extern "C" int grf_compact_steps(const int32_t *stage_col, const double *stage_s
 extern "C" int grf_compact_blocks(const int32_t *stage_col, const double *stage_sum, const int32_t *row_cnt,
                                   const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int64_t stage_stride,
                                   int32_t walks_per_node, int32_t scale_mode, GrfEntry *entries, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, blk_ptr);
     (void)row_cnt;
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && walks_per_node >= 1, "grf_compact_blocks: bad shape");
     GRF_REQUIRE(scale_mode == GRF_SCALE_MUL_RECIP || scale_mode == GRF_SCALE_DIV,
@@ -356,7 +356,7 @@ extern "C" int grf_compact_blocks(const int32_t *stage_col, const double *stage_
 
 extern "C" int grf_compact_entries(const GrfEntry *stage_entries, const int32_t *blk_ptr, int64_t n_rows,
                                    int32_t n_steps, int64_t stage_stride, GrfEntry *entries, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, blk_ptr);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && stage_stride >= 1, "grf_compact_entries: bad shape");
     if (n_rows == 0) return GRF_OK;
     GRF_REQUIRE(stage_entries && blk_ptr && entries, "grf_compact_entries: null buffer");
@@ -367,7 +367,7 @@ extern "C" int grf_compact_entries(const GrfEntry *stage_entries, const int32_t 
 
 extern "C" int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int32_t n_steps,
                                     int32_t *row_cnt, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, row_cnt);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_count_from_steps: bad shape");
     if (n_rows == 0) return GRF_OK;
     GRF_REQUIRE(offsets_step_major && row_cnt, "grf_count_from_steps: null buffer");
@@ -380,7 +380,7 @@ extern "C" int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n
 
 extern "C" int grf_row_census(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t threshold,
                               int32_t *census, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, census);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && threshold >= 1, "grf_row_census: bad shape");
     GRF_REQUIRE(census, "grf_row_census: null census");
     cudaStream_t st = (cudaStream_t)stream;
@@ -396,7 +396,7 @@ extern "C" int grf_row_census(const int32_t *blk_ptr, int64_t n_rows, int32_t n_
 extern "C" int grf_blocks_from_steps(const int64_t *offsets_step_major, const int32_t *col, const double *val,
                                      const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, GrfEntry *entries,
                                      void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, blk_ptr);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_blocks_from_steps: bad shape");
     if (n_rows == 0) return GRF_OK;
     GRF_REQUIRE(offsets_step_major && blk_ptr, "grf_blocks_from_steps: null buffer");
@@ -407,7 +407,7 @@ extern "C" int grf_blocks_from_steps(const int64_t *offsets_step_major, const in
 
 extern "C" int grf_nonempty_rows(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t *flags,
                                  int32_t *pos, void *scan_workspace, int32_t *ids, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, flags);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_nonempty_rows: bad shape");
     if (n_rows == 0) return GRF_OK;
     GRF_REQUIRE(blk_ptr && flags && pos && scan_workspace && ids, "grf_nonempty_rows: null buffer");

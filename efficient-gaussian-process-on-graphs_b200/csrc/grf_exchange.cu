@@ -102,7 +102,7 @@ extern "C" int64_t grf_exchange_flag_bytes(int32_t world) {
 
 extern "C" int grf_exchange_sum(float *const *peer_u, uint32_t *const *peer_flags, int32_t world, int32_t rank,
                                 int64_t n_floats, uint32_t epoch, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, (peer_u && rank >= 0 && rank < world ? peer_u[rank] : nullptr));
     GRF_REQUIRE(peer_u && peer_flags, "grf_exchange_sum: null pointer tables");
     GRF_REQUIRE(world >= 1 && world <= kExMaxWorld && rank >= 0 && rank < world,
                 "grf_exchange_sum: world must be 1..%d and rank inside it", kExMaxWorld);

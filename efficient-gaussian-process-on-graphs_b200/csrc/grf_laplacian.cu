@@ -180,7 +180,7 @@ static inline int lap_grid(int64_t n, int per_block) {
 using namespace grf;
 
 extern "C" int grf_laplacian_count(const GrfGraph *adj, double *deg, double *dis, int32_t *out_cnt, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, out_cnt);
     GRF_REQUIRE(adj, "grf_laplacian_count: null graph");
     GRF_REQUIRE(adj->n_nodes >= 0 && adj->n_nodes < (1ll << 31) && adj->nnz < (1ll << 31) - adj->n_nodes,
                 "grf_laplacian_count: graph exceeds int32 index range");
@@ -197,7 +197,7 @@ extern "C" int grf_laplacian_count(const GrfGraph *adj, double *deg, double *dis
 
 extern "C" int grf_laplacian_fill(const GrfGraph *adj, const double *deg, const double *dis, const int32_t *out_ptr,
                                   int32_t *out_col, double *out_val, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, out_ptr);
     GRF_REQUIRE(adj, "grf_laplacian_fill: null graph");
     if (adj->n_nodes == 0) return GRF_OK;
     GRF_REQUIRE(adj->row_ptr && deg && dis && out_ptr, "grf_laplacian_fill: null buffer");

@@ -945,7 +945,7 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
 extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *x1, int64_t n1, const int32_t *x2,
                               int64_t n2, const float *v, int64_t ldv, float *out, int64_t ldo, float *u, int64_t ldu,
                               float *vfull, int32_t t, int32_t which, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, u);
     GRF_REQUIRE(phi && f, "grf_phi_matvec: null phi/f");
     GRF_REQUIRE(t >= 1, "grf_phi_matvec: t must be >= 1");
     GRF_REQUIRE((which & 3) >= 1 && which <= 63, "grf_phi_matvec: which must be 1, 2 or 3 (+4, +8, +16, +32 flags)");
@@ -1068,7 +1068,7 @@ extern "C" int grf_phi_matvec(const GrfPhi *phi, const float *f, const int32_t *
 
 extern "C" int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, const float *left, int64_t ldl,
                              const float *p, int64_t ldp, int32_t t, float *grad, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, grad);
     GRF_REQUIRE(phi && left && p && grad, "grf_phi_fgrad: null argument");
     GRF_REQUIRE(t >= 1 && ldl >= t && ldp >= t, "grf_phi_fgrad: bad t / leading dimensions");
     GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_fgrad: n_steps out of range");
@@ -1087,7 +1087,7 @@ extern "C" int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, con
 
 extern "C" int grf_block_windows(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
                                  int32_t *win, int32_t *max_width, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, max_width);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_block_windows: bad shape");
     GRF_REQUIRE(max_width, "grf_block_windows: null max_width");
     cudaStream_t st = (cudaStream_t)stream;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) reach_round_kernel(const int32_t *__restr
 
 extern "C" int grf_shard_reach(const GrfGraph *graph, const int64_t *bounds, int32_t world, int32_t hops,
                                unsigned long long *mask, unsigned long long *scratch, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, mask);
     using namespace grf;
     GRF_REQUIRE(graph && bounds, "grf_shard_reach: null graph/bounds");
     GRF_REQUIRE(world >= 1 && world <= 64, "grf_shard_reach: world must be in [1, 64]");

@@ -355,7 +355,7 @@ static inline int grid_rows(int64_t n_rows) {
 extern "C" int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
                                      int32_t n_steps, const int32_t *col_counts, int32_t *tblk_ptr, void *workspace,
                                      int32_t census_threshold, int32_t *census_host, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, tblk_ptr);
     GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1, "grf_transpose_offsets: bad shape");
     GRF_REQUIRE(tblk_ptr && workspace, "grf_transpose_offsets: null buffer");
     GRF_REQUIRE(!census_host || census_threshold >= 1, "grf_transpose_offsets: bad census threshold");
@@ -390,7 +390,7 @@ extern "C" int grf_transpose_offsets(const int32_t *blk_ptr, const GrfEntry *ent
 extern "C" int grf_transpose_fill(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int64_t n_cols,
                                   int32_t n_steps, int64_t entry_lo, int64_t nnz, void *workspace,
                                   GrfEntry *tentries, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, workspace);
     GRF_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_steps >= 1 && nnz >= 0 && entry_lo >= 0,
                 "grf_transpose_fill: bad shape");
     GRF_REQUIRE(entry_lo + nnz < (1ll << 31), "grf_transpose_fill: entry range exceeds the 32-bit offsets");

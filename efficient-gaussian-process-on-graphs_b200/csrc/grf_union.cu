@@ -176,7 +176,7 @@ using namespace grf;
 
 extern "C" int grf_union_rank(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
                               uint32_t *mkey, float *mval, int32_t *ucnt, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, ucnt);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && n_steps <= kMaxSteps, "grf_union_rank: bad shape");
     if (n_rows == 0) return GRF_OK;
     GRF_REQUIRE(blk_ptr && mkey && mval && ucnt, "grf_union_rank: null buffer");
@@ -189,7 +189,7 @@ extern "C" int grf_union_rank(const int32_t *blk_ptr, const GrfEntry *entries, i
 
 extern "C" int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int64_t n_rows, int32_t n_steps,
                               const int32_t *uptr, int32_t *uhdr, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, uptr);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_union_fill: bad shape");
     if (n_rows == 0) return GRF_OK;
     GRF_REQUIRE(blk_ptr && mkey && uptr && uhdr, "grf_union_fill: null buffer");
@@ -201,7 +201,7 @@ extern "C" int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int6
 extern "C" int grf_union_materialize(const int32_t *blk_ptr, const int32_t *uptr, const int32_t *uhdr,
                                      const float *mval, const float *f, int64_t n_rows, int32_t n_steps,
                                      GrfEntry *entries_f, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, uptr);
     GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && n_steps <= kMaxSteps, "grf_union_materialize: bad shape");
     if (n_rows == 0) return GRF_OK;
     GRF_REQUIRE(blk_ptr && uptr && f, "grf_union_materialize: null buffer");

@@ -66,22 +66,22 @@ struct WalkParams {
 // rate and three DRAM sectors per walk-step.
 __device__ __forceinline__ uint64_t l2_policy_keep() {
     uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 __device__ __forceinline__ uint64_t l2_policy_stream() {
     uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 __device__ __forceinline__ int32_t ld_keep_s32(const int32_t *ptr, uint64_t pol) {
-    int32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    int32_t v;  // not volatile: a read-only load the compiler may schedule freely among the other gathers
+    asm("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
     return v;
 }
 __device__ __forceinline__ GrfEdge ld_stream_edge(const GrfEdge *ptr, uint64_t pol) {
     int4 raw;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
                  : "l"(ptr), "l"(pol));
     GrfEdge e;
@@ -458,7 +458,7 @@ extern "C" int64_t grf_walk_stage_stride(int32_t walks_per_node, int32_t max_wal
 
 extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t stage_stride, int32_t *stage_col,
                         double *stage_sum, int32_t *row_cnt, unsigned long long *visits_out, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, row_cnt);
     using namespace grf;
     GRF_REQUIRE(graph && cfg, "grf_walk: null graph/cfg");
     GRF_REQUIRE(graph->n_nodes >= 0 && graph->n_nodes < (1ll << 31), "grf_walk: n_nodes %lld out of int32 range",
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(256) edge_records_kernel(const int32_t *__rest
 }  // namespace grf
 
 extern "C" int grf_edge_records(const GrfGraph *graph, double p_halt, GrfEdge *edges, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream);
+    GRF_ON_STREAM_DEVICE(stream, edges);
     using namespace grf;
     GRF_REQUIRE(graph, "grf_edge_records: null graph");
     GRF_REQUIRE(p_halt >= 0.0 && p_halt <= 1.0, "grf_edge_records: p_halt must be in [0, 1]");

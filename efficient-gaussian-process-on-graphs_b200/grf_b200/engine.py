@@ -53,20 +53,23 @@ _free_small_pinned = []
 
 
 def _small_pinned() -> torch.Tensor:
-    """64 bytes of pinned host memory for a count / census that the GPU copies back asynchronously.  Recycled:
-    cudaHostAlloc costs ~0.1 ms and serialises with the device, and every Phi build needs two or three."""
-    done = [(b, e) for b, e in _pending_host if e.query()]
-    if done:
-        _pending_host[:] = [(b, e) for b, e in _pending_host if not e.query()]
-        _free_small_pinned.extend(b for b, _ in done if b.numel() == 16 and b.dtype == torch.int32)
+    """64 bytes of pinned host memory for a count / census that the GPU copies back asynchronously.  Recycled
+    (``_recycle_pinned``, by the reader once it has the value): cudaHostAlloc costs ~0.1 ms and serialises with
+    the device, and every Phi build needs two or three."""
     if _free_small_pinned:
         return _free_small_pinned.pop()
     return torch.empty(16, dtype=torch.int32, pin_memory=True)
 
 
+def _recycle_pinned(buf: Optional[torch.Tensor]) -> None:
+    if buf is not None and len(_free_small_pinned) < 64 and not any(b is buf for b in _free_small_pinned):
+        _free_small_pinned.append(buf)
+
+
 def _keep_until_done(buf: torch.Tensor, event: torch.cuda.Event) -> None:
     """The C library copies into ``buf`` (pinned) asynchronously, which torch's host allocator does
     not see: hold a reference until the copy's event has completed, whoever drops the owner first."""
+    _pending_host[:] = [(b, e) for b, e in _pending_host if not e.query()]
     _pending_host.append((buf, event))
 
 
@@ -501,10 +504,11 @@ class PhiBlocks:
         the offset scan -- is first needed; by then the compaction kernel is already queued, so reading
         it does not idle the GPU."""
         if self._nnz_pending is not None:
-            host, arrived = self._nnz_pending
+            host, arrived, base = self._nnz_pending
             arrived.synchronize()
             self._nnz_pending = None
             self._entries = self._entries[: int(host[0])]
+            _recycle_pinned(base)
         return self._entries
 
     @entries.setter
@@ -616,7 +620,7 @@ class PhiBlocks:
         if host is not None:
             arrived = torch.cuda.Event()
             arrived.record(torch.cuda.current_stream(dev))
-            tb.census = (host, arrived)
+            tb.census = (host, arrived, base)
             _keep_until_done(base, arrived)
         check(L.grf_transpose_fill(ptr, ent, r1 - r0, self.n_cols, self.n_steps, e0, nnz, _ptr(ws), _ptr(tentries), st))
         return tb
@@ -645,7 +649,7 @@ class PhiBlocks:
         host.copy_(census, non_blocking=True)
         arrived = torch.cuda.Event()
         arrived.record(torch.cuda.current_stream(dev))
-        tb.census = (host, arrived)
+        tb.census = (host, arrived, base)
         _keep_until_done(base, arrived)
 
     def build_windows(self) -> "PhiBlocks":
@@ -754,9 +758,11 @@ class PhiBlocks:
                 if tb.nnz == 0:
                     continue
                 self._start_census(tb)
-                host, done = tb.census
+                host, done, base = tb.census
                 done.synchronize()
                 long_f, _, _, long_t, _, cols_used = host.tolist()
+                tb.census = (host.clone(), done, None)      # the values stay; the pinned buffer goes back to the pool
+                _recycle_pinned(base)
                 any_long_fwd = any_long_fwd or bool(long_f)
                 tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols) if long_t else None
                 if len(self.tblocks) == 1:
@@ -1047,7 +1053,7 @@ def _blocks_from_staging(st: Staging, cfg: WalkConfig, n_cols: int, scale_mode: 
         arrived = torch.cuda.Event()
         arrived.record(torch.cuda.current_stream(dev))
         _keep_until_done(base, arrived)
-        pending = (host, arrived)
+        pending = (host, arrived, base)
         entries = torch.empty((capacity, 2), dtype=torch.int32, device=dev)
     else:
         total = int(total.item())

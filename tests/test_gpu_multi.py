@@ -26,7 +26,9 @@ def test_two_ranks_match_the_single_gpu_product_and_the_oracle():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tests", "multi_rank_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0 and "MULTI_RANK_OK" in res.stdout, (res.stdout[-3000:], res.stderr[-3000:])
+    if res.returncode != 0 or "MULTI_RANK_OK" not in res.stdout:
+        lines = [ln for ln in res.stderr.splitlines() if "Error" in ln or "error" in ln][-12:]
+        pytest.fail("multi-rank worker failed:\n" + "\n".join(lines) + "\n--- stdout ---\n" + res.stdout[-1500:])
 
 
 def test_entry_points_run_on_the_device_of_their_stream():
