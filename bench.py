@@ -341,6 +341,23 @@ def run_gpu(args):
     gc.enable()
     clocks = sampler.stop() if rank == 0 else None
 
+    # kernels of libgrf_b200.so per step, COUNTED: one more (untimed) step under torch's CUPTI profiler
+    measured_launches = None
+    if rank == 0:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                r = one_step()
+                torch.cuda.synchronize(dev)
+            del r
+            names = [e.name for e in prof.events() if str(getattr(e, "device_type", "")).endswith("CUDA")]
+            ours = [nm for nm in names if "grf::" in nm]
+            measured_launches = {"grf_kernels": len(ours), "other_kernels_and_copies": len(names) - len(ours),
+                                 "distinct_grf_kernels": len({nm.split("(")[0] for nm in ours})}
+        except Exception as exc:        # no CUPTI on the box: fall back to the structural count below
+            measured_launches = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
     step_ms_total = sum(r["step"][0].elapsed_time(r["step"][1]) for r in results)
     phase_ms = {}
     for r in results:
@@ -371,6 +388,38 @@ def run_gpu(args):
     torch.cuda.synchronize(dev)
     mv_ms = sorted(a.elapsed_time(b) for a, b in mv_events)
     half_ms = [a.elapsed_time(b) / 5 for a, b in halves]
+
+    # ---- the CG steady state: Phi_f materialised on the union pattern of the per-length matrices (rows sorted by
+    # column across the lengths: 6 % fewer entries here, and gathers in ascending order); built once per Phi,
+    # re-materialised once per modulator value, then one product per CG iteration
+    merged_ms = None
+    if not args.no_merged:
+        def timed_once(fn):
+            a, b = ev(), ev()
+            a.record(stream)
+            r = fn()
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            return r, a.elapsed_time(b)
+
+        _, union_ms = timed_once(phi.build_union)
+        mplan, _ = timed_once(lambda: phi.plan(f, T_RHS, group=group, merged=True, exchange=exchange))
+        _, mat_ms = timed_once(lambda: mplan.set_modulator(f))
+        for _ in range(3):
+            mplan(v, out)
+        evs = []
+        for _ in range(20):
+            a, b = ev(), ev()
+            a.record(stream)
+            mplan(v, out)
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        ms = sorted(a.elapsed_time(b) for a, b in evs)
+        merged_ms = [ms[len(ms) // 2], ms[0], union_ms, mat_ms, float(phi.nnz_union)]
+        del mplan
+        phi._union = None
+        torch.cuda.empty_cache()
 
     # ---- N ranks == 1 rank: rank 0 rebuilds the whole Phi on its GPU and multiplies the concatenated V
     check = None
@@ -419,6 +468,14 @@ def run_gpu(args):
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     red, work = red.tolist(), work.tolist()
+    merged = None
+    if merged_ms is not None:
+        mred = torch.tensor(merged_ms[:4], dtype=torch.float64, device=dev)
+        msum = torch.tensor(merged_ms[4:], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(mred, op=dist.ReduceOp.MAX)
+            dist.all_reduce(msum, op=dist.ReduceOp.SUM)
+        merged = mred.tolist() + msum.tolist()
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -466,11 +523,19 @@ def run_gpu(args):
                                 "note": "per GPU.  The formula counts the X gathers as free; on this graph they are not: "
                                         "2 x nnz x 64 B = 67 GB of gathered rows per product, 33 GB of them from DRAM "
                                         "(hub columns of Phi^T gather V rows spread over all 268 MB of V)"},
+            "cg_matvec_merged": None if merged is None else {
+                "ms": merged[0], "ms_min": merged[1], "algorithmic_gbs": mv_bytes / (merged[0] * 1e-3) / 1e9,
+                "frac": mv_bytes / (merged[0] * 1e-3) / 1e9 / world / peak, "nnz_union": merged[4],
+                "union_build_ms_once_per_phi": merged[2], "materialize_ms_once_per_modulator": merged[3],
+                "includes_exchange": world > 1,
+                "what": "the product a CG iteration runs: Phi_f on the union pattern (f applied when it is "
+                        "materialised, once per modulator value); same algorithmic bytes as the per-length product "
+                        "in the numerator (SURVEY 8d counts per-length entries), per GPU in frac"},
             "e2e": e2e, "config2": cfg2,
             "gpu_launches": None,
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
-        line["gpu_launches"] = count_launches(line, world)
+        line["gpu_launches"] = count_launches(line, world, measured_launches)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
         print(json.dumps(line))
@@ -478,13 +543,18 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def count_launches(line, world):
-    """Kernels of libgrf_b200.so launched per step on one rank, counted from the call structure (not a timer):
-    walker 1, row-count scan 3, compaction 1, Phi^T: offsets scan 3 + census 2 + key pass 1 + 3 radix passes x
-    (histogram 1 + scan 3 + scatter 1), matvec: 2 main passes + 2 hub-chunk passes + 2 ordered reductions,
-    exchange 1 when sharded."""
-    per_step = 1 + 3 + 1 + (3 + 2 + 1 + 3 * 5) + 6 + (1 if world > 1 else 0)
-    return {"per_step_per_rank": per_step, "timed_region": per_step * line["steps"] * world}
+def count_launches(line, world, measured):
+    """Kernels of libgrf_b200.so launched per step on one rank: counted by CUPTI (torch.profiler) over one extra
+    untimed step of rank 0 when that works, else from the call structure -- walker 1, row-count scan 3,
+    compaction 1, Phi^T: offsets scan 3 + census 2 + key pass 1 + 3 radix passes x (histogram 1 + scan 3 +
+    scatter 1), matvec: 2 main passes + 2 hub-chunk passes + 2 ordered reductions, exchange 1 when sharded."""
+    structural = 1 + 3 + 1 + (3 + 2 + 1 + 3 * 5) + 6 + (1 if world > 1 else 0)
+    if measured and "grf_kernels" in measured:
+        per_step, how = measured["grf_kernels"], "counted (CUPTI via torch.profiler, one extra untimed step on rank 0)"
+    else:
+        per_step, how = structural, "from the call structure (profiler unavailable)"
+    return {"per_step_per_rank": per_step, "timed_region": per_step * line["steps"] * world, "how": how,
+            "profile": measured, "structural_estimate": structural}
 
 
 def e2e_leg(args, torch, dist, engine, sharding, dev, world, rank, bounds, f, v, group, exchange, barrier):
@@ -502,7 +572,7 @@ def e2e_leg(args, torch, dist, engine, sharding, dev, world, rank, bounds, f, v,
     torch.cuda.empty_cache()
     v_host = v.cpu().pin_memory()
     out_host = torch.empty((hi - lo, T_RHS), dtype=torch.float32).pin_memory()
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 10))
     total, visits, h2d, d2h = 0.0, 0, 0, 0
     for i in range(1 + steps):
         barrier()
@@ -644,6 +714,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config2", action="store_true")
+    ap.add_argument("--no-merged", action="store_true", help="skip the union-layout (CG steady state) product")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -51,6 +51,7 @@ struct Vec<4> {
     // through the L1 data stage instead of two -- fill, then read; ncu on the power-law Phi: 1.75
     // wavefronts per gathered entry at a 27 % hit rate)
     __device__ __forceinline__ void load_stream(const float *p) {
+        // (ld.global.cg instead: Phi^T V 12.9 ms, Phi U 25.6 ms against 5.4 / 5.0 ms with cached loads at config 4)
         asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                      : "l"(p));
@@ -264,11 +265,14 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
         b = e = 0;
         orow = k;
         if (chunk_bounds) {
+            // chunk launch: row_ids, when given, is the order in which the chunks are issued (GrfLongRows.chunk_order)
             mine = k < n_tasks;
             if (mine) {
-                const int2 be = __ldg(chunk_bounds + k);
+                const int64_t c = row_ids ? (int64_t)__ldg(row_ids + k) : k;
+                const int2 be = __ldg(chunk_bounds + c);
                 b = be.x;
                 e = be.y;
+                orow = c;
             }
             return;
         }
@@ -296,7 +300,9 @@ __global__ void __launch_bounds__(256, spmm_min_blocks(TPR)) spmm_blocks_kernel(
     // (with a grid-wide stride every iteration of a warp landed in a fresh window).
     const int32_t n_static = sched ? (int32_t)((int64_t)n_iters * GRF_SPMM_STATIC_PCT / 100) : n_iters;
     int32_t it, it_step, it_end;
-    if (gridDim.x % kSmCount == 0) {
+    // (an ordered chunk launch wants the opposite: all SMs advance through the order together, so that the
+    // chunks in flight share one window of X in L2 -> plain grid stride)
+    if (gridDim.x % kSmCount == 0 && !(chunk_bounds && row_ids)) {
         const int warps_per_block = blockDim.x >> 5;
         const int per_sm = gridDim.x / kSmCount;
         // CTAs are handed to the SMs round-robin, so blockIdx = s, s + 148, ... share an SM and its L1
@@ -686,6 +692,57 @@ __global__ void __launch_bounds__(256) long_reduce_kernel(const int32_t *__restr
     }
 }
 
+// dots[i][l] = sum over the length-l entries e of row a_i of  e.val * Phi_f[b_i, col(e)],
+// Phi_f[b, c] = sum_l' f[l'] * M_l'[b, c]  -- so that  sum_l f[l] * dots[i][l] = <Phi_f[a_i, :], Phi_f[b_i, :]>,
+// the i-th diagonal element of K[x1, x2] (sparse_grf_kernel.py:55-57 densifies both row sets for it), and the
+// columns of `dots` are what the modulator gradient of that diagonal needs.  One warp per pair: lanes take the
+// entries of row a, and look each column up in the L column-sorted segments of row b (binary search).
+__global__ void __launch_bounds__(256) row_dots_kernel(const int32_t *__restrict__ ptr, const GrfEntry *__restrict__ ent,
+                                                       const float *__restrict__ f, int32_t L,
+                                                       const int32_t *__restrict__ x1, const int32_t *__restrict__ x2,
+                                                       int64_t n, int64_t row_lo, int64_t n_rows,
+                                                       float *__restrict__ dots) {
+    __shared__ float fs[kMaxSteps];
+    if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? __ldg(f + threadIdx.x) : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int2 *ent2 = reinterpret_cast<const int2 *>(ent);
+    for (int64_t i = warp0; i < n; i += n_warps) {
+        const int64_t a = (x1 ? (int64_t)__ldg(x1 + i) : i + row_lo) - row_lo;
+        const int64_t b = (x2 ? (int64_t)__ldg(x2 + i) : i + row_lo) - row_lo;
+        const bool mine = a >= 0 && a < n_rows && b >= 0 && b < n_rows;   // pairs outside this shard stay zero
+        for (int l = 0; l < L; ++l) {
+            double acc = 0.0;
+            if (mine) {
+                const int32_t ab = __ldg(ptr + a * L + l), ae = __ldg(ptr + a * L + l + 1);
+                for (int32_t k = ab + lane; k < ae; k += 32) {
+                    const int2 ea = __ldg(ent2 + k);
+                    const uint32_t col = (uint32_t)ea.x & kColMask;
+                    float w = 0.f;   // Phi_f[b, col]
+                    for (int m = 0; m < L; ++m) {
+                        int32_t lo = __ldg(ptr + b * L + m), hi = __ldg(ptr + b * L + m + 1);
+                        while (lo < hi) {
+                            const int32_t mid = lo + ((hi - lo) >> 1);
+                            const uint32_t c = (uint32_t)__ldg(&ent2[mid].x) & kColMask;
+                            if (c < col) lo = mid + 1; else hi = mid;
+                        }
+                        if (lo < __ldg(ptr + b * L + m + 1)) {
+                            const int2 eb = __ldg(ent2 + lo);
+                            if (((uint32_t)eb.x & kColMask) == col) w = fmaf(fs[m], __int_as_float(eb.y), w);
+                        }
+                    }
+                    acc += (double)__int_as_float(ea.y) * (double)w;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane == 0) dots[i * L + l] = (float)acc;
+        }
+    }
+}
+
 // grad[l] += sum_k sum_c left[k, c] * (sum_{e in seg(row_k, l)} e.val * P[e.col, c])
 
 template <int TPR, int VEC>
@@ -929,8 +986,8 @@ static int launch_spmm_pass(const int32_t *ptr, const GrfEntry *ent, const float
         const int32_t pvec = (lr->ld % 4 == 0) && aligned16(lr->partial);
         const int gridc = spmm_grid(lr->n_chunks, sh.tpr);
         GRF_DISPATCH_SPMM(sh, stream_gather,
-                          <<<gridc, 256, 0, st>>>(ptr, ent, f, L, nullptr, lr->n_chunks, 0, lr->n_chunks, X, ldx,
-                                                  lr->partial, lr->ld, t, t, pvec, 0,
+                          <<<gridc, 256, 0, st>>>(ptr, ent, f, L, lr->chunk_order, lr->n_chunks, 0, lr->n_chunks, X,
+                                                  ldx, lr->partial, lr->ld, t, t, pvec, 0,
                                                   (const int2 *)lr->chunk_bounds, 0, sched, 0));
         GRF_CUDA_OK(cudaGetLastError());
         int64_t g = ((int64_t)lr->n_long * t + 255) / 256;
@@ -1083,6 +1140,22 @@ extern "C" int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, con
                        <<<grid, 256, 0, (cudaStream_t)stream>>>(phi->blk_ptr, phi->entries, phi->n_steps, x, n,
                                                                 phi->row_lo, phi->n_rows, left, ldl, p, ldp, t, grad));
     return check_cuda(cudaGetLastError(), "fgrad_blocks_kernel launch");
+}
+
+extern "C" int grf_phi_row_dots(const GrfPhi *phi, const float *f, const int32_t *x1, const int32_t *x2, int64_t n,
+                                float *dots, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream, dots);
+    GRF_REQUIRE(phi && f && dots, "grf_phi_row_dots: null argument");
+    GRF_REQUIRE(phi->n_steps >= 1 && phi->n_steps <= kMaxSteps, "grf_phi_row_dots: n_steps out of range");
+    GRF_REQUIRE(n >= 0, "grf_phi_row_dots: negative n");
+    GRF_REQUIRE((x1 && x2) || n == phi->n_rows, "grf_phi_row_dots: n must equal n_rows when an index list is NULL");
+    if (n == 0) return GRF_OK;
+    GRF_REQUIRE(phi->blk_ptr, "grf_phi_row_dots: Phi blocks missing");
+    int64_t g = (n + 7) / 8;
+    if (g > (int64_t)kSmCount * 16) g = (int64_t)kSmCount * 16;
+    row_dots_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(phi->blk_ptr, phi->entries, f, phi->n_steps, x1, x2, n,
+                                                              phi->row_lo, phi->n_rows, dots);
+    return check_cuda(cudaGetLastError(), "row_dots_kernel launch");
 }
 
 extern "C" int grf_block_windows(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,

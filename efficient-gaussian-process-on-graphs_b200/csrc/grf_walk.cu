@@ -139,8 +139,13 @@ __device__ __forceinline__ int group_excl_scan(int v, int *scratch, int &total) 
 // kWide: a lane advances up to four of its walks together (graphs that miss L2: the walker is bound by DRAM
 // latency and needs the independent gathers); otherwise one walk at a time (an L2-resident graph: the walker is
 // bound by instruction issue, and the bookkeeping of four interleaved walks costs more than it hides).
-template <bool kBlock, typename KeyT, int KPL, bool kFast, bool kWide>
+// kStepSync (CTA-per-node only): the W walks of a start node advance one step at a time and every length is
+// merged and written out before the next step, so shared memory holds ONE length's visit records (W x 12 bytes)
+// instead of all L-1 of them -- the fallback for W x L beyond 227 KB (the reference's wind experiment runs
+// W = 8192, L = 5, its ablation notebook W = 10000, L = 10).  Same draws, same arithmetic, same output.
+template <bool kBlock, typename KeyT, int KPL, bool kFast, bool kWide, bool kStepSync>
 __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINBLOCKS) walk_merge_kernel(const WalkParams p) {
+    static_assert(!kStepSync || (kBlock && !kFast && !kWide), "step-synchronous walks: generic CTA variant only");
     constexpr int kIlp = !kWide ? 1 : (kBlock ? 4 : (KPL < 4 ? KPL : 4));
     const uint64_t keep = l2_policy_keep(), stream_pol = l2_policy_stream();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,6 +172,14 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
         const int64_t start = p.start_lo + row;
 
         // ---------------- phase 1: the walks -------------------------------
+        if constexpr (kStepSync) {
+            // the record of the current length doubles as the walker state: nodes[w] >= 0 = still walking
+            for (int w = tg; w < W; w += GS) {
+                nodes[w] = (int32_t)start;
+                loads[w] = 1.0;
+            }
+            my_visits += (unsigned long long)((W - tg + GS - 1) / GS);  // the length-0 visits (start, 1.0)
+        } else {
         // a walk that stops at length s leaves no visit at lengths > s: mark every slot empty first
         // (16-byte stores; per-walk tail loops cost 6 % of the kernel's instructions under ncu)
         {
@@ -282,6 +295,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 if (!any) break;
             }
         }
+        }  // !kStepSync
 
         int32_t *out_col = p.stage_ent ? nullptr : p.stage_col + row * p.stride;
         double *out_sum = p.stage_ent ? nullptr : p.stage_sum + row * p.stride;
@@ -310,6 +324,49 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
 
         // ---------------- phase 2: merge the visits of each length ----------
         for (int si = 0; si < L - 1; ++si) {
+            const int rec = kStepSync ? 0 : si * W;  // where the visit records of length si + 1 live
+            if constexpr (kStepSync) {
+                // one transition of every walk that is still alive (the generic path of phase 1, one walk at a time)
+                for (int w = tg; w < W; w += GS) {
+                    const int32_t cur = nodes[w];
+                    if (cur < 0) continue;
+                    const int32_t rs = __ldg(p.row_ptr + cur);
+                    const int32_t deg = __ldg(p.row_ptr + cur + 1) - rs;
+                    if (deg == 0) {  // dead end: stop without drawing (sparse_sampler.py:47)
+                        nodes[w] = -1;
+                        continue;
+                    }
+                    const unsigned long long walk_id = (unsigned long long)start * (unsigned long long)W + (unsigned)w;
+                    int32_t k;
+                    if (p.draw_mode == GRF_DRAW_REPLAY) {
+                        const long long ti = ((long long)walk_id - p.trace_base) * L + si;
+                        if (__ldg(p.trace_u + ti) < p.p_halt) {
+                            nodes[w] = -1;
+                            continue;
+                        }
+                        k = __ldg(p.trace_k + ti);
+                    } else {
+                        uint32_t x[4];
+                        philox4x32_10((uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)(si >> 1), 0u, p.k0,
+                                      p.k1, x);
+                        const uint32_t xh = (si & 1) ? x[2] : x[0], xk = (si & 1) ? x[3] : x[1];
+                        if ((unsigned long long)xh < p.halt_thr) {
+                            nodes[w] = -1;
+                            continue;
+                        }
+                        k = (int32_t)__umulhi(xk, (uint32_t)deg);
+                    }
+                    const int64_t e = (int64_t)rs + k;
+                    const double wv = __ldg(p.val + e);
+                    const double fac = p.load_mode == GRF_LOAD_ABLATION
+                                           ? wv
+                                           : __ddiv_rn(__dmul_rn((double)deg, wv), p.one_minus_p);
+                    nodes[w] = __ldg(p.col_idx + e);
+                    loads[w] = p.load_mode == GRF_LOAD_CUMULATIVE ? __dmul_rn(loads[w], fac) : fac;
+                    ++my_visits;
+                }
+                __syncthreads();
+            }
             if constexpr (!kBlock) {
                 // warp-per-node: sort in registers, park the sorted keys in shared memory
                 // for the run walks below
@@ -378,7 +435,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 for (int i = tg; i < Wp; i += GS) {
                     KeyT key = KEY_MAX;
                     if (i < W) {
-                        const int32_t nd = nodes[si * W + i];
+                        const int32_t nd = nodes[rec + i];
                         if (nd >= 0) key = ((KeyT)(uint32_t)nd << wbits) | (KeyT)i;
                     }
                     keys[i] = key;
@@ -420,7 +477,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                         for (int q = i; q < Wp; ++q) {
                             const KeyT kq = keys[q];
                             if ((kq >> wbits) != node) break;
-                            sum = __dadd_rn(sum, loads[si * W + (int)(kq & wmask)]);
+                            sum = __dadd_rn(sum, loads[rec + (int)(kq & wmask)]);
                         }
                         emit(off + rank, (int32_t)node, sum, si + 1);
                         if (p.col_counts) atomicAdd(p.col_counts + (int64_t)node * L + si + 1, 1);
@@ -441,9 +498,9 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
     }
 }
 
-template <bool kBlock, typename KeyT, int KPL, bool kFast = false, bool kWide = false>
+template <bool kBlock, typename KeyT, int KPL, bool kFast = false, bool kWide = false, bool kStepSync = false>
 static int launch_walk(const WalkParams &p, size_t smem, int threads, int grid, cudaStream_t stream) {
-    auto kern = walk_merge_kernel<kBlock, KeyT, KPL, kFast, kWide>;
+    auto kern = walk_merge_kernel<kBlock, KeyT, KPL, kFast, kWide, kStepSync>;
     GRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(p);
     return check_cuda(cudaGetLastError(), "walk_merge_kernel launch");
@@ -536,8 +593,11 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
     GRF_REQUIRE((uint64_t)p.W * (uint64_t)p.L < (1ull << 31), "grf_walk: W*L too large");
 
     cudaStream_t st = (cudaStream_t)stream;
-    if (warp_variant) {
-        const int warps = 4;
+    // start nodes per CTA of the warp-per-node variant: as many of 4, 2, 1 as the visit records leave room for
+    // (W = 200, L = 30: one group is 68 KB); none fits -> the CTA-per-node variants below
+    int warps = 4;
+    while (warps > 1 && warps * gb > kMaxSmem) warps >>= 1;
+    if (warp_variant && warps * gb <= kMaxSmem) {
         const int64_t want = (n_local + warps - 1) / warps;
         const int grid = (int)(want < (int64_t)kSmCount * 64 ? want : (int64_t)kSmCount * 64);
         const size_t smem = warps * gb;
@@ -565,14 +625,30 @@ extern "C" int grf_walk(const GrfGraph *graph, const GrfWalkCfg *cfg, int64_t st
         }
 #undef GRF_WALK_CASE
     }
-    if (gb > kMaxSmem)
-        return fail(GRF_ERR_UNSUPPORTED,
-                    "grf_walk: W=%d, L=%d needs %zu B of shared memory per start node (max %zu)", p.W, p.L, gb,
-                    kMaxSmem);
     const int64_t want = n_local;
     const int grid = (int)(want < (int64_t)kSmCount * 32 ? want : (int64_t)kSmCount * 32);
-    return key32 ? launch_walk<true, uint32_t, 0, false, true>(p, gb, 256, grid, st)
-                 : launch_walk<true, unsigned long long, 0, false, true>(p, gb, 256, grid, st);
+    // CTA per start node, shared-memory sort of Wp keys (the warp variant's layout does not apply)
+    const size_t cta_keys = (size_t)p.Wp * key_size;
+    const size_t gb_cta = ((size_t)p.loads_bytes + p.nodes_bytes + cta_keys + 15) & ~(size_t)15;
+    if (gb_cta <= kMaxSmem) {
+        p.sorted_bytes = 0;
+        p.group_bytes = (uint32_t)gb_cta;
+        return key32 ? launch_walk<true, uint32_t, 0, false, true>(p, gb_cta, 256, grid, st)
+                     : launch_walk<true, unsigned long long, 0, false, true>(p, gb_cta, 256, grid, st);
+    }
+    // all lengths do not fit: one length at a time (W x 12 bytes of records + the sort keys)
+    p.loads_bytes = (uint32_t)(((size_t)p.W * 8 + 15) & ~(size_t)15);
+    p.nodes_bytes = (uint32_t)(((size_t)p.W * 4 + 15) & ~(size_t)15);
+    p.sorted_bytes = 0;
+    const size_t gb_ss = ((size_t)p.loads_bytes + p.nodes_bytes + cta_keys + 15) & ~(size_t)15;
+    if (gb_ss > kMaxSmem)
+        return fail(GRF_ERR_UNSUPPORTED,
+                    "grf_walk: W=%d needs %zu B of shared memory per start node for one walk length (max %zu; "
+                    "%d-byte sort keys for %lld nodes)", p.W, gb_ss, kMaxSmem, (int)key_size,
+                    (long long)graph->n_nodes);
+    p.group_bytes = (uint32_t)gb_ss;
+    return key32 ? launch_walk<true, uint32_t, 0, false, false, true>(p, gb_ss, 256, grid, st)
+                 : launch_walk<true, unsigned long long, 0, false, false, true>(p, gb_ss, 256, grid, st);
 }
 
 namespace grf {

@@ -54,7 +54,7 @@ class SparseDiffusionKernel(Kernel):
         phi_x1 = phi if x1_idx is None else phi[x1_idx.long().flatten()]
         phi_x2 = phi if x2_idx is None else phi[x2_idx.long().flatten()]
         if diag:
-            return (phi_x1.to_dense() * phi_x2.to_dense()).sum(dim=-1)
+            return phi_x1.row_dots_with(phi_x2)
         return phi_x1 @ phi_x2.transpose(-1, -2)
 
     def _get_feature_matrix(self):

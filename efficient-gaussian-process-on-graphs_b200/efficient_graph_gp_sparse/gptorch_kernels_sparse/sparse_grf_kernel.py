@@ -53,8 +53,8 @@ class SparseGRFKernel(Kernel):
         else:
             phi_x2 = phi
         if diag:
-            # diag(A B^T) = sum(A * B, -1): one pass over the selected rows
-            return (phi_x1.to_dense() * phi_x2.to_dense()).sum(dim=-1)
+            # diag(A B^T) = sum(A * B, -1) as per-pair sparse dot products (the reference densifies both row sets)
+            return phi_x1.row_dots_with(phi_x2)
         return phi_x1 @ phi_x2.transpose(-1, -2)
 
     def _get_feature_matrix(self):

@@ -177,5 +177,29 @@ class GraphPreprocessor:
 
     @staticmethod
     def load_step_matrices(filename: str) -> List[sp.csr_matrix]:
+        """The reference's pickle (a plain list, graph_preprocessor.py:154-165) and the dict-keyed caches its
+        experiments write: ``{'step_matrices_torch': [scipy CSR, ...], ...}``
+        (experiments/sparse/scaling_exp/run_scaling_experiment.py:381-397 and
+        experiments/sparse/scalable_bo/bo_utils/data_utils.py:311-343; despite the key the values are scipy
+        matrices) or ``{'step_matrices': ...}`` for the dense method."""
         with open(filename, "rb") as f:
-            return pickle.load(f)
+            payload = pickle.load(f)
+        if isinstance(payload, dict):
+            for key in ("step_matrices_torch", "step_matrices", "step_matrices_scipy"):
+                if key in payload:
+                    payload = payload[key]
+                    break
+            else:
+                raise KeyError(f"{filename}: no step matrices in a cache with keys {sorted(payload)}")
+        return payload
+
+    @classmethod
+    def load_step_operators(cls, filename: str, device=None) -> "StepOperatorList":
+        """A cache file -> the operators ``SparseGRFKernel`` takes, on ``device``: what
+        ``load_step_matrices_from_file`` (run_scaling_experiment.py:550-562) and ``convert_to_device``
+        (data_utils.py:346-351) do with ``from_scipy_csr`` + ``SparseLinearOperator``."""
+        mats = cls.load_step_matrices(filename)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        ops = StepOperatorList(SparseLinearOperator(cls.from_scipy_csr(sp.csr_matrix(m)).to(device)) for m in mats)
+        return ops

@@ -21,14 +21,14 @@ LOAD_CUMULATIVE, LOAD_LAST_STEP, LOAD_ABLATION = 0, 1, 2
 SCALE_MUL_RECIP, SCALE_DIV = 0, 1
 ORDER_ROW_MAJOR, ORDER_STEP_MAJOR = 0, 1
 ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
-ABI_VERSION = 3        # GRF_B200_ABI_VERSION
+ABI_VERSION = 4        # GRF_B200_ABI_VERSION
 
 # every symbol include/grf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = (
     "grf_abi_version", "grf_last_error", "grf_walk_stage_stride", "grf_walk", "grf_scan_workspace_bytes",
     "grf_scan_counts", "grf_compact_steps", "grf_compact_blocks", "grf_blocks_from_steps", "grf_count_from_steps",
     "grf_row_census", "grf_nonempty_rows", "grf_transpose_workspace_bytes", "grf_transpose_offsets", "grf_transpose_fill",
-    "grf_phi_matvec", "grf_phi_fgrad", "grf_block_windows", "grf_edge_records", "grf_compact_entries", "grf_union_rank", "grf_union_fill",
+    "grf_phi_matvec", "grf_phi_fgrad", "grf_phi_row_dots", "grf_block_windows", "grf_edge_records", "grf_compact_entries", "grf_union_rank", "grf_union_fill",
     "grf_union_materialize", "grf_cg_num_partials", "grf_cg_dot", "grf_cg_update", "grf_cg_direction",
     "grf_laplacian_count", "grf_laplacian_fill", "grf_shard_reach", "grf_exchange_flag_bytes", "grf_exchange_sum",
 )
@@ -49,7 +49,8 @@ class GrfWalkCfg(Structure):
 
 class GrfLongRows(Structure):
     _fields_ = [("threshold", c_int32), ("n_long", c_int32), ("n_chunks", c_int32), ("rows", c_void_p),
-                ("chunk_ptr", c_void_p), ("chunk_bounds", c_void_p), ("partial", c_void_p), ("ld", c_int64)]
+                ("chunk_ptr", c_void_p), ("chunk_bounds", c_void_p), ("partial", c_void_p), ("ld", c_int64),
+                ("chunk_order", c_void_p)]
 
 
 class GrfPhi(Structure):
@@ -156,6 +157,8 @@ def lib():
     L.grf_block_windows.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.grf_phi_fgrad.restype = i32
     L.grf_phi_fgrad.argtypes = [POINTER(GrfPhi), vp, i64, vp, i64, vp, i64, i32, vp, vp]
+    L.grf_phi_row_dots.restype = i32
+    L.grf_phi_row_dots.argtypes = [POINTER(GrfPhi), vp, vp, vp, i64, vp, vp]
     if L.grf_abi_version() != ABI_VERSION:
         raise RuntimeError("grf_b200: ABI version mismatch between _lib.py and libgrf_b200.so")
     _lib = L

@@ -26,6 +26,7 @@ from . import _lib
 from ._lib import GrfGraph, GrfLongRows, GrfPhi, GrfWalkCfg, check
 
 LONG_ROW_THRESHOLD = 256   # rows of Phi / Phi^T with more entries are split into chunks of this size
+CHUNK_ORDER = os.environ.get("GRF_CHUNK_ORDER", "1") != "0"   # issue the chunks by the first row they gather
 _MAX_STAGE_BYTES = 16 << 30  # staging budget per walker launch; larger shards are walked in row chunks
 _LAZY_ENTRY_BYTES = 1 << 30  # up to this bound the Phi entries are allocated by capacity (no host wait for the count)
 # Rows per Phi^T block.  Transposing a shard in row blocks bounds the sort workspace (24 bytes per entry of a
@@ -111,6 +112,69 @@ class WalkConfig:
             raise ValueError("replay mode needs trace=(trace_u, trace_k)")
 
 
+def _to_host_pinned(t: torch.Tensor) -> torch.Tensor:
+    """Device tensor -> pinned host tensor (pageable destinations run at ~2 GB/s)."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host
+
+
+_UPLOAD_CHUNK = 32 << 20      # bytes per pinned staging slot
+_UPLOAD_THREADS = 4
+_UPLOAD_MIN = 64 << 20        # smaller arrays take torch's own pageable copy
+_upload_state = {}            # device index -> (executor, [(stream, [pinned slots], [events])] per thread)
+
+
+def _upload(arr: np.ndarray, dev: torch.device) -> torch.Tensor:
+    """A large pageable host array -> a device tensor, ordered on torch's current stream.
+
+    torch's pageable copy stages through one pinned buffer on one host thread (~10 GB/s: the 2 GB adjacency of a
+    70 M-edge graph took 0.2 s, five times the whole Phi build).  Here a few host threads fill pinned slots in
+    parallel (numpy copies release the GIL) and every slot goes out as its own asynchronous copy on the thread's
+    stream, so the host memcpy of one chunk overlaps the DMA of the others."""
+    arr = np.ascontiguousarray(arr)
+    if arr.nbytes < _UPLOAD_MIN or not arr.flags.c_contiguous:
+        return torch.from_numpy(arr).to(dev, non_blocking=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _upload_state:
+        with torch.cuda.device(dev):
+            lanes = [(torch.cuda.Stream(dev), [torch.empty(_UPLOAD_CHUNK, dtype=torch.uint8, pin_memory=True)
+                                               for _ in range(2)], [torch.cuda.Event(), torch.cuda.Event()])
+                     for _ in range(_UPLOAD_THREADS)]
+        _upload_state[key] = (ThreadPoolExecutor(_UPLOAD_THREADS, thread_name_prefix="grf-upload"), lanes)
+    pool, lanes = _upload_state[key]
+    out = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, device=dev)
+    src = arr.reshape(-1).view(np.uint8)
+    dst = out.reshape(-1).view(torch.uint8)
+    n = src.shape[0]
+    n_chunks = (n + _UPLOAD_CHUNK - 1) // _UPLOAD_CHUNK
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))      # `out` exists on the current stream from here on
+
+    def lane_work(t):
+        stream, slots, events = lanes[t]
+        with torch.cuda.device(dev):
+            stream.wait_event(ready)
+            for k, c in enumerate(range(t, n_chunks, _UPLOAD_THREADS)):
+                lo, hi = c * _UPLOAD_CHUNK, min(n, (c + 1) * _UPLOAD_CHUNK)
+                j = k & 1
+                events[j].synchronize()               # the copy that last used this slot has left it
+                np.copyto(slots[j].numpy()[: hi - lo], src[lo:hi])
+                with torch.cuda.stream(stream):
+                    dst[lo:hi].copy_(slots[j][: hi - lo], non_blocking=True)
+                    events[j].record(stream)
+
+    for fut in [pool.submit(lane_work, t) for t in range(_UPLOAD_THREADS)]:
+        fut.result()
+    cur = torch.cuda.current_stream(dev)
+    for stream, _, _ in lanes:
+        cur.wait_stream(stream)
+    return out
+
+
 class DeviceGraph:
     """The walk graph resident in HBM: CSR row_ptr/col_idx int32, val float64
     (what SparseRandomWalk.__init__ keeps, sparse_sampler.py:62-70)."""
@@ -127,11 +191,9 @@ class DeviceGraph:
         self.nnz = nnz
         self._scaled = {}
         self._shared = {}
-        self.row_ptr = torch.from_numpy(indptr.astype(np.int32, copy=False)).to(self.device, non_blocking=True)
-        self.col_idx = torch.from_numpy(np.ascontiguousarray(indices[:nnz]).astype(np.int32, copy=False)).to(
-            self.device, non_blocking=True)
-        self.val = torch.from_numpy(np.ascontiguousarray(data[:nnz]).astype(np.float64, copy=False)).to(
-            self.device, non_blocking=True)
+        self.row_ptr = _upload(indptr.astype(np.int32, copy=False), self.device)
+        self.col_idx = _upload(np.ascontiguousarray(indices[:nnz]).astype(np.int32, copy=False), self.device)
+        self.val = _upload(np.ascontiguousarray(data[:nnz]).astype(np.float64, copy=False), self.device)
 
     @classmethod
     def from_scipy(cls, adj, device=None) -> "DeviceGraph":
@@ -377,10 +439,20 @@ class StepMatrices:
 
     def to_dense_tensor(self) -> np.ndarray:
         """(n_rows, n_cols, L) float64 -- RandomWalk's output layout (sampler.py:196-201)."""
-        out = np.zeros((self.n_rows, self.n_cols, self.n_steps), dtype=float)
-        for s, m in enumerate(self.to_scipy()):
-            coo = m.tocoo()
-            out[coo.row, coo.col, s] = coo.data
+        return self.to_dense_device().cpu().numpy() if self.n_rows * self.n_cols * self.n_steps < (1 << 22) \
+            else _to_host_pinned(self.to_dense_device()).numpy()
+
+    def to_dense_device(self) -> torch.Tensor:
+        """The (n_rows, n_cols, L) float64 tensor assembled on the device: one scatter of the merged records
+        (every (row, column, length) occurs once), no host loop over scipy matrices."""
+        n, m, L, dev = self.n_rows, self.n_cols, self.n_steps, self.device
+        out = torch.zeros((n, m, L), dtype=torch.float64, device=dev)
+        if n and self.col.numel():
+            counts = self.offsets[1:] - self.offsets[:-1]                       # [L * n], step-major
+            seg = torch.repeat_interleave(torch.arange(L * n, device=dev), counts, output_size=self.col.numel())
+            step = torch.div(seg, n, rounding_mode="floor")
+            row = seg - step * n
+            out.view(-1)[(row * m + self.col.long()) * L + step] = self.val
         return out
 
     @staticmethod
@@ -720,8 +792,10 @@ class PhiBlocks:
                                           _stream(dev)))
         return into
 
-    def _long_rows_of(self, ptr: torch.Tensor, n: int):
-        """Chunk table for the rows of one side that are longer than LONG_ROW_THRESHOLD (or None)."""
+    def _long_rows_of(self, ptr: torch.Tensor, n: int, ent: Optional[torch.Tensor] = None):
+        """Chunk table for the rows of one side that are longer than LONG_ROW_THRESHOLD (or None).  With the
+        side's entries the chunks also get an issue order: by the first X row they gather (segments are sorted,
+        so a chunk reads an ascending run of rows) -- the chunks in flight then share a window of X in L2."""
         if n == 0 or self.nnz == 0:
             return None
         L, T = self.n_steps, LONG_ROW_THRESHOLD
@@ -740,8 +814,12 @@ class PhiBlocks:
         cb = row_b[rows][owner] + local * T
         ce = torch.minimum(cb + T, row_e[rows][owner])
         bounds = torch.stack([cb, ce], dim=1).to(torch.int32).contiguous()
+        order = None
+        if ent is not None and CHUNK_ORDER and n_chunks > 1:
+            first = ent[:, 0][cb] & ((1 << 27) - 1)
+            order = torch.argsort(first, stable=True).to(torch.int32).contiguous()
         return dict(rows=rows.to(torch.int32).contiguous(), chunk_ptr=chunk_ptr.to(torch.int32).contiguous(),
-                    bounds=bounds, n_long=int(rows.numel()), n_chunks=n_chunks)
+                    bounds=bounds, n_long=int(rows.numel()), n_chunks=n_chunks, order=order)
 
     def build_long_rows(self) -> "PhiBlocks":
         """One-off matvec preparation: which rows / columns need the long-row split, and the list of
@@ -764,7 +842,7 @@ class PhiBlocks:
                 tb.census = (host.clone(), done, None)      # the values stay; the pinned buffer goes back to the pool
                 _recycle_pinned(base)
                 any_long_fwd = any_long_fwd or bool(long_f)
-                tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols) if long_t else None
+                tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols, tb.tentries) if long_t else None
                 if len(self.tblocks) == 1:
                     # columns this (row) shard touches: worth a list when most of the N columns are empty
                     if cols_used < 0.75 * self.n_cols:
@@ -775,7 +853,7 @@ class PhiBlocks:
                         tb.touched = None
                     tb.tcols_cap = None
             if any_long_fwd:
-                self._long_fwd = self._long_rows_of(self.blk_ptr, self.n_rows)
+                self._long_fwd = self._long_rows_of(self.blk_ptr, self.n_rows, self.entries)
         return self
 
     def _long_struct(self, side: Optional[dict], cache: dict, ld: int):
@@ -786,7 +864,8 @@ class PhiBlocks:
             partial = torch.empty((side["n_chunks"], ld), dtype=torch.float32, device=self.device)
             cache.clear()
             cache[ld] = (GrfLongRows(LONG_ROW_THRESHOLD, side["n_long"], side["n_chunks"], side["rows"].data_ptr(),
-                                     side["chunk_ptr"].data_ptr(), side["bounds"].data_ptr(), partial.data_ptr(), ld),
+                                     side["chunk_ptr"].data_ptr(), side["bounds"].data_ptr(), partial.data_ptr(), ld,
+                                     side["order"].data_ptr() if side.get("order") is not None else None),
                          partial)
         return cache[ld][0]
 
@@ -852,6 +931,43 @@ class PhiBlocks:
             return None
         x = torch.as_tensor(x, device=dev)
         return x.flatten().to(torch.int32).contiguous()
+
+    @property
+    def is_shard(self) -> bool:
+        """True when these blocks hold the rows of a slice of the start nodes (ids outside it belong to a peer)."""
+        return self.row_lo != 0 or self.n_rows != self.n_cols
+
+    def check_ids(self, x) -> None:
+        """Raise IndexError for row ids outside Phi, as ``phi[idx]`` does in the reference
+        (sparse_grf_kernel.py:32-41).  The kernels themselves skip ids outside the local rows -- that is what a
+        row shard needs -- so on the whole Phi an out-of-range id would otherwise come back as a zero row.  One
+        min/max (a device sync): called where an operator or a plan is built, not per product."""
+        if x is None:
+            return
+        x = torch.as_tensor(x, device=self.device).flatten()
+        if x.numel() == 0:
+            return
+        lo, hi = (int(v) for v in torch.aminmax(x))
+        n = self.n_cols if self.is_shard else self.n_rows
+        if lo < 0 or hi >= n:
+            raise IndexError(f"row index {lo if lo < 0 else hi} is out of bounds for Phi with {n} rows")
+
+    def row_dots(self, f, x1=None, x2=None) -> torch.Tensor:
+        """dots[i, l] = <M_l[x1[i], :], Phi_f[x2[i], :]> (float32 [n, L]); ``dots @ f`` is diag(K[x1, x2]).
+        No densification: a warp per pair (``grf_phi_row_dots``)."""
+        dev = self.device
+        f = self._f(f)
+        a, b = self._ids(x1, dev), self._ids(x2, dev)
+        if (a is None) != (b is None):      # one side indexed: the other is the identity list
+            ident = torch.arange(self.row_lo, self.row_lo + self.n_rows, dtype=torch.int32, device=dev)
+            a, b = (ident if a is None else a), (ident if b is None else b)
+        n = self.n_rows if a is None else a.numel()
+        if a is not None and b.numel() != n:
+            raise ValueError("row_dots: x1 and x2 must have the same length")
+        dots = torch.zeros((n, self.n_steps), dtype=torch.float32, device=dev)
+        phi = self.c_struct()
+        check(_lib.lib().grf_phi_row_dots(ctypes.byref(phi), _ptr(f), _ptr(a), _ptr(b), n, _ptr(dots), _stream(dev)))
+        return dots
 
     def _f(self, f) -> torch.Tensor:
         f = torch.as_tensor(f, device=self.device).detach().to(torch.float32).contiguous()
@@ -1141,6 +1257,28 @@ def phi_blocks_from_scipy(mats, device=None, row_lo: int = 0, transpose: bool = 
     return PhiBlocks.from_step_matrices(sm, transpose=transpose)
 
 
+def _canonical_csr(t: torch.Tensor) -> torch.Tensor:
+    """``t`` with strictly increasing column indices in every row.  The union pattern, the Phi^T segments and the
+    binary searches assume that; torch accepts CSR tensors with unsorted or repeated columns (its SpMM adds
+    repeats), so such a tensor is coalesced -- sorted, repeats summed -- instead of multiplying wrongly.  One
+    comparison pass + one sync per tensor, once per Phi."""
+    col, crow = t.col_indices(), t.crow_indices()
+    if col.numel() < 2:
+        return t
+    bad = col[1:] <= col[:-1]
+    starts = crow[1:-1]                      # first entry of rows 1 .. n-1: no order across a row boundary
+    starts = starts[(starts > 0) & (starts < col.numel())]
+    bad[starts - 1] = False
+    if not bool(bad.any()):
+        return t
+    # (t.to_sparse_coo() would mark the result as already coalesced: rebuild the triplets by hand)
+    n_rows = t.shape[0]
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=col.device), crow[1:] - crow[:-1],
+                                   output_size=col.numel())
+    coo = torch.sparse_coo_tensor(torch.stack([rows, col.long()]), t.values(), tuple(t.shape)).coalesce()
+    return coo.to_sparse_csr()
+
+
 def phi_blocks_from_torch_csr(tensors, row_lo: int = 0, transpose: bool = True) -> PhiBlocks:
     """Phi blocks from one torch sparse-CSR tensor or a list of them (one per
     walk length) already on the GPU -- the layout ``from_scipy_csr`` produces
@@ -1153,6 +1291,7 @@ def phi_blocks_from_torch_csr(tensors, row_lo: int = 0, transpose: bool = True) 
     for t in tensors:
         if not t.is_sparse_csr:
             raise ValueError("Input tensor must be a sparse CSR tensor")
+        t = _canonical_csr(t)
         crow = t.crow_indices().to(torch.int64)
         offs.append(crow[:-1] + base)
         base += int(t.values().numel())
@@ -1196,6 +1335,8 @@ class MatvecPlan:
         self.phi.dynamic_rows = phi.dynamic_rows
         self.phi.build_windows()
         self.phi.build_long_rows()
+        phi.check_ids(x1)
+        phi.check_ids(x2)
         self.x1, self.x2 = phi._ids(x1, dev), phi._ids(x2, dev)
         self.n1 = phi.n_rows if self.x1 is None else self.x1.numel()
         self.n2 = phi.n_rows if self.x2 is None else self.x2.numel()

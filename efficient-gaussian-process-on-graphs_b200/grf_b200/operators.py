@@ -104,6 +104,7 @@ class GRFFeatureOperator(LinearOperator):
             index = torch.arange(self._n_sel(), device=self.device)[index]
         index = torch.as_tensor(index, device=self.device).long().flatten()
         rows = index if self.rows is None else self.rows.long()[index]
+        self.blocks.check_ids(rows)      # IndexError as ``phi[idx]`` in the reference, not a silent zero row
         return GRFFeatureOperator(self.blocks, self.modulator, rows.to(torch.int32), False, self.group)
 
     def __getitem__(self, index):
@@ -125,8 +126,51 @@ class GRFFeatureOperator(LinearOperator):
     __matmul__ = matmul
 
     def to_dense(self):
+        """Dense Phi[rows] (or its transpose): identity columns in chunks through the product, for tests and
+        small row sets only -- nothing on the kernel path densifies."""
         n = self.shape[-1]
-        return self._matmul(torch.eye(n, dtype=torch.float32, device=self.device))
+        return _dense_by_column_chunks(self._matmul, n, self.device)
+
+    def row_dots_with(self, other: "GRFFeatureOperator") -> torch.Tensor:
+        """sum(self * other, -1) for two row selections of the same Phi (the reference's diag=True branch,
+        sparse_grf_kernel.py:55-57) without densifying either: per-pair sparse dot products on the device,
+        differentiable w.r.t. the modulator."""
+        if self.transposed or other.transposed or other.blocks is not self.blocks:
+            raise ValueError("row_dots_with: both operands must be row selections of the same Phi")
+        d = PhiRowDots.apply(self.modulator, self.blocks, self.rows, other.rows)
+        if self.group is not None:
+            d = _reduce_partial(d.contiguous(), self.group)
+        return d
+
+
+def _dense_by_column_chunks(matmul, n: int, device, chunk: int = 1024) -> torch.Tensor:
+    cols = []
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        eye = torch.zeros((n, c1 - c0), dtype=torch.float32, device=device)
+        eye[c0:c1] = torch.eye(c1 - c0, dtype=torch.float32, device=device)
+        cols.append(matmul(eye))
+    return torch.cat(cols, dim=1) if cols else matmul(torch.zeros((n, 0), dtype=torch.float32, device=device))
+
+
+class PhiRowDots(torch.autograd.Function):
+    """d[i] = <Phi_f[x1[i]], Phi_f[x2[i]]> = sum_l f[l] * D12[i, l], D12[i, l] = <M_l[x1[i]], Phi_f[x2[i]]>.
+    dd[i]/df[l] = D12[i, l] + D21[i, l] (``grf_phi_row_dots`` with the roles swapped)."""
+
+    @staticmethod
+    def forward(ctx, f, blocks: PhiBlocks, x1, x2):
+        fd = f.detach()
+        d12 = blocks.row_dots(fd, x1, x2)
+        ctx.blocks, ctx.x1, ctx.x2 = blocks, x1, x2
+        ctx.same = x1 is x2
+        ctx.save_for_backward(fd, d12)
+        return d12 @ fd.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        fd, d12 = ctx.saved_tensors
+        d21 = d12 if ctx.same else ctx.blocks.row_dots(fd, ctx.x2, ctx.x1)
+        return (g.to(torch.float32) @ (d12 + d21)).to(fd.dtype), None, None, None
 
 
 class GRFKernelOperator(LinearOperator):
@@ -180,12 +224,20 @@ class GRFKernelOperator(LinearOperator):
         return (_reduce_partial(grad, self.group),)
 
     def diagonal(self, offset=0, dim1=-2, dim2=-1):
-        """diag(K[x, x]) = row-wise squared norms of Phi[x] (requires x1 is x2)."""
+        """diag(K[x1, x2])[i] = <Phi[x1[i]], Phi[x2[i]]>: per-pair sparse dot products, nothing densified."""
         if offset != 0:
             return self.to_dense().diagonal(offset)
-        return self.to_dense().diagonal()
+        n = min(self._size())
+        x1 = None if self.x1 is None and self.x2 is None else (
+            torch.arange(n, device=self.device, dtype=torch.int32) + self.blocks.row_lo if self.x1 is None
+            else self.x1[:n])
+        x2 = x1 if self.x2 is self.x1 else (
+            None if x1 is None else (torch.arange(n, device=self.device, dtype=torch.int32) + self.blocks.row_lo
+                                     if self.x2 is None else self.x2[:n]))
+        d = PhiRowDots.apply(self.modulator, self.blocks, x1, x2)
+        return _reduce_partial(d.contiguous(), self.group) if self.group is not None else d
 
     def to_dense(self):
-        n2 = self._size()[1]
-        return self._matmul(torch.eye(n2, dtype=torch.float32, device=self.device))
+        """Dense K[x1, x2] through identity columns in chunks (tests / small index sets)."""
+        return _dense_by_column_chunks(self._matmul, self._size()[1], self.device)
 

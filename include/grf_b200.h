@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GRF_B200_ABI_VERSION 3
+#define GRF_B200_ABI_VERSION 4
 
 enum {
     GRF_OK = 0,
@@ -129,6 +129,11 @@ typedef struct {
     const int32_t *chunk_bounds; /* [n_chunks][2] entry range {begin, end} of each chunk (device) */
     float *partial;              /* [n_chunks][ld] workspace (device) */
     int64_t ld;                  /* >= t */
+    /* optional (NULL = ascending chunk id): the order in which the chunks are handed to the warps, a
+     * permutation of 0 .. n_chunks-1 (device).  Chunks of hub columns of Phi^T are issued by the first
+     * local row they gather, so that the chunks in flight at any moment read one sliding window of V that
+     * stays in L2 (V itself is larger than L2 at 4 M nodes); results do not depend on the order */
+    const int32_t *chunk_order;
 } GrfLongRows;
 
 typedef struct {
@@ -319,6 +324,14 @@ int grf_union_materialize(const int32_t *blk_ptr, const int32_t *uptr, const int
  * P = Phi[x1]^T left) for the full derivative.  grad: float[L], accumulated. */
 int grf_phi_fgrad(const GrfPhi *phi, const int32_t *x, int64_t n, const float *left, int64_t ldl, const float *p,
                   int64_t ldp, int32_t t, float *grad, void *stream);
+
+/* Replaces the diag=True branch of sparse_grf_kernel.py:55-57 (which multiplies two densified row sets):
+ *   dots[i][l] = sum over the length-l entries e of Phi row x1[i] of  e.val * Phi_f[x2[i], col(e)],
+ * Phi_f = sum_l f[l] M_l, so that diag(K[x1, x2])[i] = sum_l f[l] * dots[i][l]; the columns of dots are what
+ * the modulator gradient of that diagonal needs.  x1 / x2: global row ids (NULL = row i of this shard; then
+ * n = n_rows); pairs with a row outside this shard are written as zeros.  dots: float [n][L]. */
+int grf_phi_row_dots(const GrfPhi *phi, const float *f, const int32_t *x1, const int32_t *x2, int64_t n,
+                     float *dots, void *stream);
 
 /* The one exchange of the path (no reference counterpart: its matvec runs on one device):
  * U <- sum over the GPUs of the partials U_g = Phi_g[x2]^T V_g between the two halves of a product, as one

@@ -78,6 +78,16 @@ if args.merged and len(phi.tblocks) == 1:
         mplan(v, out)
     _, ms = timed(lambda: mplan(v, out), 5)
     print(f"matvec t={t} merged Phi_f: {ms:.3f} ms -> {nb / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    _, ms1 = timed(lambda: mplan._call(v, None, 1), 5)
+    _, ms2 = timed(lambda: mplan._call(None, out, 2), 5)
+    print(f"   merged halves: Phi^T V {ms1:.3f} ms, Phi U {ms2:.3f} ms", flush=True)
+    if args.stats:
+        for name, e in (("Phi_f", mplan.phi.entries), ("Phi_f^T", mplan.phi.tentries)):
+            c = e[:, 0] & ((1 << 27) - 1)
+            pair = ((c[1:] == c[:-1] + 1) & ((c[:-1] & 1) == 0)).sum().item()
+            near = ((c[1:] >> 1) == (c[:-1] >> 1)).sum().item()
+            print(f"   merged {name}: {pair / c.numel():.3f} of the entries are followed by their line partner "
+                  f"(col ^ 1); same 128-B line as the predecessor: {near / c.numel():.3f}", flush=True)
 if args.stats:
     ent = phi.entries
     cols = (ent[:, 0] & ((1 << 27) - 1)).to(torch.int64)

@@ -179,8 +179,20 @@ def main():
         ("gnm50_weighted_lap_W40_p2", lap_sparse(_random_graph(50, 120, 21, weighted=True)), 40, 0.1, 4, 7, 2),
         ("grid6x6_lap_W130_p4", lap_sparse(_grid(6, 6)), 130, 0.15, 3, 13, 4),
         ("gnm30_weighted_lap_W300_p2", lap_sparse(_random_graph(30, 70, 5, weighted=True)), 300, 0.1, 4, 1, 2),
+        # W x L beyond one CTA's shared memory (the reference's wind experiment: W = 8192, L = 5; its ablation
+        # notebook: W = 10000, L = 10): the walker's fallbacks -- fewer start nodes per CTA (W = 200, L = 30: two
+        # warps; W = 250, L = 40: one), one walk length at a time (W = 2100, L = 10; W = 256, L = 80; W = 8192, L = 5)
+        ("gnm16_weighted_lap_W200_L30_p2", lap_sparse(_random_graph(16, 40, 31, weighted=True)), 200, 0.05, 30, 3, 2),
+        ("ring12_lap_W250_L40_p1", lap_sparse(sp.csr_matrix(np.roll(np.eye(12), 1, 1) + np.roll(np.eye(12), -1, 1))),
+         250, 0.04, 40, 8, 1),
+        ("gnm12_weighted_lap_W2100_L10_p2", lap_sparse(_random_graph(12, 30, 32, weighted=True)), 2100, 0.1, 10, 4, 2),
+        ("grid3x3_lap_W256_L80_p1", lap_sparse(_grid(3, 3)), 256, 0.03, 80, 6, 1),
+        ("gnm6_weighted_lap_W8192_L5_p2", lap_sparse(_random_graph(6, 12, 33, weighted=True)), 8192, 0.1, 5, 9, 2),
     ]
+    only = os.environ.get("GOLDEN_ONLY")     # regenerate just the sparse cases whose name contains this
     for name, graph, W, p, L, seed, nproc in sparse_cases:
+        if only and only not in name:
+            continue
         graph = graph.tocsr()
         pooled = ss.SparseRandomWalk(graph, seed=seed).get_random_walk_matrices(W, p, L, n_processes=nproc)
         logs, results = _record_sparse(ss, graph, W, p, L, seed, nproc)
@@ -206,6 +218,9 @@ def main():
                                                         dtype=np.uint8)
         np.savez_compressed(os.path.join(HERE, f"sparse_{name}.npz"), **out)
         print("sparse", name, [m.nnz for m in pooled])
+
+    if only:
+        return
 
     # ---------------- row slices of huge graphs (64-bit sort keys; slice-local traces) -----
     # One reference worker (sparse_sampler.py:26-56) run in-process on a contiguous chunk of start nodes

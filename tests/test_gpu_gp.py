@@ -274,3 +274,134 @@ def test_device_cg_matches_oracle_cg_semantics(setup):
     got = linear_cg(lambda v: at @ v, torch.tensor(b, dtype=torch.float32).cuda(), tolerance=1e-7, check_every=1, eps=1e-30)
     assert np.allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
     assert np.allclose(want, np.linalg.solve(a, b), rtol=1e-6, atol=1e-8)
+
+
+def test_diag_is_per_pair_sparse_dots_with_modulator_gradient(setup):
+    """diag=True (sparse_grf_kernel.py:55-57) through grf_phi_row_dots: values and d/df against a float64
+    dense evaluation, for x1 == x2, for two different index lists and for the un-indexed kernel."""
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.gptorch_kernels_sparse import SparseGRFKernel
+
+    torch.manual_seed(3)
+    kern = SparseGRFKernel(4, setup["ops"]).cuda()
+    f = kern.modulator_vector.detach().cpu().numpy().astype(np.float64)
+    mats = [m.astype(np.float32).astype(np.float64).toarray() for m in setup["pp"].step_matrices_scipy]
+    phi = sum(fl * m for fl, m in zip(f, mats))
+    rng = np.random.default_rng(5)
+    i1, i2 = rng.permutation(400)[:120], rng.permutation(400)[:120]
+    for a, b in ((i1, i1), (i1, i2)):
+        kern.raw_modulator_vector.grad = None
+        d = kern.forward(torch.tensor(a).cuda(), torch.tensor(b).cuda(), diag=True)
+        want = np.sum(phi[a] * phi[b], axis=1)
+        assert tuple(d.shape) == (120,)
+        assert np.allclose(d.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+        g = torch.tensor(rng.standard_normal(120).astype(np.float32)).cuda()
+        (d * g).sum().backward()
+        gw = g.cpu().numpy().astype(np.float64)
+        want_grad = [np.sum(gw * (np.sum(mats[l][a] * phi[b], axis=1) + np.sum(phi[a] * mats[l][b], axis=1)))
+                     for l in range(4)]
+        got_grad = kern.raw_modulator_vector.grad.cpu().numpy()
+        assert np.allclose(got_grad, want_grad, rtol=1e-4, atol=1e-4 * np.abs(want_grad).max())
+    full = kern.forward(diag=True).detach().cpu().numpy()
+    assert np.allclose(full, np.sum(phi * phi, axis=1), rtol=1e-5, atol=1e-5)
+    K = kern(torch.tensor(i1).cuda(), torch.tensor(i2).cuda())
+    assert np.allclose(K.diagonal().detach().cpu().numpy(), np.sum(phi[i1] * phi[i2], axis=1), rtol=1e-5, atol=1e-5)
+
+
+def test_diag_on_a_graph_whose_dense_rows_would_not_fit():
+    """N = 2^20 ring, 4096 prediction nodes: the densified row sets of the reference's diag branch would be
+    2 x 16 GiB; the per-pair kernel needs n x L floats."""
+    import torch
+    from grf_b200 import engine
+    from grf_b200.operators import GRFFeatureOperator
+
+    n = 1 << 20
+    idx = np.arange(n)
+    adj = sp.csr_matrix((np.ones(2 * n), (np.r_[idx, idx], np.r_[(idx + 1) % n, (idx - 1) % n])), shape=(n, n))
+    g = engine.DeviceGraph.laplacian_of(adj, torch.device("cuda", 0))
+    phi = engine.build_phi_blocks(g, engine.WalkConfig(20, 0.1, 4, seed=1), transpose=False)
+    f = torch.tensor([1.0, 0.5, -0.25, 0.125], device="cuda")
+    rows = torch.arange(0, n, n // 4096, device="cuda")[:4096]
+    op = GRFFeatureOperator(phi, f)[rows]
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    d = op.row_dots_with(op)
+    assert torch.cuda.max_memory_allocated() - base < (64 << 20)
+    # against the product route on a few rows: ||Phi_f[r]||^2 = (Phi_f Phi_f^T e_r)[r]
+    few = rows[:8]
+    e = torch.zeros(n, 8, device="cuda")
+    e[few, torch.arange(8, device="cuda")] = 1.0
+    k = phi.apply(f, phi.apply_t(f, e), rows=few)
+    assert torch.allclose(d[:8], k.diagonal(), rtol=1e-5, atol=1e-6)
+
+
+def test_bilinear_derivative_is_the_per_length_reduction(setup):
+    """Upstream protocol method GRFKernelOperator._bilinear_derivative (what gpytorch's inv_quad_logdet backward
+    calls for sparse_grf_kernel.py:51-62): d/df sum(left * (K right)) against float64, and against autograd
+    through the same operator."""
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.gptorch_kernels_sparse import SparseGRFKernel
+    from oracle import grf_oracle as orc
+
+    torch.manual_seed(9)
+    kern = SparseGRFKernel(4, setup["ops"]).cuda()
+    rng = np.random.default_rng(2)
+    i1, i2 = rng.permutation(400)[:130], rng.permutation(400)[:70]
+    K = kern(torch.tensor(i1).cuda(), torch.tensor(i2).cuda())
+    left = torch.tensor(rng.standard_normal((130, 6)).astype(np.float32)).cuda()
+    right = torch.tensor(rng.standard_normal((70, 6)).astype(np.float32)).cuda()
+    (got,) = K._bilinear_derivative(left, right)
+    f = kern.modulator_vector.detach().cpu().numpy()
+    want = orc.phi_fgrad_f64([m.astype(np.float32) for m in setup["pp"].step_matrices_scipy], f,
+                             left.cpu().numpy(), right.cpu().numpy(), x1=i1, x2=i2)
+    assert np.allclose(got.cpu().numpy(), want, rtol=2e-4, atol=2e-4 * np.abs(want).max())
+    (left * (K @ right)).sum().backward()
+    auto = kern.raw_modulator_vector.grad.cpu().numpy()
+    assert np.allclose(got.cpu().numpy(), auto, rtol=1e-4, atol=1e-4 * np.abs(auto).max())
+    (got1,) = K._bilinear_derivative(left[:, 0], right[:, 0])          # vectors, as upstream may pass them
+    want1 = orc.phi_fgrad_f64([m.astype(np.float32) for m in setup["pp"].step_matrices_scipy], f,
+                              left[:, :1].cpu().numpy(), right[:, :1].cpu().numpy(), x1=i1, x2=i2)
+    assert np.allclose(got1.cpu().numpy(), want1, rtol=2e-4, atol=2e-4 * np.abs(want1).max())
+
+
+def test_out_of_range_row_ids_raise_like_the_reference(setup):
+    """phi[idx] raises IndexError in the reference (sparse_grf_kernel.py:32-41); the kernels would return a zero
+    row for an id outside the local rows (right for a shard, wrong on the whole Phi)."""
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.gptorch_kernels_sparse import SparseGRFKernel
+
+    kern = SparseGRFKernel(4, setup["ops"]).cuda()
+    ok = torch.tensor([0, 399]).cuda()
+    kern(ok, ok)
+    for bad in ([0, 400], [-1, 3], [5, 2 ** 31 + 7]):
+        with pytest.raises(IndexError):
+            kern(torch.tensor(bad).cuda(), ok)
+        with pytest.raises(IndexError):
+            setup["ops"].phi_blocks.plan(kern.modulator_vector.detach(), 4, x1=torch.tensor(bad).cuda())
+
+
+def test_dict_keyed_experiment_caches_load_as_operators(setup, tmp_path):
+    """The experiments pickle {'step_matrices_torch': [scipy CSR, ...], ...}
+    (run_scaling_experiment.py:381-397, data_utils.py:334-343) and rebuild operators from it
+    (run_scaling_experiment.py:550-562): same thing here, and the kernel built on them equals the one built on
+    the preprocessor's own operators."""
+    import pickle
+
+    torch = setup["torch"]
+    from efficient_graph_gp_sparse.gptorch_kernels_sparse import SparseGRFKernel
+    from efficient_graph_gp_sparse.preprocessor import GraphPreprocessor
+
+    mats = setup["pp"].step_matrices_scipy
+    path = str(tmp_path / "step_matrices_sparse_n400_seed7.pkl")
+    with open(path, "wb") as fh:
+        pickle.dump({"step_matrices_torch": mats, "n_nodes": 400, "seed": 7, "method": "sparse", "config": {}}, fh)
+    ops = GraphPreprocessor.load_step_operators(path, torch.device("cuda", 0))
+    assert len(ops) == 4 and ops[0].sparse_csr_tensor.is_cuda
+    again = GraphPreprocessor(setup["adj"], 30, 0.1, 4, 7, load_from_disk=True, cache_filename=path)
+    assert all(csr_bits_equal(a, b) for a, b in zip(again.step_matrices_scipy, mats))
+    k_new, k_old = SparseGRFKernel(4, ops).cuda(), SparseGRFKernel(4, setup["ops"]).cuda()
+    with torch.no_grad():
+        k_new.raw_modulator_vector.copy_(k_old.raw_modulator_vector)
+    x = torch.arange(0, 400, 7).cuda()
+    v = torch.randn(x.numel(), 3, device="cuda")
+    assert torch.allclose(k_new(x, x) @ v, k_old(x, x) @ v, rtol=1e-5, atol=1e-6)

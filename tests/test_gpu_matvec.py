@@ -599,3 +599,28 @@ def test_streaming_gathers_are_bit_identical(env, case):
             assert torch.equal(plan(v), want), (t, mode)
     plan = phi.plan(f, 16, merged=False)
     assert plan._tune_gathers() in ((False, False), (False, True), (True, False), (True, True))
+
+
+def test_torch_csr_with_unsorted_or_repeated_columns_is_coalesced():
+    """torch accepts CSR tensors whose rows are unsorted or repeat a column (its SpMM adds the repeats); the Phi
+    blocks built from one must multiply like torch does, merged layout included."""
+    import torch
+    from grf_b200 import engine
+
+    crow = torch.tensor([0, 3, 3, 6, 8])
+    col = torch.tensor([2, 0, 2, 3, 1, 0, 1, 1])          # row 0: unsorted + repeated 2; row 3: repeated 1
+    val = torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0])
+    m1 = torch.sparse_csr_tensor(crow, col, val, (4, 4), dtype=torch.float32).cuda()
+    m0 = torch.eye(4).to_sparse_csr().cuda()
+    dense = [m0.to_dense().double(), torch.zeros(4, 4, dtype=torch.float64).cuda()]
+    for r in range(4):
+        for k in range(int(crow[r]), int(crow[r + 1])):
+            dense[1][r, int(col[k])] += float(val[k])
+    phi = engine.phi_blocks_from_torch_csr([m0, m1])
+    f = torch.tensor([0.5, -1.5]).cuda()
+    pf = f[0].double() * dense[0] + f[1].double() * dense[1]
+    v = torch.randn(4, 3).cuda()
+    want = (pf @ (pf.T @ v.double())).float()
+    for merged in (False, True):
+        got = phi.plan(f, 3, merged=merged)(v)
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), merged

@@ -303,6 +303,25 @@ def test_native_bit_exact_block_per_node_variant(env, W, L):
     _native_case(env, lap, W, 0.1, L, seed=5)
 
 
+@pytest.mark.parametrize("W,L", [(200, 30), (250, 40), (256, 80), (2100, 10), (8192, 5), (10000, 10)])
+def test_native_bit_exact_when_all_lengths_do_not_fit_shared_memory(env, W, L):
+    """W x L beyond 227 KB of visit records: two / one start node per CTA of the warp variant, then the
+    one-length-at-a-time CTA variant (the reference's wind experiment runs W = 8192, L = 5, its ablation notebook
+    W = 10000, L = 10)."""
+    lap = env["o"].normalized_laplacian_sparse(random_graph(24, 60, 13, weighted=True))
+    _native_case(env, lap, W, 0.05, L, seed=5)
+
+
+def test_walk_count_beyond_one_lengths_worth_of_shared_memory_is_refused_with_a_message(env):
+    """W = 16384 with 64-bit sort keys (node bits + 14 > 31) needs 320 KB for a single length."""
+    from grf_b200 import engine
+
+    n = 1 << 20
+    g = engine.DeviceGraph.from_scipy(ring_graph(n))
+    with pytest.raises(Exception, match="shared memory"):
+        engine.build_step_matrices(g, engine.WalkConfig(16384, 0.1, 3, seed=1), start_lo=0, start_hi=2)
+
+
 def test_native_bit_exact_wide_keys(env):
     """node bits + walk bits > 31 -> 64-bit sort keys; only a slice of start nodes is walked."""
     n = 9_000_000

@@ -147,3 +147,25 @@ def test_walk_config_validation_and_row_chunks():
     assert len(chunks) > 1 and sum(hi - lo for lo, hi in chunks) == 4_194_304
     assert all((hi - lo) * stride * 12 <= 6 << 30 for lo, hi in chunks)
     assert list(engine._row_chunks(7, 7, stride, 6 << 30)) == [(7, 7)]       # empty shard: one empty chunk
+
+
+def test_step_matrix_caches_plain_list_and_dict_keyed(tmp_path):
+    """graph_preprocessor.py:142-165 pickles a plain list; the experiments wrap it in a dict
+    (run_scaling_experiment.py:381-397 'step_matrices_torch' / 'step_matrices', data_utils.py:334-343)."""
+    import pickle
+
+    import scipy.sparse as sp
+    from efficient_graph_gp_sparse.preprocessor import GraphPreprocessor
+
+    mats = [sp.identity(5, format="csr"), sp.random(5, 5, 0.4, format="csr", random_state=1)]
+    for name, payload in (("list.pkl", mats), ("bo.pkl", {"step_matrices_torch": mats, "metadata": {"n_nodes": 5}}),
+                          ("dense.pkl", {"step_matrices": mats, "method": "dense"})):
+        path = str(tmp_path / name)
+        with open(path, "wb") as fh:
+            pickle.dump(payload, fh)
+        got = GraphPreprocessor.load_step_matrices(path)
+        assert len(got) == 2 and all((a != b).nnz == 0 for a, b in zip(got, mats))
+    with open(str(tmp_path / "other.pkl"), "wb") as fh:
+        pickle.dump({"something": 1}, fh)
+    with pytest.raises(KeyError):
+        GraphPreprocessor.load_step_matrices(str(tmp_path / "other.pkl"))
