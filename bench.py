@@ -342,21 +342,31 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # kernels of libgrf_b200.so per step, COUNTED: one more (untimed) step under torch's CUPTI profiler
+    # (every rank runs the step -- the exchange inside it is a collective -- rank 0 alone records it)
     measured_launches = None
+    prof = None
     if rank == 0:
         try:
             from torch.profiler import ProfilerActivity, profile
 
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                r = one_step()
-                torch.cuda.synchronize(dev)
-            del r
+            prof = profile(activities=[ProfilerActivity.CUDA])
+            prof.__enter__()
+        except Exception as exc:        # no CUPTI on the box: fall back to the structural count below
+            prof, measured_launches = None, {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    r = one_step()
+    torch.cuda.synchronize(dev)
+    del r
+    if prof is not None:
+        try:
+            prof.__exit__(None, None, None)
             names = [e.name for e in prof.events() if str(getattr(e, "device_type", "")).endswith("CUDA")]
             ours = [nm for nm in names if "grf::" in nm]
             measured_launches = {"grf_kernels": len(ours), "other_kernels_and_copies": len(names) - len(ours),
                                  "distinct_grf_kernels": len({nm.split("(")[0] for nm in ours})}
-        except Exception as exc:        # no CUPTI on the box: fall back to the structural count below
+        except Exception as exc:
             measured_launches = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        prof = None
+    barrier()
 
     step_ms_total = sum(r["step"][0].elapsed_time(r["step"][1]) for r in results)
     phase_ms = {}

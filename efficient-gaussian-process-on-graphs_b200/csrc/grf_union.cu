@@ -43,95 +43,124 @@ __device__ __forceinline__ int32_t lower_bound_col(const GrfEntry *__restrict__ 
     return lo - b;
 }
 
-// one warp per row; writes mkey (col << 5 | step) and mval at the merged position
+// Work is handed out in TASKS, not rows: a task is a row, or -- for a row longer than the caller's chunk
+// size -- one chunk of consecutive entries of its flat run (task_row[k], entries [task_b[k], task_e[k])).
+// The hub columns of a power-law Phi^T hold 10^5..10^6 entries; with one warp per row the longest one was a
+// serial chain of 2*10^4 iterations of dependent binary searches (config 4: 294 ms for the union build and
+// 44 ms per materialisation against 40 ms for the whole Phi build).
+
+// writes mkey (col << 5 | step) and mval at the merged position; one warp per task
 __global__ void __launch_bounds__(256) union_rank_kernel(const int32_t *__restrict__ ptr,
-                                                         const GrfEntry *__restrict__ ent, int64_t n_rows, int32_t L,
-                                                         uint32_t *__restrict__ mkey, float *__restrict__ mval) {
+                                                         const GrfEntry *__restrict__ ent,
+                                                         const int32_t *__restrict__ task_row,
+                                                         const int32_t *__restrict__ task_b,
+                                                         const int32_t *__restrict__ task_e, int64_t n_tasks,
+                                                         int32_t L, uint32_t *__restrict__ mkey,
+                                                         float *__restrict__ mval) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        const int32_t *rp = ptr + r * L;
+    for (int64_t k = warp0; k < n_tasks; k += nwarps) {
+        const int32_t *rp = ptr + (int64_t)task_row[k] * L;
         const int32_t row_b = rp[0];
-        for (int s = 0; s < L; ++s) {
-            const int32_t b = rp[s], e = rp[s + 1];
-            for (int32_t i = b + lane; i < e; i += 32) {
-                const GrfEntry en = ent[i];
-                const uint32_t col = (uint32_t)en.col & kColMask;
-                int32_t rank = i - b;
-                for (int s2 = 0; s2 < L; ++s2) {
-                    if (s2 == s) continue;
-                    // entries of an earlier length with the same col come first, of a later length after
-                    rank += lower_bound_col(ent, rp[s2], rp[s2 + 1], col, /*strict=*/s2 > s);
-                }
-                mkey[row_b + rank] = (col << 5) | (uint32_t)s;
-                mval[row_b + rank] = en.val;
+        const int32_t tb = task_b[k], te = task_e[k];
+        for (int32_t i = tb + lane; i < te; i += 32) {
+            int s = 0;
+            while (s + 1 < L && i >= rp[s + 1]) ++s;  // the segment (walk length) entry i belongs to
+            const GrfEntry en = ent[i];
+            const uint32_t col = (uint32_t)en.col & kColMask;
+            int32_t rank = i - rp[s];
+            for (int s2 = 0; s2 < L; ++s2) {
+                if (s2 == s) continue;
+                // entries of an earlier length with the same col come first, of a later length after
+                rank += lower_bound_col(ent, rp[s2], rp[s2 + 1], col, /*strict=*/s2 > s);
             }
+            mkey[row_b + rank] = (col << 5) | (uint32_t)s;
+            mval[row_b + rank] = en.val;
         }
     }
 }
 
+// distinct columns among the merged entries of each task (a column's first entry decides the task)
 __global__ void __launch_bounds__(256) union_count_kernel(const int32_t *__restrict__ ptr,
-                                                          const uint32_t *__restrict__ mkey, int64_t n_rows,
-                                                          int32_t L, int32_t *__restrict__ ucnt) {
+                                                          const uint32_t *__restrict__ mkey,
+                                                          const int32_t *__restrict__ task_row,
+                                                          const int32_t *__restrict__ task_b,
+                                                          const int32_t *__restrict__ task_e, int64_t n_tasks,
+                                                          int32_t L, int32_t *__restrict__ task_cnt) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        const int32_t b = ptr[r * L], e = ptr[(r + 1) * L];
+    for (int64_t k = warp0; k < n_tasks; k += nwarps) {
+        const int32_t row_b = ptr[(int64_t)task_row[k] * L];
+        const int32_t b = task_b[k], e = task_e[k];
         int cnt = 0;
-        for (int32_t i = b + lane; i < e; i += 32) cnt += (i == b) || ((mkey[i - 1] >> 5) != (mkey[i] >> 5));
+        for (int32_t i = b + lane; i < e; i += 32) cnt += (i == row_b) || ((mkey[i - 1] >> 5) != (mkey[i] >> 5));
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        if (lane == 0) ucnt[r] = cnt;
+        if (lane == 0) task_cnt[k] = cnt;
     }
 }
 
-// headers: {col, mask}; one warp per row, heads ranked with ballots
+// headers: {col, mask}; one warp per task, heads ranked with ballots.  task_v0[k] = merged position of the
+// task's first head (where the values of its first union entry start).
 __global__ void __launch_bounds__(256) union_fill_kernel(const int32_t *__restrict__ ptr,
-                                                         const uint32_t *__restrict__ mkey, int64_t n_rows, int32_t L,
-                                                         const int32_t *__restrict__ uptr, int2 *__restrict__ uhdr) {
+                                                         const uint32_t *__restrict__ mkey,
+                                                         const int32_t *__restrict__ task_row,
+                                                         const int32_t *__restrict__ task_b,
+                                                         const int32_t *__restrict__ task_e, int64_t n_tasks,
+                                                         int32_t L, const int32_t *__restrict__ task_u0,
+                                                         int2 *__restrict__ uhdr, int32_t *__restrict__ task_v0) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        const int32_t b = ptr[r * L], e = ptr[(r + 1) * L];
-        int32_t out = uptr[r];
+    for (int64_t k = warp0; k < n_tasks; k += nwarps) {
+        const int64_t r = task_row[k];
+        const int32_t row_b = ptr[r * L], row_e = ptr[(r + 1) * L];
+        const int32_t b = task_b[k], e = task_e[k];
+        int32_t out = task_u0[k];
+        bool first_seen = false;
         for (int32_t base = b; base < e; base += 32) {
             const int32_t i = base + lane;
             bool head = false;
             uint32_t col = 0;
             if (i < e) {
                 col = mkey[i] >> 5;
-                head = (i == b) || ((mkey[i - 1] >> 5) != col);
+                head = (i == row_b) || ((mkey[i - 1] >> 5) != col);
             }
             const unsigned heads = __ballot_sync(0xffffffffu, head);
             if (head) {
-                uint32_t mask = 0;
-                for (int32_t q = i; q < e && (mkey[q] >> 5) == col; ++q) mask |= 1u << (mkey[q] & 31u);
+                uint32_t mask = 0;  // the group may run past the end of the task (never past the row)
+                for (int32_t q = i; q < row_e && (mkey[q] >> 5) == col; ++q) mask |= 1u << (mkey[q] & 31u);
                 uhdr[out + __popc(heads & ((1u << lane) - 1u))] = make_int2((int)col, (int)mask);
+            }
+            if (!first_seen && heads) {
+                if (lane == __ffs(heads) - 1) task_v0[k] = i;
+                first_seen = true;
             }
             out += __popc(heads);
         }
+        if (!first_seen && lane == 0) task_v0[k] = e;
     }
 }
 
-// ent_f[u] = {col, sum_{l in mask} f[l] * mval[..]}; one warp per row
-__global__ void __launch_bounds__(256) union_materialize_kernel(const int32_t *__restrict__ ptr,
-                                                                const int32_t *__restrict__ uptr,
-                                                                const int2 *__restrict__ uhdr,
+// ent_f[u] = {col, sum_{l in mask} f[l] * mval[..]}; one warp per task: union entries
+// [task_u0[k], task_u0[k+1]), their values from merged position task_v0[k] on
+__global__ void __launch_bounds__(256) union_materialize_kernel(const int32_t *__restrict__ task_u0,
+                                                                const int32_t *__restrict__ task_v0,
+                                                                int64_t n_tasks, const int2 *__restrict__ uhdr,
                                                                 const float *__restrict__ mval,
-                                                                const float *__restrict__ f, int64_t n_rows,
-                                                                int32_t L, GrfEntry *__restrict__ ent_f) {
+                                                                const float *__restrict__ f, int32_t L,
+                                                                GrfEntry *__restrict__ ent_f) {
     __shared__ float fs[kMaxSteps];
     if (threadIdx.x < kMaxSteps) fs[threadIdx.x] = threadIdx.x < L ? f[threadIdx.x] : 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_rows; r += nwarps) {
-        const int32_t ub = uptr[r], ue = uptr[r + 1];
-        int32_t voff = ptr[r * L];  // the row's values start where its per-length entries start
+    for (int64_t k = warp0; k < n_tasks; k += nwarps) {
+        const int32_t ub = task_u0[k], ue = task_u0[k + 1];
+        int32_t voff = task_v0[k];
         for (int32_t base = ub; base < ue; base += 32) {
             const int32_t u = base + lane;
             int2 h = make_int2(0, 0);
@@ -162,8 +191,8 @@ __global__ void __launch_bounds__(256) union_materialize_kernel(const int32_t *_
     }
 }
 
-static inline int warp_grid(int64_t n_rows) {
-    int64_t g = (n_rows + 7) / 8;
+static inline int warp_grid(int64_t n_tasks) {
+    int64_t g = (n_tasks + 7) / 8;
     const int64_t cap = (int64_t)kSmCount * 32;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
@@ -174,38 +203,43 @@ static inline int warp_grid(int64_t n_rows) {
 
 using namespace grf;
 
-extern "C" int grf_union_rank(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
-                              uint32_t *mkey, float *mval, int32_t *ucnt, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream, ucnt);
-    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && n_steps <= kMaxSteps, "grf_union_rank: bad shape");
-    if (n_rows == 0) return GRF_OK;
-    GRF_REQUIRE(blk_ptr && mkey && mval && ucnt, "grf_union_rank: null buffer");
+extern "C" int grf_union_rank(const int32_t *blk_ptr, const GrfEntry *entries, int32_t n_steps,
+                              const int32_t *task_row, const int32_t *task_b, const int32_t *task_e, int64_t n_tasks,
+                              uint32_t *mkey, float *mval, int32_t *task_cnt, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream, task_cnt);
+    GRF_REQUIRE(n_tasks >= 0 && n_steps >= 1 && n_steps <= kMaxSteps, "grf_union_rank: bad shape");
+    if (n_tasks == 0) return GRF_OK;
+    GRF_REQUIRE(blk_ptr && task_row && task_b && task_e && mkey && mval && task_cnt, "grf_union_rank: null buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    union_rank_kernel<<<warp_grid(n_rows), 256, 0, st>>>(blk_ptr, entries, n_rows, n_steps, mkey, mval);
+    union_rank_kernel<<<warp_grid(n_tasks), 256, 0, st>>>(blk_ptr, entries, task_row, task_b, task_e, n_tasks, n_steps,
+                                                         mkey, mval);
     GRF_CUDA_OK(cudaGetLastError());
-    union_count_kernel<<<warp_grid(n_rows), 256, 0, st>>>(blk_ptr, mkey, n_rows, n_steps, ucnt);
+    union_count_kernel<<<warp_grid(n_tasks), 256, 0, st>>>(blk_ptr, mkey, task_row, task_b, task_e, n_tasks, n_steps,
+                                                          task_cnt);
     return check_cuda(cudaGetLastError(), "union_rank/count launch");
 }
 
-extern "C" int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int64_t n_rows, int32_t n_steps,
-                              const int32_t *uptr, int32_t *uhdr, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream, uptr);
-    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1, "grf_union_fill: bad shape");
-    if (n_rows == 0) return GRF_OK;
-    GRF_REQUIRE(blk_ptr && mkey && uptr && uhdr, "grf_union_fill: null buffer");
-    union_fill_kernel<<<warp_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(blk_ptr, mkey, n_rows, n_steps, uptr,
-                                                                          (int2 *)uhdr);
+extern "C" int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int32_t n_steps, const int32_t *task_row,
+                              const int32_t *task_b, const int32_t *task_e, int64_t n_tasks, const int32_t *task_u0,
+                              int32_t *uhdr, int32_t *task_v0, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream, task_u0);
+    GRF_REQUIRE(n_tasks >= 0 && n_steps >= 1, "grf_union_fill: bad shape");
+    if (n_tasks == 0) return GRF_OK;
+    GRF_REQUIRE(blk_ptr && mkey && task_row && task_b && task_e && task_u0 && uhdr && task_v0,
+                "grf_union_fill: null buffer");
+    union_fill_kernel<<<warp_grid(n_tasks), 256, 0, (cudaStream_t)stream>>>(
+        blk_ptr, mkey, task_row, task_b, task_e, n_tasks, n_steps, task_u0, (int2 *)uhdr, task_v0);
     return check_cuda(cudaGetLastError(), "union_fill_kernel launch");
 }
 
-extern "C" int grf_union_materialize(const int32_t *blk_ptr, const int32_t *uptr, const int32_t *uhdr,
-                                     const float *mval, const float *f, int64_t n_rows, int32_t n_steps,
+extern "C" int grf_union_materialize(const int32_t *task_u0, const int32_t *task_v0, int64_t n_tasks,
+                                     const int32_t *uhdr, const float *mval, const float *f, int32_t n_steps,
                                      GrfEntry *entries_f, void *stream) {
-    GRF_ON_STREAM_DEVICE(stream, uptr);
-    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && n_steps <= kMaxSteps, "grf_union_materialize: bad shape");
-    if (n_rows == 0) return GRF_OK;
-    GRF_REQUIRE(blk_ptr && uptr && f, "grf_union_materialize: null buffer");
-    union_materialize_kernel<<<warp_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(
-        blk_ptr, uptr, (const int2 *)uhdr, mval, f, n_rows, n_steps, entries_f);
+    GRF_ON_STREAM_DEVICE(stream, task_u0);
+    GRF_REQUIRE(n_tasks >= 0 && n_steps >= 1 && n_steps <= kMaxSteps, "grf_union_materialize: bad shape");
+    if (n_tasks == 0) return GRF_OK;
+    GRF_REQUIRE(task_u0 && task_v0 && f, "grf_union_materialize: null buffer");
+    union_materialize_kernel<<<warp_grid(n_tasks), 256, 0, (cudaStream_t)stream>>>(
+        task_u0, task_v0, n_tasks, (const int2 *)uhdr, mval, f, n_steps, entries_f);
     return check_cuda(cudaGetLastError(), "union_materialize_kernel launch");
 }

@@ -382,6 +382,19 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                     }
                     key[r] = kk;
                 }
+                // no walk reached this length (an isolated start node -- 42 % of the rows of the config-4 graph --
+                // or every walk halted): none reaches a later one either.  Skips four 128-key sorts per such row
+                // (ncu, config 4: the sort network was 22 % VIMNMX + 9 % SHFL of 22 warp-instructions per walk-step).
+                {
+                    bool have = false;
+#pragma unroll
+                    for (int r = 0; r < KPL; ++r) have |= key[r] != KEY_MAX;
+                    if (!__any_sync(0xffffffffu, have)) {
+                        if (lane == 0)
+                            for (int s2 = si; s2 < L - 1; ++s2) p.row_cnt[row * L + s2 + 1] = 0;
+                        break;
+                    }
+                }
                 warp_bitonic_sort<KeyT, KPL>(key, lane);
                 // park the loads in sorted order; a run (= one output entry) is then a contiguous
                 // stretch of that stream.  Heads write their node and where their run starts; one lane
@@ -432,6 +445,7 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                 off += total;
                 __syncwarp();
             } else {
+                int have = 0;
                 for (int i = tg; i < Wp; i += GS) {
                     KeyT key = KEY_MAX;
                     if (i < W) {
@@ -439,8 +453,13 @@ __global__ void __launch_bounds__(kBlock ? 256 : 128, kBlock ? 1 : GRF_WALK_MINB
                         if (nd >= 0) key = ((KeyT)(uint32_t)nd << wbits) | (KeyT)i;
                     }
                     keys[i] = key;
+                    have |= key != KEY_MAX;
                 }
-                __syncthreads();
+                if (!__syncthreads_or(have)) {  // nothing at this length, hence nothing at any later one
+                    if (tg == 0)
+                        for (int s2 = si; s2 < L - 1; ++s2) p.row_cnt[row * L + s2 + 1] = 0;
+                    break;
+                }
                 for (uint32_t k = 2; k <= (uint32_t)Wp; k <<= 1) {
                     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
                         for (uint32_t c = tg; c < (uint32_t)Wp / 2; c += GS) {

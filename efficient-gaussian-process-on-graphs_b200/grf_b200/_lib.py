@@ -21,7 +21,7 @@ LOAD_CUMULATIVE, LOAD_LAST_STEP, LOAD_ABLATION = 0, 1, 2
 SCALE_MUL_RECIP, SCALE_DIV = 0, 1
 ORDER_ROW_MAJOR, ORDER_STEP_MAJOR = 0, 1
 ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
-ABI_VERSION = 4        # GRF_B200_ABI_VERSION
+ABI_VERSION = 5        # GRF_B200_ABI_VERSION
 
 # every symbol include/grf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = (
@@ -128,11 +128,11 @@ def lib():
     L.grf_phi_matvec.restype = i32
     L.grf_phi_matvec.argtypes = [POINTER(GrfPhi), vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, vp]
     L.grf_union_rank.restype = i32
-    L.grf_union_rank.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp]
+    L.grf_union_rank.argtypes = [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp]
     L.grf_union_fill.restype = i32
-    L.grf_union_fill.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    L.grf_union_fill.argtypes = [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp]
     L.grf_union_materialize.restype = i32
-    L.grf_union_materialize.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
+    L.grf_union_materialize.argtypes = [vp, vp, i64, vp, vp, vp, i32, vp, vp]
     L.grf_cg_num_partials.restype = i32
     L.grf_cg_num_partials.argtypes = [i64, i32]
     L.grf_cg_dot.restype = i32

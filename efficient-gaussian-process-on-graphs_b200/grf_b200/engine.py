@@ -26,6 +26,7 @@ from . import _lib
 from ._lib import GrfGraph, GrfLongRows, GrfPhi, GrfWalkCfg, check
 
 LONG_ROW_THRESHOLD = 256   # rows of Phi / Phi^T with more entries are split into chunks of this size
+UNION_CHUNK = 1024         # rows with more entries are merged (union layout) chunk by chunk
 CHUNK_ORDER = os.environ.get("GRF_CHUNK_ORDER", "1") != "0"   # issue the chunks by the first row they gather
 _MAX_STAGE_BYTES = 16 << 30  # staging budget per walker launch; larger shards are walked in row chunks
 _LAZY_ENTRY_BYTES = 1 << 30  # up to this bound the Phi entries are allocated by capacity (no host wait for the count)
@@ -754,17 +755,41 @@ class PhiBlocks:
         dev = self.device
         sides = []
         for ptr, ent, n in ((self.blk_ptr, self.entries, self.n_rows), (self.tblk_ptr, self.tentries, self.n_cols)):
+            # tasks: a row, or one UNION_CHUNK-entry chunk of a long row's flat run (hub columns must not
+            # serialise one warp); listed row by row, so a scan over the tasks is a scan over the rows
+            nL = self.n_steps
+            row_b = ptr[0:n * nL:nL].to(torch.int64)
+            row_e = ptr[nL:n * nL + 1:nL].to(torch.int64)
+            nch = torch.clamp((row_e - row_b + UNION_CHUNK - 1) // UNION_CHUNK, min=1)
+            task_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(nch, 0, out=task_ptr[1:])
+            n_tasks = int(task_ptr[-1].item())
+            if n_tasks == n:
+                task_row = torch.arange(n, dtype=torch.int32, device=dev)
+                task_b, task_e = row_b.to(torch.int32), row_e.to(torch.int32)
+            else:
+                rows = torch.repeat_interleave(torch.arange(n, device=dev), nch, output_size=n_tasks)
+                local = torch.arange(n_tasks, device=dev) - task_ptr[rows]
+                tb = row_b[rows] + local * UNION_CHUNK
+                task_b = tb.to(torch.int32)
+                task_e = torch.minimum(tb + UNION_CHUNK, row_e[rows]).to(torch.int32)
+                task_row = rows.to(torch.int32)
+                del rows, local, tb
             mkey = torch.empty(max(1, self.nnz), dtype=torch.int32, device=dev)
             mval = torch.empty(max(1, self.nnz), dtype=torch.float32, device=dev)
-            ucnt = torch.empty(max(1, n), dtype=torch.int32, device=dev)
-            check(L.grf_union_rank(_ptr(ptr), _ptr(ent), n, self.n_steps, _ptr(mkey), _ptr(mval), _ptr(ucnt),
-                                   _stream(dev)))
-            uptr = scan_counts(ucnt, n, 1, _lib.ORDER_ROW_MAJOR, i64=False)
-            n_union = int(uptr[-1].item())
+            tcnt = torch.empty(max(1, n_tasks), dtype=torch.int32, device=dev)
+            check(L.grf_union_rank(_ptr(ptr), _ptr(ent), nL, _ptr(task_row), _ptr(task_b), _ptr(task_e), n_tasks,
+                                   _ptr(mkey), _ptr(mval), _ptr(tcnt), _stream(dev)))
+            task_u0 = scan_counts(tcnt, n_tasks, 1, _lib.ORDER_ROW_MAJOR, i64=False)
+            n_union = int(task_u0[-1].item())
             uhdr = torch.empty((max(1, n_union), 2), dtype=torch.int32, device=dev)[:n_union]
-            check(L.grf_union_fill(_ptr(ptr), _ptr(mkey), n, self.n_steps, _ptr(uptr), _ptr(uhdr), _stream(dev)))
-            sides.append(dict(ptr=ptr, n=n, uptr=uptr, uhdr=uhdr, mval=mval, n_union=n_union))
-            del mkey
+            task_v0 = torch.empty(max(1, n_tasks), dtype=torch.int32, device=dev)
+            check(L.grf_union_fill(_ptr(ptr), _ptr(mkey), nL, _ptr(task_row), _ptr(task_b), _ptr(task_e), n_tasks,
+                                   _ptr(task_u0), _ptr(uhdr), _ptr(task_v0), _stream(dev)))
+            uptr = task_u0[task_ptr].contiguous()
+            sides.append(dict(n=n, uptr=uptr, uhdr=uhdr, mval=mval, n_union=n_union, n_tasks=n_tasks,
+                              task_u0=task_u0, task_v0=task_v0))
+            del mkey, task_row, task_b, task_e, tcnt
         self._union = sides
         return self
 
@@ -787,8 +812,8 @@ class PhiBlocks:
             into = PhiBlocks(fwd["uptr"], ent, self.n_rows, self.n_cols, 1, self.row_lo)
             into.tblocks = [TBlock(0, self.n_rows, tr["n_union"], tr["uptr"], tent)]
         for side, ent in ((fwd, into.entries), (tr, into.tentries)):
-            check(L.grf_union_materialize(_ptr(side["ptr"]), _ptr(side["uptr"]), _ptr(side["uhdr"]),
-                                          _ptr(side["mval"]), _ptr(f), side["n"], self.n_steps, _ptr(ent),
+            check(L.grf_union_materialize(_ptr(side["task_u0"]), _ptr(side["task_v0"]), side["n_tasks"],
+                                          _ptr(side["uhdr"]), _ptr(side["mval"]), _ptr(f), self.n_steps, _ptr(ent),
                                           _stream(dev)))
         return into
 

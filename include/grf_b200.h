@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GRF_B200_ABI_VERSION 4
+#define GRF_B200_ABI_VERSION 5
 
 enum {
     GRF_OK = 0,
@@ -302,20 +302,27 @@ int grf_block_windows(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n
                       int32_t *win /* [ceil(n_rows/32)][2] */, int32_t *max_width, void *stream);
 
 /* Union rows (csrc/grf_union.cu): merge the L per-length segments of every row of Phi (or of
- * Phi^T -- pass tblk_ptr / tentries and n_cols) on their union pattern, once per Phi:
+ * Phi^T -- pass tblk_ptr / tentries) on their union pattern, once per Phi.  Work is handed out in TASKS
+ * built by the caller: task k = entries [task_b[k], task_e[k]) of row task_row[k] -- a whole row, or one chunk
+ * of a long row's flat run (hub columns of a power-law Phi^T hold 10^5..10^6 entries and would serialise a
+ * warp); tasks are listed row by row, chunks in order, and cover every entry once.
  *   grf_union_rank   mkey[nnz] = (col << 5 | length), mval[nnz] = values, both in (col, length)
- *                    order inside each row; ucnt[r] = distinct columns of row r
- *   (caller scans ucnt -> uptr with grf_scan_counts(n_rows, 1))
- *   grf_union_fill   uhdr[nU] = {col, mask of lengths present}
+ *                    order inside each row; task_cnt[k] = columns whose first merged entry lies in task k
+ *   (caller scans task_cnt -> task_u0 [n_tasks + 1] with grf_scan_counts(n_tasks, 1); the union row pointers
+ *    are uptr[r] = task_u0[first task of row r])
+ *   grf_union_fill   uhdr[nU] = {col, mask of lengths present}; task_v0[k] = merged position of the task's
+ *                    first union entry
  * and, per modulator f, grf_union_materialize writes the plain CSR of Phi_f = sum_l f[l] M_l
  * on that pattern, entries_f[nU] = {col, sum_l f[l] * value}; multiply it with
  * grf_phi_matvec using n_steps = 1, blk_ptr = uptr, f = [1]. */
-int grf_union_rank(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
-                   uint32_t *mkey, float *mval, int32_t *ucnt, void *stream);
-int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int64_t n_rows, int32_t n_steps,
-                   const int32_t *uptr, int32_t *uhdr /* [nU][2] */, void *stream);
-int grf_union_materialize(const int32_t *blk_ptr, const int32_t *uptr, const int32_t *uhdr, const float *mval,
-                          const float *f, int64_t n_rows, int32_t n_steps, GrfEntry *entries_f, void *stream);
+int grf_union_rank(const int32_t *blk_ptr, const GrfEntry *entries, int32_t n_steps, const int32_t *task_row,
+                   const int32_t *task_b, const int32_t *task_e, int64_t n_tasks, uint32_t *mkey, float *mval,
+                   int32_t *task_cnt, void *stream);
+int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int32_t n_steps, const int32_t *task_row,
+                   const int32_t *task_b, const int32_t *task_e, int64_t n_tasks, const int32_t *task_u0,
+                   int32_t *uhdr /* [nU][2] */, int32_t *task_v0, void *stream);
+int grf_union_materialize(const int32_t *task_u0, const int32_t *task_v0, int64_t n_tasks, const int32_t *uhdr,
+                          const float *mval, const float *f, int32_t n_steps, GrfEntry *entries_f, void *stream);
 
 /* Per-length reduction for the modulator gradient (what upstream
  * _bilinear_derivative yields for sparse_grf_kernel.py:51-62):

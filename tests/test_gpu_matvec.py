@@ -624,3 +624,39 @@ def test_torch_csr_with_unsorted_or_repeated_columns_is_coalesced():
     for merged in (False, True):
         got = phi.plan(f, 3, merged=merged)(v)
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), merged
+
+
+def test_union_layout_with_rows_longer_than_one_chunk(env):
+    """The union (merged) layout splits rows beyond engine.UNION_CHUNK entries into chunk tasks: a star's hub column
+    holds ~n entries per length in Phi^T, and the hub's own row of Phi holds one per leaf.  Phi_f on the union
+    pattern must equal sum_l f_l M_l entry for entry, and multiply like the per-length blocks."""
+    torch, eng = env["torch"], env["eng"]
+    n = 9000
+    leaves = np.arange(1, n)
+    adj = sp.csr_matrix((np.ones(2 * (n - 1)), (np.r_[np.zeros(n - 1, dtype=np.int64), leaves],
+                                                np.r_[leaves, np.zeros(n - 1, dtype=np.int64)])), shape=(n, n))
+    extra = random_graph(n, 3 * n, 17)
+    lap = env["o"].normalized_laplacian_sparse(((adj + extra) > 0).astype(float).tocsr())
+    g = eng.DeviceGraph.from_scipy(lap)
+    phi = eng.build_phi_blocks(g, eng.WalkConfig(12, 0.1, 4, seed=9))
+    seg = np.diff(phi.tblk_ptr.cpu().numpy().astype(np.int64)[::4])
+    assert seg.max() > 3 * eng.UNION_CHUNK, "the hub column should span several chunks"
+    f = torch.tensor([0.7, -1.3, 0.4, 2.0], device="cuda")
+    merged = phi.merged(f)
+    mats = phi.to_scipy_steps()                                     # float32 values
+    want = sum(float(fl) * m.astype(np.float64) for fl, m in zip(f.cpu().numpy(), mats)).tocsr()
+    want.sort_indices()
+    got = merged.to_scipy_steps()[0].astype(np.float64)
+    got.sort_indices()
+    assert phi.nnz_union == got.nnz
+    # the union pattern keeps a column even when its f-weighted sum cancels; compare as dense-free difference
+    diff = (got - want)
+    assert abs(diff).max() <= 1e-6 * abs(want).max()
+    got_t = sp.csr_matrix((merged.tentries.cpu().numpy()[:, 1].copy().view(np.float32).astype(np.float64),
+                           merged.tentries.cpu().numpy()[:, 0] & ((1 << 27) - 1),
+                           merged.tblk_ptr.cpu().numpy().astype(np.int64)), shape=(n, n))
+    assert abs(got_t - want.T).max() <= 1e-6 * abs(want).max()
+    v = torch.randn(n, 5, device="cuda")
+    a = phi.plan(f, 5, merged=False)(v)
+    b = phi.plan(f, 5, merged=True)(v)
+    assert float((a - b).abs().max()) <= RTOL * float(a.abs().max())
