@@ -12,7 +12,8 @@
 //   L_ij    = deg_i - A_ii on the diagonal, -A_ij elsewhere; exact zeros dropped (csr binop)
 //   out_ij  = (dis_i * L_ij) * dis_j, in that order; exact zeros dropped at either product
 //             (scipy's SpGEMM) -- so zero-degree rows come out empty
-// Two passes (count, fill) of one warp per row around a scan; streaming, HBM-bound.
+// Two passes (count, fill) of one warp per row around a scan; streaming, HBM-bound.  Rows in which nothing is
+// dropped (the usual case) are filled without any cross-lane dependency, so hub rows pipeline.
 
 #include "grf_common.cuh"
 
@@ -79,20 +80,44 @@ __device__ double numpy_pairwise_sum(const double *a, int64_t n) {
     }
 }
 
-// thread per row; the summation order is scipy's (see the header comment)
+// warp per row.  The summation order is scipy's (see the header comment) -- which only matters when the sum is
+// inexact: if every weight of the row is an integer and sum |a_ij| <= 2^53, every partial sum in ANY order is an
+// exactly representable integer, so the lanes add their strided share and a shuffle tree finishes (unit-weight
+// graphs: every row).  Otherwise lane 0 walks numpy's pairwise tree.  (One thread per row, always in numpy's order:
+// 10 ms for the 175 303-neighbour hub row of the config-4 graph, 30x the time of the rest of the graph.)
 __global__ void __launch_bounds__(256) lap_degree_kernel(const int32_t *__restrict__ row_ptr,
                                                          const double *__restrict__ val, int64_t n,
                                                          double *__restrict__ deg, double *__restrict__ dis) {
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n; r += nwarps) {
         const int32_t b = row_ptr[r], e = row_ptr[r + 1];
-        double s = 0.0;
-        if (e > b) s = e - b == 1 ? val[b] : __dadd_rn(val[b], numpy_pairwise_sum(val + b + 1, e - b - 1));
-        deg[r] = s;
-        double d = __ddiv_rn(1.0, __dsqrt_rn(s));
-        if (isinf(d)) d = 0.0;  // d_inv_sqrt[np.isinf(d_inv_sqrt)] = 0
-        dis[r] = d;
+        double s = 0.0, sa = 0.0;
+        bool whole = true;
+        for (int32_t i = b + lane; i < e; i += 32) {
+            const double a = val[i];
+            s += a;
+            sa += fabs(a);
+            whole = whole && (a == rint(a));  // false for NaN; infinities fail the bound below
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, d);
+            sa += __shfl_xor_sync(0xffffffffu, sa, d);
+        }
+        const bool exact = __all_sync(0xffffffffu, whole) && sa <= 9007199254740992.0;
+        if (lane == 0) {
+            if (!exact) s = e - b <= 1 ? (e > b ? val[b] : 0.0) : __dadd_rn(val[b], numpy_pairwise_sum(val + b + 1, e - b - 1));
+            deg[r] = s;
+            double d = __ddiv_rn(1.0, __dsqrt_rn(s));
+            if (isinf(d)) d = 0.0;  // d_inv_sqrt[np.isinf(d_inv_sqrt)] = 0
+            dis[r] = d;
+        }
     }
 }
+
+constexpr int kLapUnroll = 8;  // independent 32-entry batches of a row in flight per warp
 
 // value of output entry (r, c) given the Laplacian value l = L_rc; keep = survives both products
 __device__ __forceinline__ double lap_scale(double dis_r, double l, double dis_c, bool &keep) {
@@ -102,13 +127,64 @@ __device__ __forceinline__ double lap_scale(double dis_r, double l, double dis_c
     return y;
 }
 
-// FILL = false: out_cnt[r] = entries of output row r;  FILL = true: write them at out_ptr[r]
-template <bool FILL>
-__global__ void __launch_bounds__(256) lap_rows_kernel(const int32_t *__restrict__ row_ptr,
+// out_cnt[r] = entries of output row r.  Lanes count their strided share of the row (no cross-lane dependency
+// between the batches: a hub row's loads pipeline), one reduction at the end.
+__global__ void __launch_bounds__(256) lap_count_kernel(const int32_t *__restrict__ row_ptr,
+                                                        const int32_t *__restrict__ col, const double *__restrict__ val,
+                                                        const double *__restrict__ deg, const double *__restrict__ dis,
+                                                        int64_t n, int32_t *__restrict__ out_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const int32_t b = row_ptr[r], e = row_ptr[r + 1];
+        const double dr = dis[r], dg = deg[r];
+        int cnt = 0;
+        double a_diag = 0.0;  // a stored self-loop (at most one: canonical CSR)
+        // kLapUnroll batches in flight: the loads of a batch depend on each other (col -> dis[col]), so one
+        // batch at a time made the 175 303-neighbour hub row of the config-4 graph a chain of 5 500 round trips
+        // (6.6 ms for this kernel, all of it that one warp)
+        for (int32_t i0 = b + lane; i0 < e; i0 += 32 * kLapUnroll) {
+            int32_t c[kLapUnroll];
+            double a[kLapUnroll], dc[kLapUnroll];
+#pragma unroll
+            for (int u = 0; u < kLapUnroll; ++u) {
+                const int32_t i = i0 + 32 * u;
+                c[u] = i < e ? col[i] : -1;
+                a[u] = i < e ? val[i] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kLapUnroll; ++u) dc[u] = (c[u] >= 0 && c[u] != (int32_t)r) ? dis[c[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < kLapUnroll; ++u) {
+                if (c[u] < 0) continue;
+                if (c[u] == (int32_t)r) {
+                    a_diag = a[u];
+                } else {
+                    bool keep;
+                    lap_scale(dr, -a[u], dc[u], keep);
+                    cnt += keep;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            a_diag += __shfl_xor_sync(0xffffffffu, a_diag, d);  // all other lanes hold 0.0
+        }
+        if (lane == 0) {
+            bool keep_d;
+            lap_scale(dr, __dsub_rn(dg, a_diag), dr, keep_d);
+            out_cnt[r] = cnt + (keep_d ? 1 : 0);
+        }
+    }
+}
+
+// write the output rows at out_ptr[r]
+__global__ void __launch_bounds__(256) lap_fill_kernel(const int32_t *__restrict__ row_ptr,
                                                        const int32_t *__restrict__ col, const double *__restrict__ val,
                                                        const double *__restrict__ deg, const double *__restrict__ dis,
-                                                       int64_t n, int32_t *__restrict__ out_cnt,
-                                                       const int32_t *__restrict__ out_ptr,
+                                                       int64_t n, const int32_t *__restrict__ out_ptr,
                                                        int32_t *__restrict__ out_col, double *__restrict__ out_val) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -116,7 +192,45 @@ __global__ void __launch_bounds__(256) lap_rows_kernel(const int32_t *__restrict
     for (int64_t r = warp0; r < n; r += nwarps) {
         const int32_t b = row_ptr[r], e = row_ptr[r + 1];
         const double dr = dis[r], dg = deg[r];
-        int32_t out = FILL ? out_ptr[r] : 0;
+        int32_t out = out_ptr[r];
+        if (e > b && out_ptr[r + 1] - out == e - b + 1) {
+            // every stored entry survives, so does the diagonal, and there is no self-loop (the row could not
+            // have e - b + 1 entries otherwise): positions follow from the index alone -- entry i goes to
+            // i - b, one further if its column lies beyond the diagonal -- and the batches are independent
+            for (int32_t i0 = b + lane; i0 < e; i0 += 32 * kLapUnroll) {
+                int32_t c[kLapUnroll];
+                double a[kLapUnroll], dc[kLapUnroll];
+#pragma unroll
+                for (int u = 0; u < kLapUnroll; ++u) {
+                    const int32_t i = i0 + 32 * u;
+                    c[u] = i < e ? col[i] : -1;
+                    a[u] = i < e ? val[i] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kLapUnroll; ++u) dc[u] = c[u] >= 0 ? dis[c[u]] : 0.0;
+#pragma unroll
+                for (int u = 0; u < kLapUnroll; ++u) {
+                    if (c[u] < 0) continue;
+                    const int32_t i = i0 + 32 * u;
+                    bool keep;
+                    const double v = lap_scale(dr, -a[u], dc[u], keep);
+                    const int32_t pos = out + (i - b) + (c[u] > (int32_t)r ? 1 : 0);
+                    out_col[pos] = c[u];
+                    out_val[pos] = v;
+                    // the diagonal sits before the first column beyond r, or after the last entry
+                    const bool first_beyond = c[u] > (int32_t)r && (i == b || col[i - 1] < (int32_t)r);
+                    const bool last_below = i == e - 1 && c[u] < (int32_t)r;
+                    if (first_beyond || last_below) {
+                        bool keep_d;
+                        const int32_t pd = out + (i - b) + (last_below ? 1 : 0);
+                        out_col[pd] = (int32_t)r;
+                        out_val[pd] = lap_scale(dr, dg, dr, keep_d);
+                    }
+                }
+            }
+            continue;
+        }
+        // general path: zeros dropped / a stored self-loop; positions by ballot, batch after batch.
         // the diagonal entry goes before the first stored column > r; if every stored column is < r
         // (or the row is empty) one more, all-padding batch emits it
         bool diag_done = false;
@@ -148,22 +262,19 @@ __global__ void __launch_bounds__(256) lap_rows_kernel(const int32_t *__restrict
             double vd = 0.0;
             if (emit_diag) vd = lap_scale(dr, __dsub_rn(dg, a_diag), dr, keep_d);
             const unsigned kept = __ballot_sync(0xffffffffu, keep);
-            if (FILL) {
-                if (keep) {
-                    int pos = __popc(kept & ((1u << lane) - 1u));
-                    if (keep_d && lane >= diag_lane) ++pos;  // the diagonal sits before this lane's entry
-                    out_col[out + pos] = c;
-                    out_val[out + pos] = v;
-                }
-                if (keep_d && lane == 0) {
-                    const int pos = __popc(kept & ((1u << diag_lane) - 1u));
-                    out_col[out + pos] = (int32_t)r;
-                    out_val[out + pos] = vd;
-                }
+            if (keep) {
+                int pos = __popc(kept & ((1u << lane) - 1u));
+                if (keep_d && lane >= diag_lane) ++pos;  // the diagonal sits before this lane's entry
+                out_col[out + pos] = c;
+                out_val[out + pos] = v;
+            }
+            if (keep_d && lane == 0) {
+                const int pos = __popc(kept & ((1u << diag_lane) - 1u));
+                out_col[out + pos] = (int32_t)r;
+                out_val[out + pos] = vd;
             }
             out += __popc(kept) + (keep_d ? 1 : 0);
         }
-        if (!FILL && lane == 0) out_cnt[r] = out;
     }
 }
 
@@ -187,11 +298,10 @@ extern "C" int grf_laplacian_count(const GrfGraph *adj, double *deg, double *dis
     if (adj->n_nodes == 0) return GRF_OK;
     GRF_REQUIRE(adj->row_ptr && deg && dis && out_cnt, "grf_laplacian_count: null buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    lap_degree_kernel<<<lap_grid(adj->n_nodes, 256), 256, 0, st>>>(adj->row_ptr, adj->val, adj->n_nodes, deg, dis);
+    lap_degree_kernel<<<lap_grid(adj->n_nodes, 8), 256, 0, st>>>(adj->row_ptr, adj->val, adj->n_nodes, deg, dis);
     GRF_CUDA_OK(cudaGetLastError());
-    lap_rows_kernel<false><<<lap_grid(adj->n_nodes, 8), 256, 0, st>>>(adj->row_ptr, adj->col_idx, adj->val, deg, dis,
-                                                                       adj->n_nodes, out_cnt, nullptr, nullptr,
-                                                                       nullptr);
+    lap_count_kernel<<<lap_grid(adj->n_nodes, 8), 256, 0, st>>>(adj->row_ptr, adj->col_idx, adj->val, deg, dis,
+                                                                adj->n_nodes, out_cnt);
     return check_cuda(cudaGetLastError(), "laplacian count launch");
 }
 
@@ -201,7 +311,7 @@ extern "C" int grf_laplacian_fill(const GrfGraph *adj, const double *deg, const 
     GRF_REQUIRE(adj, "grf_laplacian_fill: null graph");
     if (adj->n_nodes == 0) return GRF_OK;
     GRF_REQUIRE(adj->row_ptr && deg && dis && out_ptr, "grf_laplacian_fill: null buffer");
-    lap_rows_kernel<true><<<lap_grid(adj->n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
-        adj->row_ptr, adj->col_idx, adj->val, deg, dis, adj->n_nodes, nullptr, out_ptr, out_col, out_val);
+    lap_fill_kernel<<<lap_grid(adj->n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
+        adj->row_ptr, adj->col_idx, adj->val, deg, dis, adj->n_nodes, out_ptr, out_col, out_val);
     return check_cuda(cudaGetLastError(), "laplacian fill launch");
 }

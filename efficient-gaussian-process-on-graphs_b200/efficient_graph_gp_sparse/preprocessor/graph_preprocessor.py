@@ -143,14 +143,17 @@ class GraphPreprocessor:
                                                      PhiBlocks.from_step_matrices(self._steps_device))
         return self.step_matrices_torch
 
-    def preprocess_phi(self, start_lo: int = 0, start_hi: Optional[int] = None, *, trace=None) -> PhiBlocks:
+    def preprocess_phi(self, start_lo: int = 0, start_hi: Optional[int] = None, *, trace=None,
+                       group=None) -> PhiBlocks:
         """The pipeline of ``preprocess_graph`` kept in the matvec layout only: host adjacency -> device
         Laplacian -> walks -> Phi blocks (+ Phi^T) for the start nodes ``[start_lo, start_hi)`` -- what a
         row-sharded run (one process per GPU) or a graph whose float64 step matrices are not wanted
-        calls.  No host copy, no torch CSR tensors; ``SparseGRFKernel`` accepts the result's operators."""
+        calls.  No host copy, no torch CSR tensors; ``SparseGRFKernel`` accepts the result's operators.
+        ``group`` (torch.distributed group or True): the ranks hold the same adjacency -- each uploads a slice of it
+        and NCCL all-gathers the rest (``DeviceGraph.__init__``)."""
         from grf_b200.engine import build_phi_blocks
 
-        graph = DeviceGraph.laplacian_of(self.adj_matrix, self.device)
+        graph = DeviceGraph.laplacian_of(self.adj_matrix, self.device, group=group)
         cfg = WalkConfig(int(self.walks_per_node), float(self.p_halt), int(self.max_walk_length),
                          seed=self.random_walk_seed or 42,
                          draw_mode=_lib.DRAW_PHILOX if trace is None else _lib.DRAW_REPLAY, trace=trace)

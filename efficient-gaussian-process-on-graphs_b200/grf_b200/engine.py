@@ -122,7 +122,7 @@ def _to_host_pinned(t: torch.Tensor) -> torch.Tensor:
 
 
 _UPLOAD_CHUNK = 32 << 20      # bytes per pinned staging slot
-_UPLOAD_THREADS = 4
+_UPLOAD_THREADS = int(os.environ.get("GRF_UPLOAD_THREADS", "4"))
 _UPLOAD_MIN = 64 << 20        # smaller arrays take torch's own pageable copy
 _upload_state = {}            # device index -> (executor, [(stream, [pinned slots], [events])] per thread)
 
@@ -176,11 +176,37 @@ def _upload(arr: np.ndarray, dev: torch.device) -> torch.Tensor:
     return out
 
 
+def _upload_shared(arr: np.ndarray, dev: torch.device, group) -> torch.Tensor:
+    """``_upload`` of an array that every rank of ``group`` holds identically: rank r uploads slice r, then one
+    all-gather (NCCL over NVLink) completes every rank's copy."""
+    import torch.distributed as dist
+
+    pg = None if group is True else group
+    world = dist.get_world_size(pg)
+    arr = np.ascontiguousarray(arr)
+    if world == 1 or arr.ndim != 1 or arr.nbytes < _UPLOAD_MIN:
+        return _upload(arr, dev)
+    rank = dist.get_rank(pg)
+    n = arr.shape[0]
+    per = (n + world - 1) // world
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    piece = torch.zeros(per, dtype=torch.from_numpy(arr[:0]).dtype, device=dev)
+    if hi > lo:
+        piece[: hi - lo].copy_(_upload(arr[lo:hi], dev))
+    out = torch.empty(per * world, dtype=piece.dtype, device=dev)
+    dist.all_gather_into_tensor(out, piece, group=pg)
+    return out[:n]
+
+
 class DeviceGraph:
     """The walk graph resident in HBM: CSR row_ptr/col_idx int32, val float64
     (what SparseRandomWalk.__init__ keeps, sparse_sampler.py:62-70)."""
 
-    def __init__(self, indptr, indices, data, n_nodes: int, device=None):
+    def __init__(self, indptr, indices, data, n_nodes: int, device=None, group=None):
+        """``group`` (a torch.distributed group, or True for the default one): every rank of the group holds the
+        SAME host arrays and wants the same replicated graph -- each then uploads one 1/world slice over its own
+        PCIe link and the slices are all-gathered over NVLink (8 ranks pushing the whole 2 GB adjacency through
+        one host's memory system took longer than the Phi build they feed)."""
         self.device = _device(device)
         indptr = np.ascontiguousarray(indptr)
         if indptr.shape[0] != n_nodes + 1:
@@ -192,9 +218,10 @@ class DeviceGraph:
         self.nnz = nnz
         self._scaled = {}
         self._shared = {}
-        self.row_ptr = _upload(indptr.astype(np.int32, copy=False), self.device)
-        self.col_idx = _upload(np.ascontiguousarray(indices[:nnz]).astype(np.int32, copy=False), self.device)
-        self.val = _upload(np.ascontiguousarray(data[:nnz]).astype(np.float64, copy=False), self.device)
+        up = (lambda a: _upload(a, self.device)) if group is None else (lambda a: _upload_shared(a, self.device, group))
+        self.row_ptr = up(indptr.astype(np.int32, copy=False))
+        self.col_idx = up(np.ascontiguousarray(indices[:nnz]).astype(np.int32, copy=False))
+        self.val = up(np.ascontiguousarray(data[:nnz]).astype(np.float64, copy=False))
 
     @classmethod
     def from_scipy(cls, adj, device=None) -> "DeviceGraph":
@@ -218,16 +245,16 @@ class DeviceGraph:
         return g
 
     @classmethod
-    def laplacian_of(cls, adj, device=None) -> "DeviceGraph":
+    def laplacian_of(cls, adj, device=None, group=None) -> "DeviceGraph":
         """The walk graph D^-1/2 (D - A) D^-1/2 of a scipy adjacency, normalised on the device
-        (graph_utils.py:5-30, bit-identical values and structure)."""
+        (graph_utils.py:5-30, bit-identical values and structure).  ``group``: see ``__init__``."""
         if adj.shape[0] != adj.shape[1]:
             raise ValueError("Adjacency matrix must be square.")
         a = adj.tocsr()
         if not a.has_canonical_format:
             a = a.copy()
             a.sum_duplicates()
-        return cls(a.indptr, a.indices, a.data.astype(float, copy=False), a.shape[0], device).laplacian()
+        return cls(a.indptr, a.indices, a.data.astype(float, copy=False), a.shape[0], device, group).laplacian()
 
     def laplacian(self) -> "DeviceGraph":
         """D^-1/2 (D - A) D^-1/2 of this graph read as a canonical CSR adjacency (sorted columns, no

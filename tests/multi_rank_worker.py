@@ -26,6 +26,20 @@ def main():
     from gpu_util import grid_graph
     from oracle import grf_oracle
 
+    # replicated graph, uploaded once per box: every rank one slice + NCCL all-gather == every rank the whole thing
+    import scipy.sparse as sp
+
+    adj = sp.random(3000, 3000, 0.01, format="csr", random_state=7)
+    adj = ((adj + adj.T) > 0).astype(float).tocsr()
+    old_min, engine._UPLOAD_MIN = engine._UPLOAD_MIN, 1 << 10
+    try:
+        shared = engine.DeviceGraph.laplacian_of(adj, dev, group=True)
+    finally:
+        engine._UPLOAD_MIN = old_min
+    alone = engine.DeviceGraph.laplacian_of(adj, dev)
+    for a, b in ((shared.row_ptr, alone.row_ptr), (shared.col_idx, alone.col_idx), (shared.val, alone.val)):
+        assert torch.equal(a, b), "slice-upload + all-gather differs from the plain upload"
+
     t, L, W = 16, 4, 24
     cases = []
     g_pl, _ = synth.rmat_walk_graph(13, 60_000, seed=3, device=dev)                 # power-law: every column shared

@@ -385,6 +385,22 @@ def test_device_laplacian_is_bit_exact(env):
     star = sp.coo_matrix((np.r_[w, w], (np.r_[np.zeros(n - 1, int), hub_cols], np.r_[hub_cols, np.zeros(n - 1, int)])),
                          shape=(n, n)).tocsr()
     cases.append((star + random_graph(n, 30000, 9, weighted=True)).tocsr())
+    # the degree shortcut (integer weights with sum |a| <= 2^53 are summed in any order) and its limits: small and
+    # signed integers (exact in any order), integers whose sum overflows 2^53 (numpy's order), a row mixing both kinds
+    ints = random_graph(400, 3000, 21).tocsr()
+    for kind in range(3):
+        m = ints.copy().tocoo()
+        w = rng.integers(1, 9, m.nnz).astype(float)
+        if kind == 1:
+            w = w * 2.0 ** 51
+        if kind == 2:
+            w[rng.integers(0, m.nnz, 50)] += 0.25
+        m = sp.coo_matrix((w, (m.row, m.col)), shape=m.shape).tocsr()
+        cases.append(((m + m.T) * 0.5 if kind == 2 else (m + m.T)).tocsr())
+    star_i = sp.coo_matrix((np.r_[np.ones(n - 1), np.ones(n - 1)],
+                            (np.r_[np.zeros(n - 1, int), hub_cols], np.r_[hub_cols, np.zeros(n - 1, int)])),
+                           shape=(n, n)).tocsr()
+    cases.append(star_i)                                                    # unit-weight hub: the pipelined paths
     for a in cases:
         a = a.tocsr()
         a.sum_duplicates()
