@@ -294,7 +294,11 @@ static RadixPlan radix_plan(int64_t n_keys_space, int64_t n) {
     if (p.passes < 1) p.passes = 1;
     // spread the bits evenly over the passes (narrow digits keep the per-tile scan of the warp tables short)
     const int base = key_bits / p.passes, extra = key_bits % p.passes;
-    for (int i = 0; i < p.passes; ++i) p.bits[i] = base + (i < extra ? 1 : 0);
+    // the wider digits go last: the last pass writes payloads only (8-byte items), so its shorter digit runs
+    // still fill whole sectors; a 9-bit first pass wrote 32-byte key runs at arbitrary offsets (ncu, config 4:
+    // 8.3 GB written for 6.3 GB of items, 6.7 ms against 4.1 ms for the 8-bit second pass)
+    // (widest first: config 4 18.9 ms, config 2 0.298 ms; widest last: 17.2 ms, 0.272 ms)
+    for (int i = 0; i < p.passes; ++i) p.bits[i] = base + (i >= p.passes - extra ? 1 : 0);
     for (int i = 0; i < p.passes; ++i)
         if (p.bits[i] < 1) p.bits[i] = 1;
     const int64_t tiles = (n + kRadixTile - 1) / kRadixTile;
