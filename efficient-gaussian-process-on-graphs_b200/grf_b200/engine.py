@@ -26,6 +26,11 @@ from . import _lib
 from ._lib import GrfGraph, GrfLongRows, GrfPhi, GrfWalkCfg, check
 
 LONG_ROW_THRESHOLD = 256   # rows of Phi / Phi^T with more entries are split into chunks of this size
+# line-pair entries for the merged t = 16 product (csrc/grf_pairs.cu).  Opt-in: on config 2 the pair kernel halves
+# the gather wavefronts (L1 data stage 77 % -> 46 % busy) but not the time -- 44 us per half against 26 us for the
+# tuned 64-byte-row kernel, which it would have to beat by instruction count as well (profiles/README.md)
+PAIR_LAYOUT = os.environ.get("GRF_PAIR_LAYOUT", "0") == "1"
+PAIR_MAX_RATIO = 0.8       # ... when pairing leaves at most this share of the union entries
 UNION_CHUNK = 1024         # rows with more entries are merged (union layout) chunk by chunk
 CHUNK_ORDER = os.environ.get("GRF_CHUNK_ORDER", "1") != "0"   # issue the chunks by the first row they gather
 _MAX_STAGE_BYTES = 16 << 30  # staging budget per walker launch; larger shards are walked in row chunks
@@ -58,13 +63,16 @@ def _small_pinned() -> torch.Tensor:
     """64 bytes of pinned host memory for a count / census that the GPU copies back asynchronously.  Recycled
     (``_recycle_pinned``, by the reader once it has the value): cudaHostAlloc costs ~0.1 ms and serialises with
     the device, and every Phi build needs two or three."""
-    if _free_small_pinned:
-        return _free_small_pinned.pop()
-    return torch.empty(16, dtype=torch.int32, pin_memory=True)
+    if not _free_small_pinned:
+        # one cudaHostAlloc (milliseconds, and it serialises with the device) serves 64 buffers: a caller that keeps
+        # many Phi alive with their counts unread would otherwise pay it once per build
+        slab = torch.empty(16 * 64, dtype=torch.int32, pin_memory=True)
+        _free_small_pinned.extend(slab[i * 16:(i + 1) * 16] for i in range(64))
+    return _free_small_pinned.pop()
 
 
 def _recycle_pinned(buf: Optional[torch.Tensor]) -> None:
-    if buf is not None and len(_free_small_pinned) < 64 and not any(b is buf for b in _free_small_pinned):
+    if buf is not None and len(_free_small_pinned) < 256 and not any(b is buf for b in _free_small_pinned):
         _free_small_pinned.append(buf)
 
 
@@ -585,6 +593,8 @@ class PhiBlocks:
         self._col_counts = None  # int32 [n_cols * L] from the walker (GrfWalkCfg.col_counts), used once by build_transpose
         self.visits = visits
         self._union = None
+        self._pairs = None      # per side: pair row pointers / slot of every union entry (build_pairs)
+        self._pent = None       # on a merged PhiBlocks: the pair entries of (Phi_f, Phi_f^T)
         # sharded matvec: columns to exchange between the ranks, if known up front (tensor of ids or
         # "all"; DeviceGraph.shared_columns); None = the plan finds them with one all-reduce
         self.shared_hint = None
@@ -820,14 +830,42 @@ class PhiBlocks:
         self._union = sides
         return self
 
+    def build_pairs(self) -> "PhiBlocks":
+        """Line pairs of the union rows (csrc/grf_pairs.cu): once per Phi, per side the pair row pointers and the
+        pair slot of every union entry."""
+        self.build_union()
+        if self._pairs is None:
+            L = _lib.lib()
+            dev = self.device
+            out = []
+            for side in self._union:
+                n, n_union = side["n"], side["n_union"]
+                pcnt = torch.empty(max(1, n), dtype=torch.int32, device=dev)
+                check(L.grf_pairs_count(_ptr(side["uptr"]), _ptr(side["uhdr"]), n, _ptr(pcnt), _stream(dev)))
+                pptr = scan_counts(pcnt, n, 1, _lib.ORDER_ROW_MAJOR, i64=False)
+                n_pairs = int(pptr[-1].item())
+                pidx = torch.empty(max(1, n_union), dtype=torch.int32, device=dev)
+                check(L.grf_pairs_index(_ptr(side["uptr"]), _ptr(side["uhdr"]), n, _ptr(pptr), _ptr(pidx),
+                                        _stream(dev)))
+                out.append(dict(pptr=pptr, pidx=pidx, n_pairs=n_pairs, n_union=n_union, n=n))
+            self._pairs = out
+        return self
+
+    @property
+    def pair_ratio(self) -> float:
+        """Pair entries / union entries over both sides (1.0 = no column has its line partner)."""
+        self.build_pairs()
+        return sum(p["n_pairs"] for p in self._pairs) / max(1, sum(p["n_union"] for p in self._pairs))
+
     @property
     def nnz_union(self) -> int:
         self.build_union()
         return self._union[0]["n_union"]
 
-    def merged(self, f, into: Optional["PhiBlocks"] = None) -> "PhiBlocks":
+    def merged(self, f, into: Optional["PhiBlocks"] = None, pairs: bool = False) -> "PhiBlocks":
         """Phi_f as a single-length PhiBlocks (multiply it with f = [1]).  ``into`` re-uses the
-        buffers of an earlier result (same Phi) when the modulator changed."""
+        buffers of an earlier result (same Phi) when the modulator changed.  ``pairs``: also fill the line-pair
+        entries (``into._pent``) that ``grf_pairs_spmm`` multiplies."""
         self.build_union()
         L = _lib.lib()
         dev = self.device
@@ -842,6 +880,14 @@ class PhiBlocks:
             check(L.grf_union_materialize(_ptr(side["task_u0"]), _ptr(side["task_v0"]), side["n_tasks"],
                                           _ptr(side["uhdr"]), _ptr(side["mval"]), _ptr(f), self.n_steps, _ptr(ent),
                                           _stream(dev)))
+        if pairs:
+            self.build_pairs()
+            if into._pent is None:
+                into._pent = [torch.empty((max(1, p["n_pairs"]), 4), dtype=torch.int32, device=dev)
+                              for p in self._pairs]
+            for p, ent, pent in zip(self._pairs, (into.entries, into.tentries), into._pent):
+                check(L.grf_pairs_fill(_ptr(ent), _ptr(p["pidx"]), p["n_union"], p["n_pairs"], _ptr(pent),
+                                       _stream(dev)))
         return into
 
     def _long_rows_of(self, ptr: torch.Tensor, n: int, ent: Optional[torch.Tensor] = None):
@@ -1406,6 +1452,22 @@ class MatvecPlan:
                             and int(torch.unique(self.x2).numel()) == self.x2.numel()) else 0
         self._fn = _lib.lib().grf_phi_matvec
         self._dev = dev
+        # line-pair path (csrc/grf_pairs.cu): the merged product over all rows with t = 16, when no row needs the
+        # long-row split and at least a fifth of the union entries find their line partner
+        self._pair = None
+        if (self.merged and PAIR_LAYOUT and self.t == 16 and self.x2 is None and self.phi._long_fwd is None
+                and all(tb.long is None for tb in self.phi.tblocks) and phi.nnz > 0
+                and phi.pair_ratio <= PAIR_MAX_RATIO):
+            phi.merged(f, into=self.phi, pairs=True)
+            if self.u.stride(0) == 16 and self.u.data_ptr() % 128 == 0:
+                fwd, tr = phi._pairs
+                pent, tpent = self.phi._pent
+                self._pair = phi._pairs
+                self._pair_fn = _lib.lib().grf_pairs_matvec
+                self._pair_u = self.u.data_ptr()
+                self._pair_args = (tr["pptr"].data_ptr(), tpent.data_ptr(), fwd["pptr"].data_ptr(), pent.data_ptr(),
+                                   None if self.x1 is None else self.x1.data_ptr(), self.n1, self.phi.row_lo,
+                                   self.phi.n_rows, self.phi.n_cols)
         self._single = len(self.phi.tblocks) == 1
         self._c = self.phi.c_struct(self.ldu)                                   # all rows (+ the only Phi^T block)
         self._cb = [self.phi.c_struct(self.ldu, block=b) for b in range(len(self.phi.tblocks))]
@@ -1427,7 +1489,7 @@ class MatvecPlan:
 
     def set_modulator(self, f) -> None:
         if self.merged:
-            self.base.merged(f, into=self.phi)
+            self.base.merged(f, into=self.phi, pairs=self._pair is not None)
         else:
             self.f.copy_(torch.as_tensor(f, device=self._dev).detach().to(torch.float32).reshape(-1))
 
@@ -1453,7 +1515,23 @@ class MatvecPlan:
             best.append(ms[1] < 0.97 * ms[0])
         return tuple(best)
 
+    def _call_pairs(self, v, out, which) -> bool:
+        """The halves of the product on the line-pair entries (one C call); False when an operand is not laid out
+        for it (a misaligned view of V, an output with an odd leading dimension)."""
+        if which & 1 and (v.stride(0) != 16 or v.data_ptr() % 128):
+            return False
+        if which & 2 and (out.stride(0) % 4 or out.data_ptr() % 16):
+            return False
+        rc = self._pair_fn(*self._pair_args, None if v is None else v.data_ptr(), self._pair_u,
+                           None if out is None else out.data_ptr(), 0 if out is None else out.stride(0), which,
+                           _stream(self._dev))
+        if rc:
+            check(rc)
+        return True
+
     def _call(self, v, out, which):
+        if self._pair is not None and self._call_pairs(v, out, which):
+            return
         st = _stream(self._dev)
         if which == 3 and self._single and self._gt == self._gf:
             rc = self._fn(ctypes.byref(self._c), _ptr(self.f), _ptr(self.x1), self.n1, _ptr(self.x2), self.n2,

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GRF_B200_ABI_VERSION 5
+#define GRF_B200_ABI_VERSION 6
 
 enum {
     GRF_OK = 0,
@@ -323,6 +323,31 @@ int grf_union_fill(const int32_t *blk_ptr, const uint32_t *mkey, int32_t n_steps
                    int32_t *uhdr /* [nU][2] */, int32_t *task_v0, void *stream);
 int grf_union_materialize(const int32_t *task_u0, const int32_t *task_v0, int64_t n_tasks, const int32_t *uhdr,
                           const float *mval, const float *f, int32_t n_steps, GrfEntry *entries_f, void *stream);
+
+/* Line-pair layout of the merged Phi_f / Phi_f^T for t = 16 (csrc/grf_pairs.cu): union entries of one row whose
+ * columns 2p and 2p+1 share a 128-byte line of X become ONE entry {p, w_even, w_odd, 0} (16 bytes), gathered with
+ * one L1 wavefront by 8 lanes.  Pays on lattices, rings and any numbering with locality; the caller compares
+ * n_pairs with n_union and keeps grf_phi_matvec otherwise.  Same role as grf_phi_matvec for the CG steady state
+ * (sparse_lo.py:16-18 x 2L), whole halves only:
+ *   grf_pairs_count  pcnt[r] = pair entries of union row r (uent: the union headers or the merged entries --
+ *                    only the column field is read); caller scans -> pptr [n_rows + 1]
+ *   grf_pairs_index  pidx[u] = pair slot of union entry u            (both once per Phi)
+ *   grf_pairs_fill   pent[n_pairs][4] from the merged entries of one modulator value
+ *   grf_pairs_spmm   y[k, 0:16] = sum_{pairs of row k} w_even * x[2p, :] + w_odd * x[2p+1, :]; x [n_x][16] with
+ *                    leading dimension 16 and 128-byte alignment; row_ids (or NULL) as in grf_phi_matvec */
+int grf_pairs_count(const int32_t *uptr, const GrfEntry *uent, int64_t n_rows, int32_t *pcnt, void *stream);
+int grf_pairs_index(const int32_t *uptr, const GrfEntry *uent, int64_t n_rows, const int32_t *pptr, int32_t *pidx,
+                    void *stream);
+int grf_pairs_fill(const GrfEntry *uent, const int32_t *pidx, int64_t n_union, int64_t n_pairs, int32_t *pent,
+                   void *stream);
+int grf_pairs_spmm(const int32_t *pptr, const int32_t *pent, const int32_t *row_ids, int64_t n_tasks, int64_t row_lo,
+                   int64_t n_rows, const float *x, int64_t n_x, float *y, int64_t ldy, void *stream);
+
+/* both halves on pair entries in one call: which & 1: u = Phi_f^T v (tpptr / tpent: the transposed side, n_cols
+ * rows, v [n_rows][16]);  which & 2: out = Phi_f[x1] u (u [n_cols][16]) */
+int grf_pairs_matvec(const int32_t *tpptr, const int32_t *tpent, const int32_t *pptr, const int32_t *pent,
+                     const int32_t *x1, int64_t n1, int64_t row_lo, int64_t n_rows, int64_t n_cols, const float *v,
+                     float *u, float *out, int64_t ldo, int32_t which, void *stream);
 
 /* Per-length reduction for the modulator gradient (what upstream
  * _bilinear_derivative yields for sparse_grf_kernel.py:51-62):

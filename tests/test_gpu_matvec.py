@@ -660,3 +660,52 @@ def test_union_layout_with_rows_longer_than_one_chunk(env):
     a = phi.plan(f, 5, merged=False)(v)
     b = phi.plan(f, 5, merged=True)(v)
     assert float((a - b).abs().max()) <= RTOL * float(a.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(37, 29), (64, 48)])
+def test_line_pair_layout_multiplies_like_the_merged_entries(env, shape, monkeypatch):
+    """csrc/grf_pairs.cu: on a lattice most columns of a row have their line partner (col ^ 1); the t = 16 merged
+    product then runs on pair entries.  Same result as the plain merged product (same weights, one more
+    rounding order), as the per-length product and as float64; odd row counts, a row subset x1, modulator updates."""
+    torch, eng = env["torch"], env["eng"]
+    lap = env["o"].normalized_laplacian_sparse(grid_graph(*shape))
+    n = lap.shape[0]
+    g = eng.DeviceGraph.from_scipy(lap)
+    phi = eng.build_phi_blocks(g, eng.WalkConfig(30, 0.1, 4, seed=3))
+    assert phi.pair_ratio < 0.75, phi.pair_ratio
+    f = torch.tensor([1.0, -0.6, 0.3, 0.2], device="cuda")
+    v = torch.randn(n, 16, device="cuda")
+    plain = phi.plan(f, 16, merged=True)
+    assert plain._pair is None or eng.PAIR_LAYOUT            # opt-in (GRF_PAIR_LAYOUT=1)
+    want = plain(v)
+    monkeypatch.setattr(eng, "PAIR_LAYOUT", True)
+    plan = phi.plan(f, 16, merged=True)
+    assert plan._pair is not None
+    got = plan(v)
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= RTOL * scale
+    mats = phi.to_scipy_steps()
+    pf = sum(float(fl) * m.astype(np.float64) for fl, m in zip(f.cpu().numpy(), mats))
+    ref = pf @ (pf.T @ v.cpu().numpy().astype(np.float64))
+    assert _close(got.cpu().numpy(), ref)
+    # a row subset on the output side, and a new modulator through the same plan
+    x1 = torch.arange(1, n, 3, device="cuda")
+    sub = phi.plan(f, 16, x1=x1, merged=True)
+    assert sub._pair is not None
+    assert _close(sub(v).cpu().numpy(), ref[x1.cpu().numpy()])
+    f2 = torch.tensor([0.5, 0.25, -1.0, 0.7], device="cuda")
+    plan.set_modulator(f2)
+    pf2 = sum(float(fl) * m.astype(np.float64) for fl, m in zip(f2.cpu().numpy(), mats))
+    assert _close(plan(v).cpu().numpy(), pf2 @ (pf2.T @ v.cpu().numpy().astype(np.float64)))
+    # operands the pair kernel cannot take (a misaligned view of V) fall back to the merged entries
+    big = torch.randn(n + 1, 16, device="cuda")
+    assert _close(plan(big[1:]).cpu().numpy(), pf2 @ (pf2.T @ big[1:].cpu().numpy().astype(np.float64)))
+
+
+def test_line_pair_layout_is_not_chosen_on_power_law_graphs(env, monkeypatch):
+    torch, eng = env["torch"], env["eng"]
+    monkeypatch.setattr(eng, "PAIR_LAYOUT", True)
+    lap = env["o"].normalized_laplacian_sparse(powerlaw_graph(3000, 20000, 4))
+    phi = eng.build_phi_blocks(eng.DeviceGraph.from_scipy(lap), eng.WalkConfig(20, 0.1, 3, seed=1))
+    plan = phi.plan(torch.ones(3, device="cuda"), 16, merged=True)
+    assert plan._pair is None
