@@ -890,34 +890,25 @@ class PhiBlocks:
                                        _stream(dev)))
         return into
 
-    def _long_rows_of(self, ptr: torch.Tensor, n: int, ent: Optional[torch.Tensor] = None):
-        """Chunk table for the rows of one side that are longer than LONG_ROW_THRESHOLD (or None).  With the
+    def _long_rows_of(self, ptr: torch.Tensor, n: int, ent: Optional[torch.Tensor], n_long: int, n_chunks: int):
+        """Chunk table for the rows of one side that are longer than LONG_ROW_THRESHOLD (or None), built on the
+        device from the census counts (``grf_long_rows_build``: no host round trip, two launches).  With the
         side's entries the chunks also get an issue order: by the first X row they gather (segments are sorted,
         so a chunk reads an ascending run of rows) -- the chunks in flight then share a window of X in L2."""
-        if n == 0 or self.nnz == 0:
+        if n == 0 or self.nnz == 0 or n_long == 0:
             return None
-        L, T = self.n_steps, LONG_ROW_THRESHOLD
-        row_b = ptr[0:n * L:L].to(torch.int64)
-        row_e = ptr[L:n * L + 1:L].to(torch.int64)
-        lens = row_e - row_b
-        rows = torch.nonzero(lens > T).flatten()
-        if rows.numel() == 0:
-            return None
-        nch = (lens[rows] + T - 1) // T
-        chunk_ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=ptr.device)
-        torch.cumsum(nch, 0, out=chunk_ptr[1:])
-        n_chunks = int(chunk_ptr[-1].item())
-        owner = torch.repeat_interleave(torch.arange(rows.numel(), device=ptr.device), nch)
-        local = torch.arange(n_chunks, device=ptr.device) - chunk_ptr[owner]
-        cb = row_b[rows][owner] + local * T
-        ce = torch.minimum(cb + T, row_e[rows][owner])
-        bounds = torch.stack([cb, ce], dim=1).to(torch.int32).contiguous()
-        order = None
-        if ent is not None and CHUNK_ORDER and n_chunks > 1:
-            first = ent[:, 0][cb] & ((1 << 27) - 1)
-            order = torch.argsort(first, stable=True).to(torch.int32).contiguous()
-        return dict(rows=rows.to(torch.int32).contiguous(), chunk_ptr=chunk_ptr.to(torch.int32).contiguous(),
-                    bounds=bounds, n_long=int(rows.numel()), n_chunks=n_chunks, order=order)
+        dev = ptr.device
+        rows = torch.empty(n_long, dtype=torch.int32, device=dev)
+        chunk_ptr = torch.empty(n_long + 1, dtype=torch.int32, device=dev)
+        bounds = torch.empty((n_chunks, 2), dtype=torch.int32, device=dev)
+        ordered = ent is not None and CHUNK_ORDER and n_chunks > 1
+        first = torch.empty(n_chunks, dtype=torch.int32, device=dev) if ordered else None
+        ticket = torch.empty(1, dtype=torch.int64, device=dev)
+        check(_lib.lib().grf_long_rows_build(_ptr(ptr), _ptr(ent), n, self.n_steps, LONG_ROW_THRESHOLD, n_long,
+                                             n_chunks, _ptr(ticket), _ptr(rows), _ptr(chunk_ptr), _ptr(bounds),
+                                             _ptr(first), _stream(dev)))
+        order = torch.argsort(first).to(torch.int32) if ordered else None
+        return dict(rows=rows, chunk_ptr=chunk_ptr, bounds=bounds, n_long=n_long, n_chunks=n_chunks, order=order)
 
     def build_long_rows(self) -> "PhiBlocks":
         """One-off matvec preparation: which rows / columns need the long-row split, and the list of
@@ -929,18 +920,18 @@ class PhiBlocks:
             self._long_fwd = None
             if self.nnz == 0:
                 return self
-            any_long_fwd = False
+            fwd_long = fwd_chunks = 0      # rows of Phi: summed over the row blocks of Phi^T
             for tb in self.tblocks:
                 if tb.nnz == 0:
                     continue
                 self._start_census(tb)
                 host, done, base = tb.census
                 done.synchronize()
-                long_f, _, _, long_t, _, cols_used = host.tolist()
+                long_f, chunks_f, _, long_t, chunks_t, cols_used = host.tolist()
                 tb.census = (host.clone(), done, None)      # the values stay; the pinned buffer goes back to the pool
                 _recycle_pinned(base)
-                any_long_fwd = any_long_fwd or bool(long_f)
-                tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols, tb.tentries) if long_t else None
+                fwd_long, fwd_chunks = fwd_long + long_f, fwd_chunks + chunks_f
+                tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols, tb.tentries, long_t, chunks_t)
                 if len(self.tblocks) == 1:
                     # columns this (row) shard touches: worth a list when most of the N columns are empty
                     if cols_used < 0.75 * self.n_cols:
@@ -950,8 +941,7 @@ class PhiBlocks:
                     else:
                         tb.touched = None
                     tb.tcols_cap = None
-            if any_long_fwd:
-                self._long_fwd = self._long_rows_of(self.blk_ptr, self.n_rows, self.entries)
+            self._long_fwd = self._long_rows_of(self.blk_ptr, self.n_rows, self.entries, fwd_long, fwd_chunks)
         return self
 
     def _long_struct(self, side: Optional[dict], cache: dict, ld: int):
