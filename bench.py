@@ -92,7 +92,7 @@ def workload_config(n_gpus, stats, scale, edges):
                     f"{1 << scale} nodes, >= {edges / 1e6:.0f} M undirected edges), GRF Phi build node-sharded over "
                     f"{n_gpus} x B200, walks_per_node=100, max_walk_length=5, p_halt=0.1, learnable modulator, t=16",
         "graph": stats, "walks_per_node": W, "max_walk_length": L, "p_halt": P_HALT, "rhs_columns": T_RHS,
-        "sharding": f"start nodes in {n_gpus} contiguous range(s) of equal estimated work (strong scaling), CSR "
+        "sharding": f"start nodes in {n_gpus} contiguous range(s) of equal estimated cost (walks + entries of a 25-walk pilot; strong scaling), CSR "
                     f"walk graph replicated",
         "l2": "not flushed: every phase streams 4-17 GB (edge records 2.3 GB, staging 13 GB, Phi entries 4.2 GB), "
               "far beyond the 126 MB L2; config2 section: flushed (256 MB write) before every timed phase",
@@ -290,10 +290,12 @@ def run_gpu(args):
     torch.cuda.synchronize(dev)
     stats["generated_on_device_s"] = round(time.perf_counter() - t_gen, 2)
     n = graph.n_nodes
-    bounds = sharding.balanced_bounds(graph, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
     cfg = engine.WalkConfig(W, P_HALT, L, seed=SEED)
     graph.edge_records(P_HALT)                           # per graph and p_halt, like the Laplacian itself
+    # sharding decision (setup, like the graph itself): equal estimated cost per rank from a 25-walk pilot
+    bounds = sharding.balanced_bounds(graph, world, row_cost=sharding.pilot_row_cost(graph, cfg) if world > 1 else None)
+    torch.cuda.empty_cache()
+    lo, hi = bounds[rank], bounds[rank + 1]
     torch.manual_seed(42)
     f = torch.randn(L).to(dev)                           # learnable modulator init, sparse_grf_kernel.py:14-17
 
