@@ -681,12 +681,27 @@ __global__ void __launch_bounds__(256) edge_records_kernel(const int32_t *__rest
     for (int64_t r = warp0; r < n_nodes; r += nwarps) {
         const int32_t b = row_ptr[r], e = row_ptr[r + 1];
         const double deg = (double)(e - b);
-        for (int32_t i = b + lane; i < e; i += 32) {
-            GrfEdge ed;
-            ed.scaled = __ddiv_rn(__dmul_rn(deg, val[i]), one_minus_p);
-            ed.col = col[i];
-            ed.pad = 0;
-            out[i] = ed;
+        // eight batches of a row in flight (a hub row of 175 303 neighbours is 5 500 batches for one warp)
+        constexpr int kU = 8;
+        for (int32_t i0 = b + lane; i0 < e; i0 += 32 * kU) {
+            double v[kU];
+            int32_t c[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int32_t i = i0 + 32 * u;
+                v[u] = i < e ? val[i] : 0.0;
+                c[u] = i < e ? col[i] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int32_t i = i0 + 32 * u;
+                if (i >= e) continue;
+                GrfEdge ed;
+                ed.scaled = __ddiv_rn(__dmul_rn(deg, v[u]), one_minus_p);
+                ed.col = c[u];
+                ed.pad = 0;
+                out[i] = ed;
+            }
         }
     }
 }
