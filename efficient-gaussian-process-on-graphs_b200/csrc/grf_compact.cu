@@ -399,7 +399,7 @@ namespace grf {
 // ids grow with the slot (chunk_ptr ascending) whatever order the rows arrive in; the table's order differs from
 // run to run, the sums do not (every row adds its own chunks in order).
 __global__ void __launch_bounds__(256) long_rows_claim_kernel(const int32_t *__restrict__ ptr, int64_t n_rows,
-                                                              int32_t L, int32_t threshold,
+                                                              int32_t L, int32_t threshold, int32_t chunk,
                                                               unsigned long long *__restrict__ ticket,
                                                               int32_t *__restrict__ rows,
                                                               int32_t *__restrict__ chunk_ptr, int32_t n_long,
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) long_rows_claim_kernel(const int32_t *__r
          r += (int64_t)gridDim.x * blockDim.x) {
         const int32_t len = ptr[(r + 1) * L] - ptr[r * L];
         if (len > threshold) {
-            const unsigned long long nch = (unsigned long long)((len + threshold - 1) / threshold);
+            const unsigned long long nch = (unsigned long long)((len + chunk - 1) / chunk);
             const unsigned long long old = atomicAdd(ticket, (1ull << 32) | nch);
             const int32_t slot = (int32_t)(old >> 32);
             if (slot < n_long) {
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) long_rows_claim_kernel(const int32_t *__r
 
 // bounds[k] = entry range of chunk k; first[k] = the first X row it gathers (its issue key)
 __global__ void __launch_bounds__(256) long_rows_chunks_kernel(const int32_t *__restrict__ ptr, int32_t L,
-                                                               int32_t threshold, const GrfEntry *__restrict__ ent,
+                                                               int32_t chunk, const GrfEntry *__restrict__ ent,
                                                                const int32_t *__restrict__ rows,
                                                                const int32_t *__restrict__ chunk_ptr, int32_t n_long,
                                                                int32_t n_chunks, int2 *__restrict__ bounds,
@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(256) long_rows_chunks_kernel(const int32_t *__
             if (__ldg(chunk_ptr + mid) <= k) lo = mid; else hi = mid;
         }
         const int64_t r = rows[lo];
-        const int32_t b = ptr[r * L] + (k - __ldg(chunk_ptr + lo)) * threshold;
-        const int32_t e = min(b + threshold, ptr[(r + 1) * L]);
+        const int32_t b = ptr[r * L] + (k - __ldg(chunk_ptr + lo)) * chunk;
+        const int32_t e = min(b + chunk, ptr[(r + 1) * L]);
         bounds[k] = make_int2(b, e);
         if (first) first[k] = (int32_t)((uint32_t)ent[b].col & kColMask);
     }
@@ -443,12 +443,14 @@ __global__ void __launch_bounds__(256) long_rows_chunks_kernel(const int32_t *__
 }  // namespace grf
 
 extern "C" int grf_long_rows_build(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
-                                   int32_t threshold, int32_t n_long, int32_t n_chunks, unsigned long long *ticket,
+                                   int32_t threshold, int32_t chunk, int32_t n_long, int32_t n_chunks,
+                                   unsigned long long *ticket,
                                    int32_t *rows, int32_t *chunk_ptr, int32_t *bounds, int32_t *first,
                                    void *stream) {
     GRF_ON_STREAM_DEVICE(stream, rows);
     using namespace grf;
-    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && threshold >= 1 && n_long >= 0 && n_chunks >= n_long,
+    GRF_REQUIRE(n_rows >= 0 && n_steps >= 1 && threshold >= 1 && chunk >= 1 && chunk <= threshold && n_long >= 0 &&
+                    n_chunks >= n_long,
                 "grf_long_rows_build: bad shape");
     if (n_long == 0) return GRF_OK;
     GRF_REQUIRE(blk_ptr && ticket && rows && chunk_ptr && bounds, "grf_long_rows_build: null buffer");
@@ -457,12 +459,12 @@ extern "C" int grf_long_rows_build(const int32_t *blk_ptr, const GrfEntry *entri
     GRF_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
     int64_t g = (n_rows + 255) / 256;
     if (g > (int64_t)kSmCount * 16) g = (int64_t)kSmCount * 16;
-    long_rows_claim_kernel<<<(int)g, 256, 0, st>>>(blk_ptr, n_rows, n_steps, threshold, ticket, rows, chunk_ptr, n_long,
-                                                   n_chunks);
+    long_rows_claim_kernel<<<(int)g, 256, 0, st>>>(blk_ptr, n_rows, n_steps, threshold, chunk, ticket, rows, chunk_ptr,
+                                                   n_long, n_chunks);
     GRF_CUDA_OK(cudaGetLastError());
     int64_t gc = ((int64_t)n_chunks + 255) / 256;
     if (gc > (int64_t)kSmCount * 16) gc = (int64_t)kSmCount * 16;
-    long_rows_chunks_kernel<<<(int)gc, 256, 0, st>>>(blk_ptr, n_steps, threshold, entries, rows, chunk_ptr, n_long,
+    long_rows_chunks_kernel<<<(int)gc, 256, 0, st>>>(blk_ptr, n_steps, chunk, entries, rows, chunk_ptr, n_long,
                                                      n_chunks, (int2 *)bounds, first);
     return check_cuda(cudaGetLastError(), "long_rows kernels launch");
 }

@@ -132,7 +132,7 @@ def lib():
     L.grf_union_fill.restype = i32
     L.grf_union_fill.argtypes = [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp]
     L.grf_long_rows_build.restype = i32
-    L.grf_long_rows_build.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.grf_long_rows_build.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.grf_pairs_count.restype = i32
     L.grf_pairs_count.argtypes = [vp, vp, i64, vp, vp]
     L.grf_pairs_index.restype = i32

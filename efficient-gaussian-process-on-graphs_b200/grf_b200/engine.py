@@ -32,6 +32,9 @@ LONG_ROW_THRESHOLD = 256   # rows of Phi / Phi^T with more entries are split int
 PAIR_LAYOUT = os.environ.get("GRF_PAIR_LAYOUT", "0") == "1"
 PAIR_MAX_RATIO = 0.8       # ... when pairing leaves at most this share of the union entries
 UNION_CHUNK = 1024         # rows with more entries are merged (union layout) chunk by chunk
+# entries per chunk of a long COLUMN (<= LONG_ROW_THRESHOLD).  Smaller chunks span fewer rows of V but cost a
+# partial-sum row each: config 4 Phi^T V 5.41 ms at 256, 5.49 at 128, 6.10 at 64
+T_CHUNK = int(os.environ.get("GRF_T_CHUNK", str(LONG_ROW_THRESHOLD)))
 CHUNK_ORDER = os.environ.get("GRF_CHUNK_ORDER", "1") != "0"   # issue the chunks by the first row they gather
 _MAX_STAGE_BYTES = 16 << 30  # staging budget per walker launch; larger shards are walked in row chunks
 _LAZY_ENTRY_BYTES = 1 << 30  # up to this bound the Phi entries are allocated by capacity (no host wait for the count)
@@ -890,7 +893,8 @@ class PhiBlocks:
                                        _stream(dev)))
         return into
 
-    def _long_rows_of(self, ptr: torch.Tensor, n: int, ent: Optional[torch.Tensor], n_long: int, n_chunks: int):
+    def _long_rows_of(self, ptr: torch.Tensor, n: int, ent: Optional[torch.Tensor], n_long: int, n_chunks: int,
+                      chunk: int = LONG_ROW_THRESHOLD):
         """Chunk table for the rows of one side that are longer than LONG_ROW_THRESHOLD (or None), built on the
         device from the census counts (``grf_long_rows_build``: no host round trip, two launches).  With the
         side's entries the chunks also get an issue order: by the first X row they gather (segments are sorted,
@@ -898,13 +902,17 @@ class PhiBlocks:
         if n == 0 or self.nnz == 0 or n_long == 0:
             return None
         dev = ptr.device
+        if chunk != LONG_ROW_THRESHOLD:        # the census counted chunks of LONG_ROW_THRESHOLD entries
+            nL = self.n_steps
+            lens = (ptr[nL:n * nL + 1:nL] - ptr[0:n * nL:nL]).to(torch.int64)
+            n_chunks = int(((lens[lens > LONG_ROW_THRESHOLD] + chunk - 1) // chunk).sum().item())
         rows = torch.empty(n_long, dtype=torch.int32, device=dev)
         chunk_ptr = torch.empty(n_long + 1, dtype=torch.int32, device=dev)
         bounds = torch.empty((n_chunks, 2), dtype=torch.int32, device=dev)
         ordered = ent is not None and CHUNK_ORDER and n_chunks > 1
         first = torch.empty(n_chunks, dtype=torch.int32, device=dev) if ordered else None
         ticket = torch.empty(1, dtype=torch.int64, device=dev)
-        check(_lib.lib().grf_long_rows_build(_ptr(ptr), _ptr(ent), n, self.n_steps, LONG_ROW_THRESHOLD, n_long,
+        check(_lib.lib().grf_long_rows_build(_ptr(ptr), _ptr(ent), n, self.n_steps, LONG_ROW_THRESHOLD, chunk, n_long,
                                              n_chunks, _ptr(ticket), _ptr(rows), _ptr(chunk_ptr), _ptr(bounds),
                                              _ptr(first), _stream(dev)))
         order = torch.argsort(first).to(torch.int32) if ordered else None
@@ -931,7 +939,7 @@ class PhiBlocks:
                 tb.census = (host.clone(), done, None)      # the values stay; the pinned buffer goes back to the pool
                 _recycle_pinned(base)
                 fwd_long, fwd_chunks = fwd_long + long_f, fwd_chunks + chunks_f
-                tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols, tb.tentries, long_t, chunks_t)
+                tb.long = self._long_rows_of(tb.tblk_ptr, self.n_cols, tb.tentries, long_t, chunks_t, T_CHUNK)
                 if len(self.tblocks) == 1:
                     # columns this (row) shard touches: worth a list when most of the N columns are empty
                     if cols_used < 0.75 * self.n_cols:

@@ -232,12 +232,13 @@ int grf_count_from_steps(const int64_t *offsets_step_major, int64_t n_rows, int3
 int grf_row_census(const int32_t *blk_ptr, int64_t n_rows, int32_t n_steps, int32_t threshold, int32_t *census,
                    void *stream);
 
-/* The chunk table of GrfLongRows on the device, sized by grf_row_census()'s {long rows, chunks}: rows [n_long],
+/* The chunk table of GrfLongRows on the device: rows longer than `threshold` entries in chunks of `chunk` (<=
+ * threshold) entries; n_long / n_chunks from grf_row_census() when chunk == threshold.  rows [n_long],
  * chunk_ptr [n_long + 1], chunk_bounds [n_chunks][2] and, with entries, first [n_chunks] = the first X row each
  * chunk gathers (sort it to get chunk_order).  ticket: one device uint64 of scratch.  The order of the rows in
  * the table is not deterministic; the products are (a row adds its own chunks in order). */
 int grf_long_rows_build(const int32_t *blk_ptr, const GrfEntry *entries, int64_t n_rows, int32_t n_steps,
-                        int32_t threshold, int32_t n_long, int32_t n_chunks, unsigned long long *ticket,
+                        int32_t threshold, int32_t chunk, int32_t n_long, int32_t n_chunks, unsigned long long *ticket,
                         int32_t *rows, int32_t *chunk_ptr, int32_t *bounds, int32_t *first, void *stream);
 
 /* Multi-GPU row of the path (no reference counterpart: its fork pool merges dictionaries on the host,
