@@ -709,3 +709,41 @@ def test_line_pair_layout_is_not_chosen_on_power_law_graphs(env, monkeypatch):
     phi = eng.build_phi_blocks(eng.DeviceGraph.from_scipy(lap), eng.WalkConfig(20, 0.1, 3, seed=1))
     plan = phi.plan(torch.ones(3, device="cuda"), 16, merged=True)
     assert plan._pair is None
+
+
+def test_threaded_pinned_upload_equals_the_plain_copy(env, monkeypatch):
+    """engine._upload: large host arrays leave pageable memory through pinned slots filled by several host threads
+    (chunks in flight on per-thread streams); forced here on a small graph, odd sizes included."""
+    torch, eng = env["torch"], env["eng"]
+    adj = random_graph(5000, 40011, 3, weighted=True)
+    plain = eng.DeviceGraph.from_scipy(adj)
+    monkeypatch.setattr(eng, "_UPLOAD_MIN", 1 << 10)
+    monkeypatch.setattr(eng, "_UPLOAD_CHUNK", 7 << 10)          # many chunks per array, the last one partial
+    eng._upload_state.clear()
+    try:
+        threaded = eng.DeviceGraph.from_scipy(adj)
+        for a, b in ((plain.row_ptr, threaded.row_ptr), (plain.col_idx, threaded.col_idx), (plain.val, threaded.val)):
+            assert torch.equal(a, b)
+    finally:
+        eng._upload_state.clear()                                  # slots of the test's chunk size must not survive
+
+
+def test_pilot_balanced_shards_even_out_the_entries(env):
+    """sharding.pilot_row_cost / balanced_bounds: contiguous, covering, and on a power-law graph closer to equal
+    entries per shard than the degree-only estimate."""
+    torch, eng = env["torch"], env["eng"]
+    from grf_b200 import sharding, synth
+
+    g, _ = synth.rmat_walk_graph(15, 300_000, seed=2, device=torch.device("cuda", 0))
+    cfg = eng.WalkConfig(60, 0.1, 4, seed=3)
+    full = eng.build_phi_blocks(g, cfg, transpose=False)
+    ptr = full.blk_ptr.cpu().numpy().astype(np.int64)[::4]
+
+    def spread(bounds):
+        assert bounds[0] == 0 and bounds[-1] == g.n_nodes and all(a <= b for a, b in zip(bounds, bounds[1:]))
+        nnz = np.array([ptr[b] - ptr[a] for a, b in zip(bounds, bounds[1:])], dtype=float)
+        return nnz.max() / nnz.mean()
+
+    by_degree = spread(sharding.balanced_bounds(g, 8))
+    by_pilot = spread(sharding.balanced_bounds(g, 8, row_cost=sharding.pilot_row_cost(g, cfg, pilot_walks=15)))
+    assert by_pilot < by_degree and by_pilot < 1.15, (by_degree, by_pilot)
