@@ -564,7 +564,9 @@ def run_gpu(args):
             "gpu_launches": None,
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
-        line["gpu_launches"] = count_launches(line, world, measured_launches)
+        detail = count_launches(line, world, measured_launches)
+        line["gpu_launches"] = int(detail["timed_region"])      # kernels of libgrf_b200.so inside the timed region
+        line["gpu_launches_detail"] = detail
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
         print(json.dumps(line))
