@@ -747,3 +747,65 @@ def test_pilot_balanced_shards_even_out_the_entries(env):
     by_degree = spread(sharding.balanced_bounds(g, 8))
     by_pilot = spread(sharding.balanced_bounds(g, 8, row_cost=sharding.pilot_row_cost(g, cfg, pilot_walks=15)))
     assert by_pilot < by_degree and by_pilot < 1.15, (by_degree, by_pilot)
+
+
+def test_config4_full_size_properties(env):
+    """BASELINE config 4 at full size (R-MAT 2^22 nodes, >= 70 M edges, W = 100, L = 5, t = 16), through
+    size-independent properties: M_0 = I, Phi^T is a permutation of Phi (sums of a hash of (row, column, length,
+    value) over both layouts, and every segment row-sorted on a sample), the product is linear and symmetric
+    (<a, K b> = <K a, b>), the union layout multiplies like the per-length blocks, and a row shard rebuilt on its
+    own reproduces its rows bit for bit (counter-based draws)."""
+    torch, eng = env["torch"], env["eng"]
+    from grf_b200 import synth
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 << 30:
+        pytest.skip("needs ~50 GB of device memory")
+    dev = torch.device("cuda", 0)
+    g, stats = synth.rmat_walk_graph(22, 70_000_000, seed=0, device=dev)
+    assert stats["n_nodes"] == 1 << 22 and stats["undirected_edges"] >= 70_000_000
+    cfg = eng.WalkConfig(100, 0.1, 5, seed=42)
+    phi = eng.build_phi_blocks(g, cfg)
+    n, L, mask = phi.n_rows, 5, (1 << 27) - 1
+    ptr = phi.blk_ptr.view(-1)[:-1].view(n, L)
+    assert bool((ptr[:, 1] - ptr[:, 0] == 1).all())
+    first = phi.entries[ptr[:, 0].long()]
+    assert bool((first[:, 0] == torch.arange(n, device=dev, dtype=torch.int32)).all())
+    assert bool((first[:, 1].view(torch.float32) == 1.0).all())                       # M_0 = I exactly
+    assert int(phi.tblk_ptr[-1]) == phi.nnz > 500_000_000
+
+    def digest(ptr_all, ent, rows_are_owner):
+        # sum over entries of a 61-bit mix of (row, column, length, value bits); order-independent
+        owner = torch.repeat_interleave(torch.arange(ptr_all.numel() - 1, device=dev),
+                                        (ptr_all[1:] - ptr_all[:-1]).long(), output_size=ent.shape[0]) // L
+        other = (ent[:, 0] & mask).long()
+        step = (ent[:, 0] >> 27).long() & 31
+        row, col = (owner, other) if rows_are_owner else (other, owner)
+        h = (row * 1000003 + col) * 31 + step
+        h = (h * 2654435761 + ent[:, 1].long() * 97) & ((1 << 61) - 1)
+        return int(h.sum() & ((1 << 62) - 1)), int((h ^ (h >> 17)).sum() & ((1 << 62) - 1))
+
+    assert digest(phi.blk_ptr, phi.entries, True) == digest(phi.tblk_ptr, phi.tentries, False)
+    tptr = phi.tblk_ptr
+    seg = (tptr[1:] - tptr[:-1])
+    for s in torch.topk(seg, 3).indices.tolist() + torch.randint(0, seg.numel(), (200,), device=dev).tolist():
+        r = phi.tentries[int(tptr[s]):int(tptr[s + 1]), 0] & mask
+        assert bool((r[1:] > r[:-1]).all())
+    gen = torch.Generator(device=dev).manual_seed(1)
+    f = torch.randn(L, device=dev, generator=gen)
+    a = torch.randn(n, 16, device=dev, generator=gen)
+    b = torch.randn(n, 16, device=dev, generator=gen)
+    plan = phi.plan(f, 16, merged=False)
+    ka, kb = plan(a).clone(), plan(b).clone()
+    lhs, rhs = float((b.double() * ka.double()).sum()), float((a.double() * kb.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs))
+    kab = plan(2.5 * a + b)
+    assert float((kab - (2.5 * ka + kb)).abs().max()) <= RTOL * float(kab.abs().max())
+    merged = phi.plan(f, 16, merged=True)(a)
+    assert float((merged - ka).abs().max()) <= RTOL * float(ka.abs().max())
+    del plan, merged, kab, kb
+    lo, hi = 1_000_000, 1_050_000
+    part = eng.build_phi_blocks(g, cfg, lo, hi, transpose=False)
+    b0, b1 = int(phi.blk_ptr[lo * L]), int(phi.blk_ptr[hi * L])
+    assert torch.equal(part.entries, phi.entries[b0:b1])
+    assert torch.equal(part.blk_ptr, phi.blk_ptr[lo * L:hi * L + 1] - b0)
