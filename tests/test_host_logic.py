@@ -169,3 +169,29 @@ def test_step_matrix_caches_plain_list_and_dict_keyed(tmp_path):
         pickle.dump({"something": 1}, fh)
     with pytest.raises(KeyError):
         GraphPreprocessor.load_step_matrices(str(tmp_path / "other.pkl"))
+
+
+def test_balanced_bounds_follow_the_cost_estimate():
+    """sharding.balanced_bounds cuts contiguous start-node ranges at the equal-cost quantiles (host logic: plain
+    torch ops, runs on CPU tensors): degree-only estimate, and a per-row cost such as pilot_row_cost's."""
+    import types
+
+    import torch
+    from grf_b200 import sharding
+
+    n = 1000
+    deg = torch.ones(n, dtype=torch.int32)
+    deg[600:] = 0                                             # the tail is isolated: 0.15 of a walking node each
+    graph = types.SimpleNamespace(n_nodes=n, row_ptr=torch.cat([torch.zeros(1, dtype=torch.int32),
+                                                                 torch.cumsum(deg, 0).to(torch.int32)]))
+    b = sharding.balanced_bounds(graph, 4)
+    assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:])) and len(b) == 5
+    w = torch.where(deg > 0, 1.0, 0.15).double()
+    loads = [float(w[x:y].sum()) for x, y in zip(b, b[1:])]
+    assert max(loads) - min(loads) <= 1.0 + 1e-9              # within one node's weight of each other
+    assert sharding.balanced_bounds(graph, 1) == [0, n]
+    cost = torch.zeros(n, dtype=torch.float64)
+    cost[:100] = 9.0                                          # a hub region: ten times the cost per row
+    cost[100:] = 1.0
+    b2 = sharding.balanced_bounds(graph, 2, row_cost=cost)
+    assert b2[0] == 0 and b2[2] == n and 95 <= b2[1] <= 105   # half of the cost sits in the first 100 rows
