@@ -92,9 +92,68 @@ __global__ void __launch_bounds__(kExThreads, 1) exchange_sum_kernel(const Excha
     cross_rank_barrier(a, 1);  // every rank's slice has landed in this rank's U
 }
 
+// The same exchange through the NVSwitch (NVLS): `mc` is the MULTICAST address of U (every rank's copy behind one
+// pointer).  multimem.ld_reduce has the switch read all copies of a vector and return their sum -- 1/G of U
+// enters this GPU instead of (G-1)/G -- and multimem.st writes the sum to every copy with one store.  Each slice
+// is reduced by one rank and multicast, so all copies still come out bit-identical.
+__device__ __forceinline__ float4 mc_ld_reduce(const float4 *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float4 *mc, const float4 &v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kExThreads, 1) exchange_nvls_kernel(const ExchangeArgs a, float *mc_u) {
+    cross_rank_barrier(a, 0);  // every rank's partial U_g is complete and visible
+    const int64_t lo = a.n_vec * a.rank / a.world, hi = a.n_vec * (a.rank + 1) / a.world;
+    const int64_t stride = (int64_t)gridDim.x * kExThreads;
+    float4 *mc = reinterpret_cast<float4 *>(mc_u);
+    for (int64_t i0 = lo + (int64_t)blockIdx.x * kExThreads + threadIdx.x; i0 < hi; i0 += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * stride < hi) v[k] = mc_ld_reduce(mc + i0 + k * stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * stride < hi) mc_st(mc + i0 + k * stride, v[k]);
+    }
+    cross_rank_barrier(a, 1);  // every rank's slice has landed in this rank's U
+}
+
 }  // namespace grf
 
 using namespace grf;
+
+extern "C" int grf_exchange_sum_nvls(float *multicast_u, uint32_t *const *peer_flags, int32_t world, int32_t rank,
+                                     int64_t n_floats, uint32_t epoch, void *stream) {
+    GRF_ON_STREAM_DEVICE(stream, (peer_flags && rank >= 0 && rank < world ? peer_flags[rank] : nullptr));
+    GRF_REQUIRE(multicast_u && peer_flags, "grf_exchange_sum_nvls: null pointer");
+    GRF_REQUIRE(world >= 1 && world <= kExMaxWorld && rank >= 0 && rank < world,
+                "grf_exchange_sum_nvls: world must be 1..%d and rank inside it", kExMaxWorld);
+    GRF_REQUIRE(n_floats >= 0 && n_floats % 4 == 0, "grf_exchange_sum_nvls: U must hold a multiple of 4 floats");
+    GRF_REQUIRE(((uintptr_t)multicast_u & 15u) == 0, "grf_exchange_sum_nvls: U must be 16-byte aligned");
+    GRF_REQUIRE(epoch != 0, "grf_exchange_sum_nvls: epoch 0 is the flags' initial value; start at 1");
+    if (world == 1 || n_floats == 0) return GRF_OK;
+    ExchangeArgs a;
+    for (int g = 0; g < world; ++g) {
+        GRF_REQUIRE(peer_flags[g], "grf_exchange_sum_nvls: null peer flag block");
+        a.u[g] = nullptr;
+        a.flags[g] = peer_flags[g];
+    }
+    a.world = world;
+    a.rank = rank;
+    a.n_vec = n_floats / 4;
+    a.epoch = epoch;
+    exchange_nvls_kernel<<<kExCtas, kExThreads, 0, (cudaStream_t)stream>>>(a, multicast_u);
+    return check_cuda(cudaGetLastError(), "exchange_nvls_kernel launch");
+}
 
 extern "C" int64_t grf_exchange_flag_bytes(int32_t world) {
     return world < 1 ? 0 : (int64_t)2 * kExCtas * world * (int64_t)sizeof(uint32_t);

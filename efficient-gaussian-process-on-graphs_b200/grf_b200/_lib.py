@@ -21,7 +21,7 @@ LOAD_CUMULATIVE, LOAD_LAST_STEP, LOAD_ABLATION = 0, 1, 2
 SCALE_MUL_RECIP, SCALE_DIV = 0, 1
 ORDER_ROW_MAJOR, ORDER_STEP_MAJOR = 0, 1
 ENTRY_STEP_SHIFT = 27  # GRF_ENTRY_STEP_SHIFT
-ABI_VERSION = 7        # GRF_B200_ABI_VERSION
+ABI_VERSION = 8        # GRF_B200_ABI_VERSION
 
 # every symbol include/grf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = (
@@ -30,7 +30,7 @@ EXPORTS = (
     "grf_row_census", "grf_long_rows_build", "grf_nonempty_rows", "grf_transpose_workspace_bytes", "grf_transpose_offsets", "grf_transpose_fill",
     "grf_phi_matvec", "grf_phi_fgrad", "grf_phi_row_dots", "grf_block_windows", "grf_edge_records", "grf_compact_entries", "grf_union_rank", "grf_union_fill",
     "grf_union_materialize", "grf_pairs_count", "grf_pairs_index", "grf_pairs_fill", "grf_pairs_spmm", "grf_pairs_matvec", "grf_cg_num_partials", "grf_cg_dot", "grf_cg_update", "grf_cg_direction",
-    "grf_laplacian_count", "grf_laplacian_fill", "grf_shard_reach", "grf_exchange_flag_bytes", "grf_exchange_sum",
+    "grf_laplacian_count", "grf_laplacian_fill", "grf_shard_reach", "grf_exchange_flag_bytes", "grf_exchange_sum", "grf_exchange_sum_nvls",
 )
 
 
@@ -165,6 +165,8 @@ def lib():
     L.grf_exchange_flag_bytes.argtypes = [i32]
     L.grf_exchange_sum.restype = i32
     L.grf_exchange_sum.argtypes = [POINTER(vp), POINTER(vp), i32, i32, i64, ctypes.c_uint32, vp]
+    L.grf_exchange_sum_nvls.restype = i32
+    L.grf_exchange_sum_nvls.argtypes = [vp, POINTER(vp), i32, i32, i64, ctypes.c_uint32, vp]
     L.grf_block_windows.restype = i32
     L.grf_block_windows.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.grf_phi_fgrad.restype = i32

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GRF_B200_ABI_VERSION 7
+#define GRF_B200_ABI_VERSION 8
 
 enum {
     GRF_OK = 0,
@@ -385,6 +385,11 @@ int grf_phi_row_dots(const GrfPhi *phi, const float *f, const int32_t *x1, const
 int64_t grf_exchange_flag_bytes(int32_t world);
 int grf_exchange_sum(float *const *peer_u, uint32_t *const *peer_flags, int32_t world, int32_t rank,
                      int64_t n_floats, uint32_t epoch, void *stream);
+/* The same sum through the NVSwitch (NVLS): multicast_u = the multicast address of the ranks' U buffers (torch
+ * symmetric memory: handle.multicast_ptr).  The switch adds the copies on load (multimem.ld_reduce) and replicates
+ * the store (multimem.st): 1/G of U crosses this GPU's links each way instead of (G-1)/G.  Flags as above. */
+int grf_exchange_sum_nvls(float *multicast_u, uint32_t *const *peer_flags, int32_t world, int32_t rank,
+                          int64_t n_floats, uint32_t epoch, void *stream);
 
 /* Fused vector kernels of batched CG on (K + sigma2 I) X = B (csrc/grf_cg.cu); replace the
  * elementwise / reduction launches of upstream linear_cg as called at

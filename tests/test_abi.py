@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(so_path):
 
 def test_version_and_pure_host_entry_points(so_path):
     lib = _lib.lib()
-    assert lib.grf_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.grf_abi_version() == _lib.ABI_VERSION == 8
     assert lib.grf_walk_stage_stride(100, 5) == 401
     assert lib.grf_walk_stage_stride(7, 1) == 1
     assert lib.grf_scan_workspace_bytes(0) >= 8
