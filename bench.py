@@ -214,7 +214,9 @@ def run_reference(args):
     n = lap.shape[0]
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(7)
-    per_step = 3000 * cores                        # ~1.2e6 walk-steps per core and step: a few seconds
+    # ~1.2e6 walk-steps per core and step (a dozen seconds) at the default 5 + 3 steps; fewer start nodes per step
+    # when more steps are asked for, so that the whole run stays within a couple of minutes
+    per_step = max(64 * cores, int(3000 * cores * min(1.0, 8.0 / max(1, args.steps + args.warmup))))
     times, visits = [], 0
     for i in range(args.warmup + args.steps):
         starts = np.sort(rng.choice(n, size=min(n, per_step), replace=False))
