@@ -461,6 +461,45 @@ def run_gpu(args):
     results = None
     torch.cuda.empty_cache()
 
+    # ---- L = 3 (the reference's social-graph setting, graph_bo/configs/default_config.yaml:25; SURVEY 8d asks for it
+    # beside the primary L = 5): Phi build and one product, one GPU only, never allowed to break the line
+    l3 = None
+    if world == 1 and not args.no_l3:
+        try:
+            cfg3 = engine.WalkConfig(W, P_HALT, 3, seed=SEED)
+            f3 = torch.randn(3, generator=torch.Generator().manual_seed(42)).to(dev)
+            runs3 = []
+            for i in range(4):
+                a, m, b = ev(), ev(), ev()
+                a.record(stream)
+                phi3 = engine.build_phi_blocks(graph, cfg3)
+                m.record(stream)
+                plan3 = phi3.plan(f3, T_RHS, merged=False)
+                plan3(v, out)
+                b.record(stream)
+                torch.cuda.synchronize(dev)
+                if i > 0:
+                    runs3.append((a.elapsed_time(m), m.elapsed_time(b), int(phi3.visits), int(phi3.nnz)))
+                if i < 3:
+                    del phi3, plan3
+            for _ in range(3):
+                plan3(v, out)
+            a, b = ev(), ev()
+            a.record(stream)
+            for _ in range(10):
+                plan3(v, out)
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            build_ms = sorted(r[0] for r in runs3)[1]
+            l3 = {"max_walk_length": 3, "phi_build_ms": build_ms, "walk_steps": runs3[-1][2], "nnz_phi": runs3[-1][3],
+                  "walk_steps_per_sec_phi_build": runs3[-1][2] / (build_ms * 1e-3), "matvec_ms": a.elapsed_time(b) / 10,
+                  "what": "same graph, W = 100, L = 3: walker + compaction + Phi^T (median of 3), then the per-length "
+                          "product (mean of 10)"}
+            del phi3, plan3
+        except Exception as exc:
+            l3 = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        torch.cuda.empty_cache()
+
     # ---- e2e: the public drop-in call with HOST buffers: GraphPreprocessor(host scipy adjacency) -> operators on
     # the device, then one kernel matvec with V from pinned host memory and the product read back
     e2e = None
@@ -562,6 +601,7 @@ def run_gpu(args):
                 "what": "the product a CG iteration runs: Phi_f on the union pattern (f applied when it is "
                         "materialised, once per modulator value); same algorithmic bytes as the per-length product "
                         "in the numerator (SURVEY 8d counts per-length entries), per GPU in frac"},
+            "config4_L3": l3,
             "e2e": e2e, "config2": cfg2,
             "gpu_launches": None,
             "clocks": clocks, "wall_s_timed_region": t_wall,
@@ -763,6 +803,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config2", action="store_true")
     ap.add_argument("--no-merged", action="store_true", help="skip the union-layout (CG steady state) product")
+    ap.add_argument("--no-l3", action="store_true", help="skip the L = 3 section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
